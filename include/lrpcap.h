@@ -1,0 +1,149 @@
+/* lrpcap -- C ABI of the B200-native LRP engine for attention-LSTM image captioners.
+ *
+ * The reference (SunJiamei/LRP-ImageCaptioning) has no FFI: its boundary is the Python class surface of
+ * models/explainers.py and the iNNvestigate analyzers.  This header is the boundary a binding for that
+ * surface attaches to (ctypes stubs in INTEGRATION.md; the in-tree host layer is
+ * lrp_imagecaptioning_b200/{_lib,explainers,analyzers}.py).  Conventions:
+ *   - every function returns 0 on success or a negative LRPCAP_ERR_* code; the message is in
+ *     lrpcap_last_error() (thread-local).  No exceptions cross this boundary.
+ *   - "d_" pointers are device memory on the current CUDA device, "h_" pointers are host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on that
+ *     stream unless they return host data.
+ *   - tensors are NHWC fp32, channel order as the model sees it (BGR, caffe-mode preprocessing done by the caller).
+ *   - one handle per GPU/stream; distinct handles may be used from distinct threads.
+ */
+#ifndef LRPCAP_H_
+#define LRPCAP_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRPCAP_OK 0
+#define LRPCAP_ERR_INVALID_ARG (-1)
+#define LRPCAP_ERR_SHAPE (-2)
+#define LRPCAP_ERR_CUDA (-3)
+#define LRPCAP_ERR_UNSUPPORTED (-4)
+#define LRPCAP_ERR_STATE (-5)
+
+/* arithmetic of the dense contractions */
+#define LRPCAP_PREC_FP32_SIMT 0 /* fp32 FMA on CUDA cores (exact-fp32 validation mode) */
+#define LRPCAP_PREC_BF16X3_TC 1 /* tcgen05 tensor cores, split-bf16 operands (3 products), fp32 accumulate */
+
+/* encoder rules; replaces the iNNvestigate analyzer classes constructed in
+ * models/explainers.py:32,671,883,928 (LRPSequentialPresetA, Gradient, InputTimesGradient, GuidedBackprop) and
+ * innvestigate/analyzer/relevance_based/relevance_analyzer.py:531-721 */
+#define LRPCAP_RULE_EPSILON 0          /* LRPEpsilon(epsilon, bias) */
+#define LRPCAP_RULE_Z 1                /* LRPZ(bias) */
+#define LRPCAP_RULE_ALPHA_BETA 2       /* LRPAlphaBeta(alpha, beta, bias); Alpha1Beta0, ZPlus, SequentialPresetA */
+#define LRPCAP_RULE_ZPLUS_FAST 3       /* LRPZPlusFast */
+#define LRPCAP_RULE_GRADIENT 4         /* Gradient */
+#define LRPCAP_RULE_INPUT_T_GRADIENT 5 /* InputTimesGradient */
+#define LRPCAP_RULE_GUIDED_BACKPROP 6  /* GuidedBackprop */
+
+#define LRPCAP_DECODER_ADAPTIVE 0 /* ExplainImgCaptioningAdaptiveAttention*, explainers.py:260-949 */
+#define LRPCAP_DECODER_GRIDTD 1   /* ExplainImgCaptioningGridTD*,            explainers.py:995-1653 */
+
+typedef struct lrpcap_encoder lrpcap_encoder_t;
+typedef struct lrpcap_decoder lrpcap_decoder_t;
+
+const char* lrpcap_last_error(void);
+int lrpcap_version(void);
+
+/* ----------------------------------------------------------------------------------------------- encoder
+ * VGG16 input_1 -> block5_conv3 (the `_image_model` of explainers.py:29-30). */
+
+/* h_kernels_hwio[13], h_biases[13]: host fp32, Keras layouts (3,3,Cin,Cout) / (Cout,), layer order
+ * block1_conv1 .. block5_conv3.  image_hw: 224 (any multiple of 16 is accepted). */
+int lrpcap_encoder_create(lrpcap_encoder_t** out, const float* const* h_kernels_hwio, const float* const* h_biases,
+                          int image_hw, int precision);
+int lrpcap_encoder_destroy(lrpcap_encoder_t* enc);
+
+/* Replaces `_image_model.predict(img)` (explainers.py:375, 1097) and the forward half of
+ * `analyzer.analyze([X, R])` (innvestigate/analyzer/base.py:478-520): runs the conv stack once per image and keeps,
+ * per image and layer, the multiplier tensor the chosen rule needs in the backward pass.
+ * d_images: [n_images, hw, hw, 3]. */
+int lrpcap_encoder_forward(lrpcap_encoder_t* enc, const float* d_images, int n_images, int rule, float epsilon,
+                           float alpha, float beta, int bias, void* stream);
+/* d_features: [n_images, hw/16, hw/16, 512] (post-ReLU block5_conv3). */
+int lrpcap_encoder_features(lrpcap_encoder_t* enc, float* d_features, void* stream);
+
+/* Replaces `_explain_CNN(X, relevance_value)` = `analyzer.analyze([X, R])` (explainers.py:179-181) for a whole batch
+ * of words: word w belongs to image h_img_index[w]; d_R_head[w] is the tensor that seeds the backward pass at
+ * block5_conv3's output ('replace' mode, base.py:366-410, graph.py:898-900); d_R_pix[w] is the result at input_1.
+ * d_R_head: [n_words, hw/16, hw/16, 512]; d_R_pix: [n_words, hw, hw, 3]. */
+int lrpcap_encoder_relevance(lrpcap_encoder_t* enc, const int* h_img_index, const float* d_R_head, int n_words,
+                             float* d_R_pix, void* stream);
+/* Host-buffer variant (H2D of R_head and D2H of R_pix inside the call, synchronous). */
+int lrpcap_encoder_relevance_host(lrpcap_encoder_t* enc, const int* h_img_index, const float* h_R_head, int n_words,
+                                  float* h_R_pix, void* stream);
+int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words);
+long long lrpcap_encoder_launches(lrpcap_encoder_t* enc);
+
+/* ----------------------------------------------------------------------------------------------- decoder */
+
+typedef struct lrpcap_decoder_weights {
+  int kind;          /* LRPCAP_DECODER_* */
+  int V, H, E, D;    /* vocabulary, hidden, embedding, CNN feature depth */
+  /* shared heads (explainers.py:264-269,278 / 1000-1006,1016); all host fp32, Keras layouts (in, out) */
+  const float* image_features_w; /* (D, H)  */
+  const float* image_features_b; /* (H)     */
+  const float* global_w;         /* (D, E)  */
+  const float* global_b;         /* (E)     */
+  const float* embedding;        /* (V, E)  */
+  const float* output_w;         /* (H, V)  */
+  const float* output_b;         /* (V)     */
+  /* adaptive attention (explainers.py:270-277): LSTM (2E,4H),(H,4H),(4H); Wv,Wg,Wh,Ws (H,H); Wx (2E,H); V (H,1) */
+  const float *lstm_wi, *lstm_wh, *lstm_b, *Wv, *Wg, *Wx, *Wh, *Ws, *Vatt;
+  /* grid-TD (explainers.py:1007-1019): language LSTM (2H,4H),(H,4H),(4H); top-down LSTM (H+2E,4H),(H,4H),(4H);
+   * W_va,W_ha,W_h,W_s (H,H); W_x (H+2E,H); W_a (H,1) */
+  const float *lang_wi, *lang_wh, *lang_b, *td_wi, *td_wh, *td_b, *W_va, *W_ha, *W_a, *W_x, *W_h, *W_s;
+} lrpcap_decoder_weights_t;
+
+/* keras_logits != 0: grid-TD logits = (h2 + c_hat) W_o + b as in the Keras model (models/model.py:816);
+ * 0 (default): h2 W_o + b as in the reference explainer (explainers.py:1154). */
+int lrpcap_decoder_create(lrpcap_decoder_t** out, const lrpcap_decoder_weights_t* w, int sos_token, int keras_logits);
+int lrpcap_decoder_destroy(lrpcap_decoder_t* dec);
+
+/* Replaces `_forward_beam_search(X, caption)` (explainers.py:370-436, 690-778, 1092-1178, 1344-1450) for a batch:
+ * teacher-forced decoder forward over T steps storing every intermediate the relevance pass reads.
+ * d_features: [n_images, L, D]; h_captions: [n_images, T] tokenizer ids (model index = id - 1).
+ * greedy != 0: h_captions is an OUTPUT -- token t is the arg-max of step t's logits (EOS never suppressed here;
+ * pass eos_token < 0 to disable; when >= 0 that id is excluded from the arg-max so every caption has T words). */
+int lrpcap_decoder_forward(lrpcap_decoder_t* dec, const float* d_features, int n_images, int L, int* h_captions, int T,
+                           int greedy, int eos_token, void* stream);
+
+/* Replaces `_explain_lstm_single_word_sequence(t)` (explainers.py:537-666, 1180-1321) for a batch of words:
+ * word w = (image h_word_img[w], 1-based position h_word_t[w]).
+ * d_R_head: [n_words, L, D] fp32 relevance of the CNN grid features.
+ * h_r_words: optional [n_words, T] (adaptive: normalised, entry j = reference r_words[j] for j < t-1, rest 0;
+ * grid-TD: raw, entries j < t).  h_attention: optional [n_words, L] = attention[t]. */
+int lrpcap_decoder_relevance(lrpcap_decoder_t* dec, const int* h_word_img, const int* h_word_t, int n_words,
+                             float* d_R_head, double* h_r_words, float* h_attention, void* stream);
+/* Replaces `_lstm_decoder_backward(t)` (explainers.py:780-832, 1452-1532): manual BPTT with frozen attention. */
+int lrpcap_decoder_backward(lrpcap_decoder_t* dec, const int* h_word_img, const int* h_word_t, int n_words,
+                            float* d_R_head, double* h_r_words, void* stream);
+/* h_logit: [n_images, T] logit of the caption token at each step (fp64). */
+int lrpcap_decoder_caption_logits(lrpcap_decoder_t* dec, double* h_logit);
+long long lrpcap_decoder_launches(lrpcap_decoder_t* dec);
+
+/* ----------------------------------------------------------------------------------------------- whole path
+ * One call per batch, host buffers in and out (the end-to-end entry the benchmark times):
+ *   images -> encoder forward -> decoder forward (teacher-forced or greedy) -> decoder relevance for every
+ *   (image, t = 1..T) word -> encoder relevance -> pixel maps.
+ * h_images [n, hw, hw, 3]; h_captions [n, T] (in, or out when greedy); h_R_pix [n*T, hw, hw, 3], word (i, t) at
+ * row i*T + (t-1).  method: 0 = LRP (decoder relevance), 1 = gradient family (decoder backward). */
+int lrpcap_explain_batch_host(lrpcap_encoder_t* enc, lrpcap_decoder_t* dec, const float* h_images, int n_images,
+                              int* h_captions, int T, int greedy, int eos_token, int method, int rule, float epsilon,
+                              float alpha, float beta, int bias, float* h_R_pix, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- debug / tests
+ * Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
+ * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */
+int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
+                      int Nout, float* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRPCAP_H_ */

@@ -1,0 +1,156 @@
+// extern "C" surface declared in include/lrpcap.h: error plumbing, encoder entry points, debug conv.
+#include "../../include/lrpcap.h"
+#include "encoder.cuh"
+#include "encoder_kernels.cuh"
+#include "tc_conv.cuh"
+#include <vector>
+
+namespace lrpcap {
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+}  // namespace lrpcap
+
+using namespace lrpcap;
+
+struct lrpcap_encoder {
+  Encoder* impl;
+};
+
+extern "C" {
+
+const char* lrpcap_last_error(void) { return get_last_error(); }
+int lrpcap_version(void) { return 100; }
+
+int lrpcap_encoder_create(lrpcap_encoder_t** out, const float* const* h_kernels_hwio, const float* const* h_biases,
+                          int image_hw, int precision) {
+  LRPCAP_REQUIRE(out != nullptr, kErrInvalidArg, "encoder_create: null out");
+  Encoder* e = nullptr;
+  LRPCAP_TRY(Encoder::create(&e, h_kernels_hwio, h_biases, image_hw, precision));
+  *out = new lrpcap_encoder{e};
+  return kOk;
+}
+
+int lrpcap_encoder_destroy(lrpcap_encoder_t* enc) {
+  if (!enc) return kOk;
+  delete enc->impl;
+  delete enc;
+  return kOk;
+}
+
+int lrpcap_encoder_forward(lrpcap_encoder_t* enc, const float* d_images, int n_images, int rule, float epsilon,
+                           float alpha, float beta, int bias, void* stream) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_forward: null handle");
+  EncoderRule r;
+  r.kind = rule;
+  r.epsilon = epsilon;
+  r.alpha = alpha;
+  r.beta = beta;
+  r.bias = bias;
+  return enc->impl->forward(d_images, n_images, r, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int lrpcap_encoder_features(lrpcap_encoder_t* enc, float* d_features, void* stream) {
+  LRPCAP_REQUIRE(enc && enc->impl && d_features, kErrInvalidArg, "encoder_features: null argument");
+  Encoder* e = enc->impl;
+  LRPCAP_REQUIRE(e->n_images() > 0, kErrState, "encoder_features: call encoder_forward first");
+  const size_t n = (size_t)e->n_images() * e->feature_hw() * e->feature_hw() * 512;
+  LRPCAP_CUDA(cudaMemcpyAsync(d_features, e->features(), n * sizeof(float), cudaMemcpyDeviceToDevice,
+                              reinterpret_cast<cudaStream_t>(stream)));
+  return kOk;
+}
+
+int lrpcap_encoder_relevance(lrpcap_encoder_t* enc, const int* h_img_index, const float* d_R_head, int n_words,
+                             float* d_R_pix, void* stream) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_relevance: null handle");
+  return enc->impl->relevance(h_img_index, d_R_head, n_words, d_R_pix, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int lrpcap_encoder_relevance_host(lrpcap_encoder_t* enc, const int* h_img_index, const float* h_R_head, int n_words,
+                                  float* h_R_pix, void* stream) {
+  LRPCAP_REQUIRE(enc && enc->impl && h_R_head && h_R_pix && n_words > 0, kErrInvalidArg,
+                 "encoder_relevance_host: bad argument");
+  Encoder* e = enc->impl;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t head = (size_t)n_words * e->feature_hw() * e->feature_hw() * 512;
+  const size_t pix = (size_t)n_words * e->image_hw() * e->image_hw() * 3;
+  DevBuf dR, dP;
+  int st = dR.ensure(head * sizeof(float));
+  if (st == kOk) st = dP.ensure(pix * sizeof(float));
+  if (st == kOk && cudaMemcpyAsync(dR.p, h_R_head, head * sizeof(float), cudaMemcpyHostToDevice, s) != cudaSuccess) {
+    set_last_error("encoder_relevance_host: H2D copy failed");
+    st = kErrCuda;
+  }
+  if (st == kOk) st = e->relevance(h_img_index, dR.as<float>(), n_words, dP.as<float>(), s);
+  if (st == kOk && cudaMemcpyAsync(h_R_pix, dP.p, pix * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
+    set_last_error("encoder_relevance_host: D2H copy failed");
+    st = kErrCuda;
+  }
+  if (st == kOk) {
+    cudaError_t err = cudaStreamSynchronize(s);
+    if (err != cudaSuccess) {
+      set_last_error("encoder_relevance_host: %s", cudaGetErrorString(err));
+      st = kErrCuda;
+    }
+  }
+  dR.release();
+  dP.release();
+  return st;
+}
+
+int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words) {
+  LRPCAP_REQUIRE(enc && enc->impl && chunk_words > 0, kErrInvalidArg, "encoder_set_chunk_words: bad argument");
+  enc->impl->set_chunk_words(chunk_words);
+  return kOk;
+}
+
+long long lrpcap_encoder_launches(lrpcap_encoder_t* enc) { return (enc && enc->impl) ? enc->impl->launches() : 0; }
+
+int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
+                      int Nout, float* h_out) {
+  LRPCAP_REQUIRE(h_A && h_B && h_out, kErrInvalidArg, "debug_conv: null argument");
+  LRPCAP_REQUIRE(items > 0 && H > 0 && W > 0 && C > 0 && Nout > 0 && (taps == 1 || taps == 9), kErrShape,
+                 "debug_conv: bad shape");
+  const size_t nA = (size_t)items * H * W * C, nB = (size_t)taps * C * Nout, nO = (size_t)items * H * W * Nout;
+  DevBuf dA, dB, dO, sA, sB;
+  int st = kOk;
+  auto run = [&]() -> int {
+    LRPCAP_TRY(dA.ensure(nA * 4));
+    LRPCAP_TRY(dB.ensure(nB * 4));
+    LRPCAP_TRY(dO.ensure(nO * 4));
+    LRPCAP_CUDA(cudaMemcpy(dA.p, h_A, nA * 4, cudaMemcpyHostToDevice));
+    LRPCAP_CUDA(cudaMemcpy(dB.p, h_B, nB * 4, cudaMemcpyHostToDevice));
+    LRPCAP_CUDA(cudaMemset(dO.p, 0xff, nO * 4));   // NaN-fill: untouched outputs must show up
+    EpiParams ep;
+    ep.mode = EPI_RAW;
+    ep.out_f32 = dO.as<float>();
+    if (precision == PREC_BF16X3_TC) {
+      LRPCAP_TRY(sA.ensure(nA * 4));
+      LRPCAP_TRY(sB.ensure(nB * 4));
+      LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0));
+      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps));
+      TcConvArgs a;
+      a.A = sA.p; a.A_elems = nA; a.n_items = items; a.H = H; a.W = W; a.C = C;
+      a.B = sB.p; a.B_elems = nB; a.taps = taps; a.Nout = Nout; a.epi = ep;
+      LRPCAP_TRY(tc_conv_launch(a, 0));
+    } else {
+      SimtConvArgs a;
+      a.A = dA.as<float>(); a.n_items = items; a.H = H; a.W = W; a.C = C;
+      a.B = dB.as<float>(); a.taps = taps; a.Nout = Nout; a.split_out = false; a.epi = ep;
+      LRPCAP_TRY(simt_conv_launch(a, 0));
+    }
+    LRPCAP_CUDA(cudaDeviceSynchronize());
+    LRPCAP_CUDA(cudaMemcpy(h_out, dO.p, nO * 4, cudaMemcpyDeviceToHost));
+    return kOk;
+  };
+  st = run();
+  dA.release(); dB.release(); dO.release(); sA.release(); sB.release();
+  return st;
+}
+
+}  // extern "C"

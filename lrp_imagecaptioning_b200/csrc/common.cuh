@@ -1,0 +1,92 @@
+// Shared helpers for the lrpcap CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+
+namespace lrpcap {
+
+// ---- status codes returned across the C ABI (include/lrpcap.h) ----
+enum : int {
+  kOk = 0,
+  kErrInvalidArg = -1,
+  kErrShape = -2,
+  kErrCuda = -3,
+  kErrUnsupported = -4,
+  kErrState = -5,
+};
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+#define LRPCAP_CUDA(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::lrpcap::set_last_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,          \
+                               cudaGetErrorString(_e));                                    \
+      return ::lrpcap::kErrCuda;                                                           \
+    }                                                                                      \
+  } while (0)
+
+#define LRPCAP_TRY(expr)                  \
+  do {                                    \
+    int _s = (expr);                      \
+    if (_s != ::lrpcap::kOk) return _s;   \
+  } while (0)
+
+#define LRPCAP_REQUIRE(cond, code, ...)          \
+  do {                                           \
+    if (!(cond)) {                               \
+      ::lrpcap::set_last_error(__VA_ARGS__);     \
+      return (code);                             \
+    }                                            \
+  } while (0)
+
+// ---- split-bf16 storage: a float tensor of n elements is kept as two bf16 planes,
+//      hi[n] followed by lo[n], with v ~= float(hi) + float(lo) (16 mantissa bits).
+//      Same 4 bytes/element as fp32; both planes are tcgen05 kind::f16 operands. ----
+struct SplitPtr {
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+};
+__host__ __device__ inline SplitPtr split_ptr(void* base, size_t n_elems) {
+  SplitPtr p;
+  p.hi = reinterpret_cast<__nv_bfloat16*>(base);
+  p.lo = p.hi + n_elems;
+  return p;
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float join_bf16(__nv_bfloat16 hi, __nv_bfloat16 lo) {
+  return __bfloat162float(hi) + __bfloat162float(lo);
+}
+
+// pack two floats' hi parts / lo parts into 32-bit words (element 0 in the low half)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  __nv_bfloat16 ah, al, bh, bl;
+  split_bf16(a, ah, al);
+  split_bf16(b, bh, bl);
+  hi2 = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo2 = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+}
+
+__device__ __forceinline__ float bf16lo_to_float(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_float(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// ---- rule arithmetic shared by every kernel ----
+// epsilon rule: z + sgn+(z)*eps, sgn+(0) = +1   (relevance_rule.py:131)
+__device__ __forceinline__ float stab_eps(float z, float eps) { return z + (z >= 0.f ? eps : -eps); }
+// SafeDivide denominator: z + [z==0]*1e-7      (layers.py:456-458)
+__device__ __forceinline__ float safe_den(float z) { return z + (z == 0.f ? 1e-7f : 0.f); }
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace lrpcap

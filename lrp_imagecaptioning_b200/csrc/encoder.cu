@@ -1,0 +1,285 @@
+// Encoder: per-image forward state and batched per-word relevance backward (see encoder.cuh).
+#include "encoder.cuh"
+#include "encoder_kernels.cuh"
+#include "tc_conv.cuh"
+
+namespace lrpcap {
+
+int DevBuf::ensure(size_t n) {
+  if (n <= bytes) return kOk;
+  release();
+  LRPCAP_CUDA(cudaMalloc(&p, n));
+  bytes = n;
+  return kOk;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+namespace {
+const int kCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
+const int kCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+const int kShift[13] = {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
+const bool kPool[13] = {false, true, false, true, false, false, true, false, false, true, false, false, false};
+constexpr int kForwardChunk = 8;
+}  // namespace
+
+Encoder::~Encoder() {
+  for (auto& l : L_) {
+    if (l.w_hwio) cudaFree(l.w_hwio);
+    if (l.bias) cudaFree(l.bias);
+    for (auto& f : l.prepared)
+      for (auto& p : f)
+        if (p) cudaFree(p);
+  }
+  if (w0_pm_) cudaFree(w0_pm_);
+  X0_.release(); F_.release(); Mseed_.release(); posneg_.release(); idx_.release();
+  for (auto& g : G_) g.release();
+  for (auto& a : act_) a.release();
+  for (auto& m : msg_) m.release();
+}
+
+int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float* const* biases, int image_hw,
+                    int precision) {
+  LRPCAP_REQUIRE(out && kernels_hwio && biases, kErrInvalidArg, "encoder_create: null argument");
+  LRPCAP_REQUIRE(image_hw >= 16 && image_hw % 16 == 0, kErrShape, "encoder_create: image size %d must be a multiple of 16", image_hw);
+  LRPCAP_REQUIRE(precision == PREC_FP32_SIMT || precision == PREC_BF16X3_TC, kErrInvalidArg, "encoder_create: unknown precision %d", precision);
+  Encoder* e = new Encoder();
+  e->hw_ = image_hw;
+  e->precision_ = precision;
+  for (int l = 0; l < kLayers; ++l) {
+    Layer& L = e->L_[l];
+    L.cin = kCin[l];
+    L.cout = kCout[l];
+    L.hw = image_hw >> kShift[l];
+    L.pool_after = kPool[l];
+    const size_t nw = (size_t)9 * L.cin * L.cout;
+    if (!kernels_hwio[l] || !biases[l]) {
+      delete e;
+      set_last_error("encoder_create: layer %d weights missing", l);
+      return kErrInvalidArg;
+    }
+    cudaError_t err = cudaMalloc(&L.w_hwio, nw * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&L.bias, L.cout * sizeof(float));
+    if (err == cudaSuccess) err = cudaMemcpy(L.w_hwio, kernels_hwio[l], nw * sizeof(float), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(L.bias, biases[l], L.cout * sizeof(float), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+      delete e;
+      set_last_error("encoder_create: device allocation/copy failed: %s", cudaGetErrorString(err));
+      return kErrCuda;
+    }
+  }
+  e->w0_host_.assign(kernels_hwio[0], kernels_hwio[0] + 9 * 3 * 64);
+  *out = e;
+  return kOk;
+}
+
+int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
+  Layer& L = L_[l];
+  if (!L.prepared[fmt][sign]) {
+    void* p = nullptr;
+    LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * sizeof(float)));
+    L.prepared[fmt][sign] = p;
+    LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, fmt, sign, s));
+    ++launches_;
+  }
+  *out = L.prepared[fmt][sign];
+  return kOk;
+}
+
+int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const EpiParams& epi,
+                  cudaStream_t s) {
+  const Layer& L = L_[l];
+  const int C = backward ? L.cout : L.cin;
+  const int Nout = backward ? L.cin : L.cout;
+  void* B = nullptr;
+  ++launches_;
+  if (split() && C % 64 == 0 && Nout % 64 == 0) {
+    LRPCAP_TRY(get_weights(l, backward ? WF_TC_BWD : WF_TC_FWD, sign, &B, s));
+    TcConvArgs a;
+    a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
+    a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout; a.taps = 9; a.Nout = Nout;
+    a.epi = epi;
+    return tc_conv_launch(a, s);
+  }
+  LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
+  LRPCAP_TRY(get_weights(l, backward ? WF_SIMT_BWD : WF_SIMT_FWD, sign, &B, s));
+  SimtConvArgs a;
+  a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
+  a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout; a.split_out = split();
+  a.epi = epi;
+  return simt_conv_launch(a, s);
+}
+
+int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cudaStream_t s) {
+  LRPCAP_REQUIRE(d_images && n > 0, kErrInvalidArg, "encoder_forward: no images");
+  switch (rule.kind) {
+    case RULE_EPSILON:
+      LRPCAP_REQUIRE(rule.epsilon > 0.f, kErrInvalidArg, "encoder_forward: epsilon must be > 0");
+      break;
+    case RULE_ALPHA_BETA:
+      LRPCAP_REQUIRE(rule.alpha >= 1.f && rule.beta >= 0.f && fabsf(rule.alpha - rule.beta - 1.f) < 1e-6f,
+                     kErrInvalidArg, "encoder_forward: need alpha >= 1, beta >= 0, alpha - beta = 1");
+      LRPCAP_REQUIRE(rule.beta == 0.f, kErrUnsupported,
+                     "encoder_forward: alpha-beta with beta != 0 (inhibitor branch) is not built yet");
+      break;
+    case RULE_Z: case RULE_ZPLUS_FAST: case RULE_GRADIENT: case RULE_INPUT_T_GRADIENT: case RULE_GUIDED_BACKPROP:
+      break;
+    default:
+      set_last_error("encoder_forward: unknown rule %d", rule.kind);
+      return kErrInvalidArg;
+  }
+  n_images_ = 0;
+  rule_ = rule;
+  const size_t img_elems = (size_t)hw_ * hw_ * 3;
+  LRPCAP_TRY(X0_.ensure((size_t)n * img_elems * sizeof(float)));
+  LRPCAP_CUDA(cudaMemcpyAsync(X0_.p, d_images, (size_t)n * img_elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  for (int l = 0; l < kLayers - 1; ++l) LRPCAP_TRY(G_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
+  LRPCAP_TRY(Mseed_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
+  LRPCAP_TRY(F_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
+  const int FC = n < kForwardChunk ? n : kForwardChunk;
+  const size_t act_bytes = (size_t)FC * hw_ * hw_ * 64 * sizeof(float);
+  for (auto& a : act_) LRPCAP_TRY(a.ensure(act_bytes));
+
+  const bool ab = rule.kind == RULE_ALPHA_BETA, zpf = rule.kind == RULE_ZPLUS_FAST;
+  int gmode = G_MASK;
+  if (rule.kind == RULE_EPSILON) gmode = G_EPS;
+  else if (rule.kind == RULE_Z) gmode = G_Z;
+  else if (ab || zpf) gmode = G_NONE;
+
+  if (ab && !w0_pm_) {   // [W+ ; W-] stacked along the input-channel axis for the [x+, x-] first-layer input
+    std::vector<float> pm((size_t)9 * 6 * 64);
+    for (int tap = 0; tap < 9; ++tap)
+      for (int ci = 0; ci < 3; ++ci)
+        for (int co = 0; co < 64; ++co) {
+          const float w = w0_host_[((size_t)tap * 3 + ci) * 64 + co];
+          pm[((size_t)tap * 6 + ci) * 64 + co] = w >= 0.f ? w : 0.f;
+          pm[((size_t)tap * 6 + 3 + ci) * 64 + co] = w < 0.f ? w : 0.f;
+        }
+    LRPCAP_CUDA(cudaMalloc(&w0_pm_, pm.size() * sizeof(float)));
+    LRPCAP_CUDA(cudaMemcpy(w0_pm_, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+
+  for (int i0 = 0; i0 < n; i0 += FC) {
+    const int m = (n - i0) < FC ? (n - i0) : FC;
+    const float* img = X0_.as<float>() + (size_t)i0 * img_elems;
+    const void* X = img;
+    size_t X_elems = (size_t)m * img_elems;
+    int bx = -1;  // act_ buffer currently holding X (-1: the image)
+    for (int l = 0; l < kLayers; ++l) {
+      const Layer& L = L_[l];
+      const size_t oe = layer_out_elems(l);
+      int by = 0;
+      while (by == bx) ++by;
+      void* Y = act_[by].p;
+      float* Gl = (l < kLayers - 1) ? G_[l].as<float>() + (size_t)i0 * oe : nullptr;
+      float* Ml = (l == kLayers - 1) ? Mseed_.as<float>() + (size_t)i0 * oe : nullptr;
+
+      EpiParams ep;
+      ep.mode = EPI_FWD_TRUE;
+      ep.bias = L.bias;
+      ep.out_act = Y;
+      ep.out_act_elems = (size_t)m * oe;
+      ep.out_f32 = (l == kLayers - 1) ? F_.as<float>() + (size_t)i0 * oe : nullptr;
+      ep.gmode = gmode;
+      ep.eps = rule.epsilon;
+      ep.rule_bias = rule.bias;
+      if (gmode != G_NONE) { ep.G = Gl; ep.Mseed = Ml; }
+      LRPCAP_TRY(conv(l, false, WS_ALL, X, X_elems, m, ep, s));
+
+      if (ab || zpf) {
+        EpiParams ez;
+        ez.mode = EPI_FWD_ZACT;
+        ez.bias = L.bias;
+        ez.rule_bias = ab ? rule.bias : 0;
+        ez.x_act = Y;
+        ez.x_act_elems = (size_t)m * oe;
+        ez.G = Gl;
+        ez.Mseed = Ml;
+        if (l == 0 && ab) {
+          LRPCAP_TRY(posneg_.ensure((size_t)m * hw_ * hw_ * 6 * sizeof(float)));
+          LRPCAP_TRY(make_posneg(img, posneg_.as<float>(), (size_t)m * hw_ * hw_, s));
+          SimtConvArgs a;
+          a.A = posneg_.as<float>(); a.n_items = m; a.H = hw_; a.W = hw_; a.C = 6;
+          a.B = w0_pm_; a.taps = 9; a.Nout = 64; a.split_out = split();
+          a.epi = ez;
+          LRPCAP_TRY(simt_conv_launch(a, s));
+          launches_ += 2;
+        } else {
+          LRPCAP_TRY(conv(l, false, WS_PLUS, X, X_elems, m, ez, s));
+        }
+      }
+
+      if (L.pool_after) {
+        int bp = 0;
+        while (bp == bx || bp == by) ++bp;
+        LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, split(), act_[bp].p, (size_t)m * oe / 4, Gl, m, L.hw, L.hw, L.cout, s));
+        ++launches_;
+        X = act_[bp].p;
+        X_elems = (size_t)m * oe / 4;
+        bx = bp;
+      } else {
+        X = Y;
+        X_elems = (size_t)m * oe;
+        bx = by;
+      }
+    }
+  }
+  n_images_ = n;
+  return kOk;
+}
+
+int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s) {
+  LRPCAP_REQUIRE(n_images_ > 0, kErrState, "encoder_relevance: call encoder_forward first");
+  LRPCAP_REQUIRE(h_img_index && d_R_head && d_R_pix && n_words > 0, kErrInvalidArg, "encoder_relevance: bad argument");
+  for (int w = 0; w < n_words; ++w)
+    LRPCAP_REQUIRE(h_img_index[w] >= 0 && h_img_index[w] < n_images_, kErrInvalidArg,
+                   "encoder_relevance: img_index[%d]=%d out of range [0,%d)", w, h_img_index[w], n_images_);
+  LRPCAP_TRY(idx_.ensure((size_t)n_words * sizeof(int)));
+  LRPCAP_CUDA(cudaMemcpyAsync(idx_.p, h_img_index, (size_t)n_words * sizeof(int), cudaMemcpyHostToDevice, s));
+  const int CW = n_words < chunk_words_ ? n_words : chunk_words_;
+  const size_t msg_bytes = (size_t)CW * hw_ * hw_ * 64 * sizeof(float);
+  for (auto& m : msg_) LRPCAP_TRY(m.ensure(msg_bytes));
+
+  const bool ab = rule_.kind == RULE_ALPHA_BETA, zpf = rule_.kind == RULE_ZPLUS_FAST;
+  const bool guided = rule_.kind == RULE_GUIDED_BACKPROP;
+  const int sign = (ab || zpf) ? WS_PLUS : WS_ALL;
+  const int mult = (rule_.kind == RULE_GRADIENT || guided) ? 0 : 1;
+  const int fh = hw_ / 16;
+  const size_t head_elems = layer_out_elems(12);
+  const size_t pix_elems = (size_t)hw_ * hw_ * 3;
+
+  void *Wa = nullptr, *Wb = nullptr;
+  LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, sign, &Wa, s));
+  if (ab) LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, WS_MINUS, &Wb, s));
+
+  for (int w0 = 0; w0 < n_words; w0 += CW) {
+    const int m = (n_words - w0) < CW ? (n_words - w0) : CW;
+    const int* idx = idx_.as<int>() + w0;
+    int cur = 0;
+    LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), idx, msg_[cur].p, (size_t)m * head_elems,
+                            split(), m, fh * fh, 512, guided ? 1 : 0, s));
+    ++launches_;
+    for (int l = kLayers - 1; l >= 1; --l) {
+      EpiParams ep;
+      ep.mode = EPI_BWD;
+      ep.img_index = idx;
+      ep.Gin = G_[l - 1].as<float>();
+      ep.up = L_[l - 1].pool_after ? 2 : 1;
+      ep.relu_acc = guided ? 1 : 0;
+      ep.out_msg = msg_[cur ^ 1].p;
+      ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1);
+      LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l), m, ep, s));
+      cur ^= 1;
+    }
+    LRPCAP_TRY(last_dgrad(msg_[cur].p, (size_t)m * layer_out_elems(0), split(), reinterpret_cast<const float*>(Wa),
+                          reinterpret_cast<const float*>(Wb), X0_.as<float>(), idx, d_R_pix + (size_t)w0 * pix_elems, m,
+                          hw_, hw_, 64, mult, s));
+    ++launches_;
+  }
+  return kOk;
+}
+
+}  // namespace lrpcap

@@ -1,0 +1,88 @@
+// VGG16 (input_1 -> block5_conv3) forward state + batched relevance / gradient backward to pixels.
+//
+// What the reference does per *word* with one TF session run (analyzer.analyze([img, R]),
+// innvestigate/analyzer/base.py:478-520 -> reverse graph built by utils/keras/graph.py:704-942):
+// VGG16 forward + per conv layer {forward conv(s), stabilised divide, transposed conv, multiply}.
+//
+// Here the per-image work is done once (forward(): activations, and per layer one fp32 multiplier tensor
+//   G_l = x_l / stab(z_l)   [eps, z rules]     G_l = x_l / safe(z+_l)   [alpha-beta family]     G_l = [z_l > 0]   [gradients]
+// with the max-pool arg-max routing folded in as zeros), and the per-word work is a chain of 12 fused
+// "transposed conv -> multiply by G" launches over all words at once plus a seed and a 64->3 tail:
+//   s_12 = R * M            s_{l-1} = G'_{l-1} * (W_l^T (*) s_l)            R_pix = x_0 * (W_0^T (*) s_0)
+// which is algebraically the rule chain of relevance_rule.py (R_in = x * c, s = R_in / stab(z) => s = c * x/stab(z)).
+#pragma once
+#include <vector>
+#include "common.cuh"
+
+namespace lrpcap {
+
+enum Precision : int { PREC_FP32_SIMT = 0, PREC_BF16X3_TC = 1 };
+
+enum RuleKind : int {
+  RULE_EPSILON = 0,       // LRPEpsilon            (relevance_analyzer.py:531-552)
+  RULE_Z = 1,             // LRPZ
+  RULE_ALPHA_BETA = 2,    // LRPAlphaBeta / Alpha1Beta0 / Alpha2Beta1 / ZPlus / SequentialPresetA conv rule
+  RULE_ZPLUS_FAST = 3,    // LRPZPlusFast
+  RULE_GRADIENT = 4,      // Gradient
+  RULE_INPUT_T_GRADIENT = 5,
+  RULE_GUIDED_BACKPROP = 6,
+};
+
+struct EncoderRule {
+  int kind = RULE_EPSILON;
+  float epsilon = 1e-7f;
+  float alpha = 1.f, beta = 0.f;
+  int bias = 1;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t n);   // grows (never shrinks); contents undefined after growth
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+class Encoder {
+ public:
+  static constexpr int kLayers = 13;
+  ~Encoder();
+  static int create(Encoder** out, const float* const* kernels_hwio, const float* const* biases, int image_hw,
+                    int precision);
+  // images: device fp32 [n, hw, hw, 3] (already preprocessed). Builds features + per-image rule state.
+  int forward(const float* d_images, int n_images, const EncoderRule& rule, cudaStream_t s);
+  const float* features() const { return F_.as<float>(); }   // device fp32 [n, hw/16, hw/16, 512]
+  int feature_hw() const { return hw_ / 16; }
+  int n_images() const { return n_images_; }
+  int image_hw() const { return hw_; }
+  // h_img_index[w] -> image of word w; d_R_head fp32 [n_words, fh, fh, 512]; d_R_pix fp32 [n_words, hw, hw, 3].
+  int relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s);
+  void set_chunk_words(int n) { chunk_words_ = n > 0 ? n : 1; }
+  // kernels launched by this object since construction (bench.py's gpu_launches)
+  long long launches() const { return launches_; }
+
+ private:
+  struct Layer {
+    int cin, cout, hw;        // hw: spatial size of the conv's input == output
+    bool pool_after;
+    float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
+    float* bias = nullptr;    // device fp32 [cout]
+    void* prepared[4][3] = {};  // [WeightFormat][WeightSign]
+  };
+  int get_weights(int l, int fmt, int sign, void** out, cudaStream_t s);
+  int conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const struct EpiParams& epi,
+           cudaStream_t s);
+  bool split() const { return precision_ == PREC_BF16X3_TC; }
+  size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
+
+  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256;
+  long long launches_ = 0;
+  EncoderRule rule_;
+  Layer L_[kLayers];
+  std::vector<float> w0_host_;       // first-layer kernel (host copy) for the signed-input alpha-beta path
+  float* w0_pm_ = nullptr;           // device fp32 [9][6][64]: [W+ ; W-] stacked for the [x+, x-] input
+  DevBuf X0_, F_, Mseed_, G_[kLayers - 1];
+  DevBuf act_[3], posneg_, msg_[2], idx_;
+};
+
+}  // namespace lrpcap

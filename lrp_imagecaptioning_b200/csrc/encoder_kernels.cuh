@@ -1,0 +1,41 @@
+// HBM-bound helper kernels of the encoder relevance path (first/last layer).
+#pragma once
+#include "common.cuh"
+
+namespace lrpcap {
+
+enum WeightFormat : int {
+  WF_SIMT_FWD = 0,  // fp32 [tap][cin][cout]                 (= HWIO)
+  WF_SIMT_BWD = 1,  // fp32 [tap'][cout][cin], tap' = flipped (transposed conv)
+  WF_TC_FWD = 2,    // split-bf16 [tap][cout][cin]           (K-major B operand of the forward GEMM)
+  WF_TC_BWD = 3,    // split-bf16 [tap'][cin][cout]          (K-major B operand of the dgrad GEMM)
+};
+enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
+
+// w_hwio: device fp32 [3,3,cin,cout]. out: 9*cin*cout elements in `fmt`.
+int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps = 9);
+
+// 2x2/2 max-pool of `act` [items,H,W,C] (storage-typed). If `pooled` != null writes [items,H/2,W/2,C];
+// if `G` != null zeroes every G entry that is not the first maximum of its window (TF MaxPoolGrad routing,
+// innvestigate relevance_analyzer.py:459-480).
+int pool_mask(const void* act, size_t act_elems, bool split, void* pooled, size_t pooled_elems, float* G, int items,
+              int H, int W, int C, cudaStream_t s);
+
+// msg[item] = (relu?)(R[item]) * M[img_index[item]]   ([items, hw, hw, C]); msg storage-typed.
+int seed_message(const float* R, const float* M, const int* img_index, void* msg, size_t msg_elems, bool split,
+                 int items, int pix, int C, int relu, cudaStream_t s);
+
+// Last transposed conv (64 -> 3 channels) + input re-weighting:
+//   c_a = Wa^T (*) s,  c_b = Wb^T (*) s (only if Wb != null)
+//   out = mult ? (x >= 0 ? x * c_a : x * c_b) : c_a            x = image[img_index[item]]
+// Wa/Wb: fp32 [tap'][C][3] (WF_SIMT_BWD of the first layer).
+int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, const float* Wb, const float* images,
+               const int* img_index, float* out, int items, int H, int W, int C, int mult, cudaStream_t s);
+
+// [x] (3 ch) -> [x+, x-] (6 ch), fp32 NHWC.
+int make_posneg(const float* x, float* out, size_t pixels, cudaStream_t s);
+
+int f32_to_split(const float* in, void* out, size_t n, cudaStream_t s);
+int split_to_f32(const void* in, float* out, size_t n, cudaStream_t s);
+
+}  // namespace lrpcap

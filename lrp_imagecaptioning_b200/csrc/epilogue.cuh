@@ -1,0 +1,211 @@
+// Fused rule arithmetic applied to a run of NV consecutive output channels of one pixel.
+// Shared by the tcgen05 kernel (NV = 16, split-bf16 storage) and the fp32 SIMT kernel (NV = 4, fp32 storage),
+// so both precisions implement exactly the same rules:
+//   EpsilonRule / ZRule          innvestigate/analyzer/relevance_based/relevance_rule.py:74-144
+//   AlphaBetaRule (z+ forward)   relevance_rule.py:216-322
+//   max-pool routing             relevance_analyzer.py:459-480 (fused as a 2x2 up-sampling store with a
+//                                pre-masked per-image multiplier)
+//   Gradient / GuidedBackprop    analyzer/gradient_based.py:101-172, 228-265
+#pragma once
+#include "tc_conv.cuh"
+
+namespace lrpcap {
+
+struct EpiDev {
+  const float* bias;
+  void* out;          // activation (forward) or message (backward) tensor, storage-typed
+  size_t out_elems;
+  float* out_f32;
+  float* G;
+  float* Mseed;
+  int gmode;
+  int rule_bias;      // 0: the rule's z excludes the bias (IgnoreBias variants); the true forward always adds it
+  float eps;
+  const void* x_act;  // FWD_ZACT: true activation, storage-typed
+  size_t x_elems;
+  const int* img_index;
+  const float* Gin;
+  int up;
+  int relu_acc;
+};
+
+// ---- storage policies ----
+struct StoreSplit {
+  template <int NV>
+  static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "split storage moves 4 or 8 elements per vector");
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base);
+    __nv_bfloat16* lo = hi + elems;
+    if constexpr (NV % 8 == 0) {
+#pragma unroll
+      for (int j = 0; j < NV / 8; ++j) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1], h[i], l[i]);
+        reinterpret_cast<uint4*>(hi + off)[j] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(lo + off)[j] = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV / 4; ++j) {
+        uint32_t h[2], l[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) split2(v[4 * j + 2 * i], v[4 * j + 2 * i + 1], h[i], l[i]);
+        reinterpret_cast<uint2*>(hi + off)[j] = make_uint2(h[0], h[1]);
+        reinterpret_cast<uint2*>(lo + off)[j] = make_uint2(l[0], l[1]);
+      }
+    }
+  }
+  template <int NV>
+  static __device__ __forceinline__ void load(const void* base, size_t elems, size_t off, float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "split storage moves 4 or 8 elements per vector");
+    const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(base);
+    const __nv_bfloat16* lo = hi + elems;
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi + off) + j);
+      const uint2 b = __ldg(reinterpret_cast<const uint2*>(lo + off) + j);
+      v[4 * j + 0] = bf16lo_to_float(a.x) + bf16lo_to_float(b.x);
+      v[4 * j + 1] = bf16hi_to_float(a.x) + bf16hi_to_float(b.x);
+      v[4 * j + 2] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y);
+      v[4 * j + 3] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y);
+    }
+  }
+};
+
+struct StoreF32 {
+  template <int NV>
+  static __device__ __forceinline__ void store(void* base, size_t, size_t off, const float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "fp32 storage moves 4 elements per 16 B");
+    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+  template <int NV>
+  static __device__ __forceinline__ void load(const void* base, size_t, size_t off, float (&v)[NV]) {
+    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 t = __ldg(q + i);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  }
+};
+
+template <int NV>
+__device__ __forceinline__ void load_f32(const float* p, float (&v)[NV]) { StoreF32::load<NV>(p, 0, 0, v); }
+template <int NV>
+__device__ __forceinline__ void store_f32(float* p, const float (&v)[NV]) { StoreF32::store<NV>(p, 0, 0, v); }
+
+// v: accumulator values for channels [n, n+NV) of output pixel (item, y, x) of an H x W x Nout map.
+template <int MODE, int NV, class ST>
+__device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nout, int item, int y, int x, int n,
+                                          float (&v)[NV]) {
+  if (MODE == EPI_RAW) {
+    store_f32<NV>(e.out_f32 + (((size_t)item * H + y) * W + x) * Nout + n, v);
+  } else if (MODE == EPI_FWD_TRUE) {
+    const size_t off = (((size_t)item * H + y) * W + x) * Nout + n;
+    float z[NV], xo[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      z[i] = v[i] + (e.bias ? __ldg(e.bias + n + i) : 0.f);
+      xo[i] = fmaxf(z[i], 0.f);
+    }
+    ST::template store<NV>(e.out, e.out_elems, off, xo);
+    if (e.out_f32) store_f32<NV>(e.out_f32 + off, xo);
+    if (e.G || e.Mseed) {
+      float gg[NV], mm[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float zr = e.rule_bias ? z[i] : v[i];
+        if (e.gmode == G_EPS) {
+          const float d = stab_eps(zr, e.eps);
+          mm[i] = 1.f / d;
+          gg[i] = xo[i] / d;
+        } else if (e.gmode == G_Z) {
+          const float d = safe_den(zr);
+          mm[i] = 1.f / d;
+          gg[i] = xo[i] / d;
+        } else {
+          mm[i] = z[i] > 0.f ? 1.f : 0.f;
+          gg[i] = mm[i];
+        }
+      }
+      if (e.G) store_f32<NV>(e.G + off, gg);
+      if (e.Mseed) store_f32<NV>(e.Mseed + off, mm);
+    }
+  } else if (MODE == EPI_FWD_ZACT) {
+    const size_t off = (((size_t)item * H + y) * W + x) * Nout + n;
+    float xa[NV], gg[NV], mm[NV];
+    ST::template load<NV>(e.x_act, e.x_elems, off, xa);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float d = safe_den(v[i] + ((e.bias && e.rule_bias) ? __ldg(e.bias + n + i) : 0.f));
+      mm[i] = 1.f / d;
+      gg[i] = xa[i] / d;
+    }
+    if (e.G) store_f32<NV>(e.G + off, gg);
+    if (e.Mseed) store_f32<NV>(e.Mseed + off, mm);
+  } else {  // EPI_BWD
+    const int img = __ldg(e.img_index + item);
+    const int HH = H * e.up, WW = W * e.up;
+    if (e.relu_acc) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    for (int sy = 0; sy < e.up; ++sy) {
+      for (int sx = 0; sx < e.up; ++sx) {
+        const size_t pix = (size_t)(y * e.up + sy) * WW + (x * e.up + sx);
+        float gg[NV], o[NV];
+        load_f32<NV>(e.Gin + ((size_t)img * HH * WW + pix) * Nout + n, gg);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[i];
+        ST::template store<NV>(e.out, e.out_elems, ((size_t)item * HH * WW + pix) * Nout + n, o);
+      }
+    }
+  }
+}
+
+// Fills the device-side epilogue struct from the host-side description; validates per mode.
+inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
+  e->bias = p.bias;
+  e->out_f32 = p.out_f32;
+  e->G = p.G;
+  e->Mseed = p.Mseed;
+  e->gmode = p.gmode;
+  e->rule_bias = p.rule_bias;
+  e->eps = p.eps;
+  e->x_act = p.x_act;
+  e->x_elems = p.x_act_elems;
+  e->img_index = p.img_index;
+  e->Gin = p.Gin;
+  e->up = p.up;
+  e->relu_acc = p.relu_acc;
+  e->out = nullptr;
+  e->out_elems = 0;
+  switch (p.mode) {
+    case EPI_BWD:
+      LRPCAP_REQUIRE(p.out_msg && p.Gin && p.img_index && (p.up == 1 || p.up == 2), kErrInvalidArg,
+                     "conv: incomplete backward epilogue");
+      e->out = p.out_msg;
+      e->out_elems = p.out_msg_elems;
+      break;
+    case EPI_FWD_TRUE:
+      LRPCAP_REQUIRE(p.out_act != nullptr, kErrInvalidArg, "conv: forward epilogue needs out_act");
+      e->out = p.out_act;
+      e->out_elems = p.out_act_elems;
+      break;
+    case EPI_FWD_ZACT:
+      LRPCAP_REQUIRE(p.x_act != nullptr && (p.G || p.Mseed), kErrInvalidArg, "conv: zact epilogue incomplete");
+      break;
+    case EPI_RAW:
+      LRPCAP_REQUIRE(p.out_f32 != nullptr, kErrInvalidArg, "conv: raw epilogue needs out_f32");
+      break;
+    default:
+      set_last_error("conv: unknown epilogue mode %d", p.mode);
+      return kErrInvalidArg;
+  }
+  return kOk;
+}
+
+}  // namespace lrpcap

@@ -1,0 +1,78 @@
+// tcgen05 implicit-GEMM 3x3 / 1x1 convolution with split-bf16 ("bf16x3") operands -- interface.
+//
+// One kernel serves every dense contraction on the hot path:
+//   D[pixel, n] = sum_{tap, c} A[item, y+dy(tap), x+dx(tap), c] * B[tap, n, c]
+// A: activations / relevance messages, NHWC, split-bf16 planes.   B: prepared weights [taps*Nout, C].
+// Products: A_hi*B_hi + A_hi*B_lo + A_lo*B_hi, fp32 accumulation in TMEM.
+#pragma once
+#include "common.cuh"
+
+namespace lrpcap {
+
+enum EpiMode : int {
+  EPI_FWD_TRUE = 0,   // z = acc + b ; x = relu(z) ; write x (split [+fp32]) ; optional G / seed multiplier
+  EPI_FWD_ZACT = 1,   // zact = acc (+ b) ; G = x / safe(zact) with x read back from the true forward
+  EPI_BWD = 2,        // s_prev = (relu?)(acc) * G[img(item)] ; optional 2x2 up-sampling (fused max-pool routing)
+  EPI_RAW = 3,        // out_f32 = acc (debug / generic GEMM)
+};
+
+enum GMode : int {
+  G_NONE = 0,
+  G_EPS = 1,    // G = relu(z) / (z + sgn+(z) eps)      seed multiplier 1 / (z + sgn+(z) eps)
+  G_Z = 2,      // G = relu(z) / safe(z)                seed multiplier 1 / safe(z)
+  G_MASK = 3,   // G = [z > 0]                          seed multiplier [z > 0]      (gradient family)
+};
+
+struct EpiParams {
+  int mode = EPI_RAW;
+  // forward
+  const float* bias = nullptr;      // [Nout] (may be null)
+  void* out_act = nullptr;          // split storage [items, H, W, Nout]
+  size_t out_act_elems = 0;
+  float* out_f32 = nullptr;         // optional fp32 copy [items, H, W, Nout]
+  float* G = nullptr;               // fp32 [items, H, W, Nout]
+  float* Mseed = nullptr;           // fp32 [items, H, W, Nout] seed multiplier (last layer only)
+  int gmode = G_NONE;
+  float eps = 0.f;
+  int rule_bias = 1;                // 0 for the *IgnoreBias rule variants (the true forward still adds the bias)
+  const void* x_act = nullptr;      // FWD_ZACT: split storage of the true activation, same shape as the output
+  size_t x_act_elems = 0;
+  // backward
+  const int* img_index = nullptr;   // [items] -> image
+  const float* Gin = nullptr;       // fp32 [images, H*up, W*up, Nout]
+  int up = 1;
+  int relu_acc = 0;
+  void* out_msg = nullptr;          // split storage [items, H*up, W*up, Nout]
+  size_t out_msg_elems = 0;
+};
+
+struct TcConvArgs {
+  const void* A = nullptr;  // split storage [n_items, H, W, C]
+  size_t A_elems = 0;
+  int n_items = 0, H = 0, W = 0, C = 0;
+  const void* B = nullptr;  // split storage [taps * Nout, C]
+  size_t B_elems = 0;
+  int taps = 9, Nout = 0;
+  EpiParams epi;
+};
+
+// Launches on `stream`. Returns a status code (common.cuh).
+int tc_conv_launch(const TcConvArgs& args, cudaStream_t stream);
+
+// fp32 SIMT implicit-GEMM convolution with the same epilogues (exact-fp32 precision mode, and the
+// 3-channel first layer in both modes). A: fp32 [n_items, H, W, C]; B: fp32 [taps][C][Nout].
+// `split_out`: storage of out_act / out_msg / x_act (true = split-bf16 planes, false = fp32).
+struct SimtConvArgs {
+  const float* A = nullptr;
+  int n_items = 0, H = 0, W = 0, C = 0;
+  const float* B = nullptr;
+  int taps = 9, Nout = 0;
+  bool split_out = false;
+  EpiParams epi;
+};
+int simt_conv_launch(const SimtConvArgs& args, cudaStream_t stream);
+
+// Tile geometry used for a given map size (exposed for tests / docs).
+void tc_conv_tile(int H, int W, int* TW, int* TH);
+
+}  // namespace lrpcap

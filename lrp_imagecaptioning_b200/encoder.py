@@ -1,0 +1,119 @@
+"""Host-side handle of the CUDA VGG16 encoder (include/lrpcap.h, "encoder" section).
+
+`ImageModel` plays the role of the reference's `_image_model` (Keras sub-model input_1 -> block5_conv3,
+models/explainers.py:29-30): it owns the 13 conv kernels/biases with their Keras names and `predict`s grid
+features.  The relevance rules are chosen per call (analyzers.py).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synth import VGG16_CFG
+
+
+class RuleSpec(object):
+    def __init__(self, kind, epsilon=1e-7, alpha=1.0, beta=0.0, bias=True):
+        self.kind, self.epsilon, self.alpha, self.beta, self.bias = kind, float(epsilon), float(alpha), float(beta), bool(bias)
+
+    def key(self):
+        return (self.kind, self.epsilon, self.alpha, self.beta, self.bias)
+
+
+def _as_cuda_f32(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if not x.is_cuda:
+        x = x.to(device, non_blocking=True)
+    return x.contiguous().float()
+
+
+class ImageModel(object):
+    """VGG16 conv stack with Keras layer names; `weights` = list of 13 (kernel HWIO, bias)."""
+    layer_names = [c[0] for c in VGG16_CFG]
+
+    def __init__(self, weights, image_hw=224, precision="bf16x3", device="cuda:0"):
+        if len(weights) != 13:
+            raise ValueError("VGG16 to block5_conv3 has 13 conv layers, got %d" % len(weights))
+        for (k, b), (name, cin, cout, _) in zip(weights, VGG16_CFG):
+            if tuple(k.shape) != (3, 3, cin, cout) or tuple(b.shape) != (cout,):
+                raise ValueError("layer %s: expected kernel (3,3,%d,%d) and bias (%d,)" % (name, cin, cout, cout))
+        self.weights = [(np.ascontiguousarray(k, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32))
+                        for k, b in weights]
+        self.image_hw = int(image_hw)
+        self.precision = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3_TC}[precision]
+        self.device = torch.device(device)
+        self._h = None
+        self._state = None   # (rule key, n_images) of the resident forward state
+
+    # -- handle management
+    def handle(self):
+        if self._h is None:
+            if not torch.cuda.is_available():
+                raise _lib.LrpcapError(-3, "no CUDA device: lrpcap has no CPU path")
+            lib = _lib.load()
+            torch.cuda.set_device(self.device)
+            ks = (_lib.c_float_p * 13)(*[_lib.fptr(k) for k, _ in self.weights])
+            bs = (_lib.c_float_p * 13)(*[_lib.fptr(b) for _, b in self.weights])
+            h = _lib.c_void_p()
+            _lib.check(lib.lrpcap_encoder_create(ctypes.byref(h), ks, bs, self.image_hw, self.precision))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            _lib.load().lrpcap_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return _lib.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- compute
+    def forward(self, images, rule):
+        """images: [N, hw, hw, 3] float32 (numpy or torch); builds features + the rule's per-image state."""
+        x = _as_cuda_f32(images, self.device)
+        if x.dim() != 4 or x.shape[1] != self.image_hw or x.shape[2] != self.image_hw or x.shape[3] != 3:
+            raise ValueError("images must be [N, %d, %d, 3], got %s" % (self.image_hw, self.image_hw, tuple(x.shape)))
+        lib = _lib.load()
+        _lib.check(lib.lrpcap_encoder_forward(self.handle(), _lib.c_void_p(x.data_ptr()), x.shape[0], rule.kind,
+                                              rule.epsilon, rule.alpha, rule.beta, int(rule.bias), self._stream()))
+        self._state = (rule.key(), x.shape[0])
+        self._images = x   # keep alive until the async copy inside forward has been consumed
+        return self
+
+    def features(self):
+        n = self._state[1]
+        fh = self.image_hw // 16
+        out = torch.empty((n, fh, fh, 512), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().lrpcap_encoder_features(self.handle(), _lib.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def predict(self, images):
+        """Keras-style: grid features as a numpy array [N, hw/16, hw/16, 512]."""
+        self.forward(images, RuleSpec(_lib.RULE_GRADIENT))
+        return self.features().cpu().numpy()
+
+    def relevance(self, img_index, R_head):
+        """img_index: int array [W]; R_head [W, fh, fh, 512] (torch cuda or numpy). Returns torch cuda [W, hw, hw, 3]."""
+        idx = np.ascontiguousarray(np.asarray(img_index), dtype=np.int32)
+        R = _as_cuda_f32(R_head, self.device)
+        fh = self.image_hw // 16
+        if tuple(R.shape) != (idx.shape[0], fh, fh, 512):
+            raise ValueError("R_head must be [%d, %d, %d, 512], got %s" % (idx.shape[0], fh, fh, tuple(R.shape)))
+        out = torch.empty((idx.shape[0], self.image_hw, self.image_hw, 3), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.load().lrpcap_encoder_relevance(self.handle(), _lib.iptr(idx), _lib.c_void_p(R.data_ptr()),
+                                                        idx.shape[0], _lib.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def set_chunk_words(self, n):
+        _lib.check(_lib.load().lrpcap_encoder_set_chunk_words(self.handle(), int(n)))
+
+    def launches(self):
+        return int(_lib.load().lrpcap_encoder_launches(self.handle()))

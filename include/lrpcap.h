@@ -125,6 +125,9 @@ int lrpcap_decoder_backward(lrpcap_decoder_t* dec, const int* h_word_img, const 
                             float* d_R_head, double* h_r_words, void* stream);
 /* h_logit: [n_images, T] logit of the caption token at each step (fp64). */
 int lrpcap_decoder_caption_logits(lrpcap_decoder_t* dec, double* h_logit);
+/* The `.attention` / `.beta` attributes the reference explainers expose after `_forward_beam_search`
+ * (explainers.py:429-431): h_alpha [n_images, T+1, L] and h_beta [n_images, T+1], row 0 all zeros. Either may be NULL. */
+int lrpcap_decoder_attention(lrpcap_decoder_t* dec, float* h_alpha, float* h_beta);
 long long lrpcap_decoder_launches(lrpcap_decoder_t* dec);
 
 /* ----------------------------------------------------------------------------------------------- whole path

@@ -1,6 +1,6 @@
 // extern "C" surface declared in include/lrpcap.h: error plumbing, encoder entry points, debug conv.
 #include "../../include/lrpcap.h"
-#include "encoder.cuh"
+#include "handles.cuh"
 #include "encoder_kernels.cuh"
 #include "tc_conv.cuh"
 #include <vector>
@@ -18,9 +18,6 @@ const char* get_last_error() { return g_err; }
 
 using namespace lrpcap;
 
-struct lrpcap_encoder {
-  Encoder* impl;
-};
 
 extern "C" {
 

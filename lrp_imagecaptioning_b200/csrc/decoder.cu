@@ -1,0 +1,405 @@
+// Decoder: batched forward with stored state + batched word-level relevance (see decoder.cuh).
+#include "decoder.cuh"
+#include "decoder_kernels.cuh"
+#include "../../include/lrpcap.h"
+#include <algorithm>
+#include <numeric>
+
+namespace lrpcap {
+
+using namespace dk;
+
+namespace {
+inline unsigned nblk(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
+}  // namespace
+
+Decoder::~Decoder() {
+  for (void* p : owned_) cudaFree(p);
+  DevBuf* bufs[] = {&F_, &Vp_, &P_, &a_, &gp_, &tok_, &logitk_, &logits_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_,
+                    &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
+                    &Z_, &hp_, &sg_, &sp_, &e_, &hc_, &d_wimg_, &d_wt_, &d_order_, &Rh1_, &Rh2_, &Rh2n_, &Rc1_, &Rc2_,
+                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_};
+  for (DevBuf* b : bufs) b->release();
+}
+
+int Decoder::upload(const float* h, size_t n, double** out) {
+  LRPCAP_REQUIRE(h != nullptr, kErrInvalidArg, "decoder_create: missing weight tensor");
+  std::vector<double> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = (double)h[i];
+  void* p = nullptr;
+  LRPCAP_CUDA(cudaMalloc(&p, n * sizeof(double)));
+  owned_.push_back(p);
+  LRPCAP_CUDA(cudaMemcpy(p, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  *out = reinterpret_cast<double*>(p);
+  return kOk;
+}
+
+int Decoder::upload_t(const float* h, int rows, int cols, double** out) {
+  LRPCAP_REQUIRE(h != nullptr, kErrInvalidArg, "decoder_create: missing weight tensor");
+  std::vector<float> t((size_t)rows * cols);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = h[(size_t)r * cols + c];
+  return upload(t.data(), t.size(), out);
+}
+
+// rows of a [ra, cols] stacked over rows of b [rb, cols], column slice [col0, col0+ncols); optionally transposed.
+int Decoder::upload_cat(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, bool transpose,
+                        double** out) {
+  LRPCAP_REQUIRE(a && b, kErrInvalidArg, "decoder_create: missing weight tensor");
+  const int R = ra + rb;
+  std::vector<float> t((size_t)R * ncols);
+  for (int r = 0; r < R; ++r) {
+    const float* src = (r < ra) ? a + (size_t)r * cols : b + (size_t)(r - ra) * cols;
+    for (int c = 0; c < ncols; ++c) {
+      if (transpose) t[(size_t)c * R + r] = src[col0 + c];
+      else t[(size_t)r * ncols + c] = src[col0 + c];
+    }
+  }
+  return upload(t.data(), t.size(), out);
+}
+
+int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_token, int keras_logits) {
+  LRPCAP_REQUIRE(out && w, kErrInvalidArg, "decoder_create: null argument");
+  LRPCAP_REQUIRE(w->kind == LRPCAP_DECODER_ADAPTIVE || w->kind == LRPCAP_DECODER_GRIDTD, kErrInvalidArg,
+                 "decoder_create: unknown kind %d", w->kind);
+  LRPCAP_REQUIRE(w->V > 0 && w->H > 0 && w->E > 0 && w->D > 0, kErrShape, "decoder_create: bad dimensions");
+  LRPCAP_REQUIRE(sos_token >= 1 && sos_token <= w->V, kErrInvalidArg, "decoder_create: SOS id %d out of [1,%d]", sos_token, w->V);
+  Decoder* d = new Decoder();
+  d->kind_ = w->kind; d->V_ = w->V; d->H_ = w->H; d->E_ = w->E; d->D_ = w->D;
+  d->sos_ = sos_token; d->keras_logits_ = keras_logits;
+  const int V = w->V, H = w->H, E = w->E, D = w->D;
+  auto fail = [&](int st) { delete d; return st; };
+  int st;
+#define UP(expr) if ((st = (expr)) != kOk) return fail(st)
+  UP(d->upload(w->image_features_w, (size_t)D * H, &d->Wif_));
+  UP(d->upload(w->image_features_b, H, &d->bif_));
+  UP(d->upload_t(w->image_features_w, D, H, &d->WifT_));
+  UP(d->upload(w->global_w, (size_t)D * E, &d->Wgf_));
+  UP(d->upload(w->global_b, E, &d->bgf_));
+  UP(d->upload_t(w->global_w, D, E, &d->WgfT_));
+  UP(d->upload(w->embedding, (size_t)V * E, &d->Emb_));
+  UP(d->upload(w->output_w, (size_t)H * V, &d->Wo_));
+  UP(d->upload_t(w->output_w, H, V, &d->WoT_));
+  UP(d->upload(w->output_b, V, &d->bo_));
+  if (w->kind == LRPCAP_DECODER_ADAPTIVE) {
+    d->Kin1_ = 2 * E + H;
+    UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat1_));
+    UP(d->upload(w->lstm_b, 4 * H, &d->b1_));
+    UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, true, &d->Wgate1T_));
+    UP(d->upload(w->Wv, (size_t)H * H, &d->Wp_));
+    UP(d->upload(w->Wg, (size_t)H * H, &d->Whp_));
+    UP(d->upload_cat(w->Wx, 2 * E, w->Wh, H, H, 0, H, false, &d->Wsx_));
+    UP(d->upload(w->Ws, (size_t)H * H, &d->Wss_));
+    UP(d->upload(w->Vatt, H, &d->Va_));
+  } else {
+    d->Kin1_ = 2 * H + 2 * E;
+    d->Kin2_ = 3 * H;
+    UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat1_));
+    UP(d->upload(w->td_b, 4 * H, &d->b1_));
+    UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, true, &d->Wgate1T_));
+    UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat2_));
+    UP(d->upload(w->lang_b, 4 * H, &d->b2_));
+    UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, true, &d->Wgate2T_));
+    UP(d->upload(w->W_va, (size_t)H * H, &d->Wp_));
+    UP(d->upload(w->W_ha, (size_t)H * H, &d->Whp_));
+    UP(d->upload_cat(w->W_x, H + 2 * E, w->W_h, H, H, 0, H, false, &d->Wsx_));
+    UP(d->upload(w->W_s, (size_t)H * H, &d->Wss_));
+    UP(d->upload(w->W_a, H, &d->Va_));
+  }
+#undef UP
+  *out = d;
+  return kOk;
+}
+
+int Decoder::gemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                  const double* bias, cudaStream_t s) {
+  if (M <= 0) return kOk;
+  dim3 grid(nblk(N, GN), nblk(M, GM));
+  dgemm_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, bias);
+  ++launches_;
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int T, int greedy, int eos_token,
+                     cudaStream_t s) {
+  LRPCAP_REQUIRE(d_features && h_captions && N > 0 && L > 0 && T > 0, kErrInvalidArg, "decoder_forward: bad argument");
+  const int H = H_, E = E_, D = D_, V = V_;
+  const bool td = kind_ == LRPCAP_DECODER_GRIDTD;
+  if (!greedy)
+    for (int i = 0; i < N * T; ++i)
+      LRPCAP_REQUIRE(h_captions[i] >= 1 && h_captions[i] <= V, kErrInvalidArg,
+                     "decoder_forward: token id %d at %d outside [1,%d]", h_captions[i], i, V);
+  N_ = 0;
+  const size_t NL = (size_t)N * L, st = (size_t)N * (T + 1) * H;
+  LRPCAP_TRY(F_.ensure(NL * D * 8));
+  LRPCAP_TRY(Vp_.ensure(NL * H * 8));
+  LRPCAP_TRY(P_.ensure(NL * H * 8));
+  LRPCAP_TRY(UV_.ensure(NL * H * 8));   // scratch for relu(Vp) while projecting
+  LRPCAP_TRY(a_.ensure((size_t)N * D * 8));
+  LRPCAP_TRY(gp_.ensure((size_t)N * E * 8));
+  LRPCAP_TRY(tok_.ensure((size_t)N * T * sizeof(int)));
+  LRPCAP_TRY(logitk_.ensure((size_t)N * T * 8));
+  DevBuf* states[] = {&h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_, &ctx_, &s_, &chat_};
+  for (DevBuf* b : states) {
+    LRPCAP_TRY(b->ensure(st * 8));
+    LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, st * 8, s));
+  }
+  if (td) {
+    DevBuf* states2[] = {&h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_};
+    for (DevBuf* b : states2) {
+      LRPCAP_TRY(b->ensure(st * 8));
+      LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, st * 8, s));
+    }
+    LRPCAP_TRY(XH2_.ensure((size_t)N * T * Kin2_ * 8));
+  }
+  LRPCAP_TRY(alpha_.ensure((size_t)N * (T + 1) * L * 8));
+  LRPCAP_TRY(beta_.ensure((size_t)N * (T + 1) * 8));
+  LRPCAP_CUDA(cudaMemsetAsync(alpha_.p, 0, (size_t)N * (T + 1) * L * 8, s));
+  LRPCAP_CUDA(cudaMemsetAsync(beta_.p, 0, (size_t)N * (T + 1) * 8, s));
+  LRPCAP_TRY(XH1_.ensure((size_t)N * T * Kin1_ * 8));
+  LRPCAP_TRY(Z_.ensure((size_t)N * 4 * H * 8));
+  LRPCAP_TRY(hp_.ensure((size_t)N * H * 8));
+  LRPCAP_TRY(sg_.ensure((size_t)N * H * 8));
+  LRPCAP_TRY(sp_.ensure((size_t)N * H * 8));
+  LRPCAP_TRY(e_.ensure((size_t)N * (L + 1) * 8));
+  LRPCAP_TRY(hc_.ensure((size_t)N * H * 8));
+  if (greedy) LRPCAP_TRY(logits_.ensure((size_t)N * V * 8));
+  else LRPCAP_CUDA(cudaMemcpyAsync(tok_.p, h_captions, (size_t)N * T * sizeof(int), cudaMemcpyHostToDevice, s));
+
+  double *F = F_.as<double>(), *Vp = Vp_.as<double>(), *P = P_.as<double>(), *Vf = UV_.as<double>();
+  // image_features / global_img_feature heads (explainers.py:375-388)
+  f32_to_f64_kernel<<<nblk(NL * D, 256), 256, 0, s>>>(d_features, F, NL * D);
+  LRPCAP_TRY(gemm(F, D, Wif_, H, Vp, H, (int)NL, H, D, bif_, s));
+  round_f32_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, NL * H);   // rows are float32 results in the reference
+  relu_copy_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, Vf, NL * H);
+  LRPCAP_TRY(gemm(Vf, H, Wp_, H, P, H, (int)NL, H, H, nullptr, s));
+  mean_feat_kernel<<<N, 256, 0, s>>>(F, a_.as<double>(), L, D);
+  LRPCAP_TRY(gemm(a_.as<double>(), D, Wgf_, E, gp_.as<double>(), E, N, E, D, bgf_, s));
+  round_f32_kernel<<<nblk((size_t)N * E, 256), 256, 0, s>>>(gp_.as<double>(), (size_t)N * E);
+  launches_ += 5;
+
+  int* tok = tok_.as<int>();
+  for (int i = 0; i < T; ++i) {
+    build_xh_kernel<<<N, 256, 0, s>>>(XH1_.as<double>(), Emb_, gp_.as<double>(), h1_.as<double>(),
+                                      td ? h2_.as<double>() : nullptr, tok, i, T, H, E, sos_, td ? 1 : 0);
+    const double* xh = XH1_.as<double>() + (size_t)i * Kin1_;
+    LRPCAP_TRY(gemm(xh, T * Kin1_, Wcat1_, 4 * H, Z_.as<double>(), 4 * H, N, 4 * H, Kin1_, b1_, s));
+    lstm_point_kernel<<<N, 256, 0, s>>>(Z_.as<double>(), h1_.as<double>(), c1_.as<double>(), zg1_.as<double>(),
+                                        ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(), i, T, H);
+    const double* h_new = h1_.as<double>() + (size_t)(i + 1) * H;
+    LRPCAP_TRY(gemm(h_new, (T + 1) * H, Whp_, H, hp_.as<double>(), H, N, H, H, nullptr, s));
+    LRPCAP_TRY(gemm(xh, T * Kin1_, Wsx_, H, sg_.as<double>(), H, N, H, Kin1_, nullptr, s));
+    sentinel_kernel<<<N, 256, 0, s>>>(sg_.as<double>(), c1_.as<double>(), s_.as<double>(), i, T, H);
+    const double* s_new = s_.as<double>() + (size_t)(i + 1) * H;
+    LRPCAP_TRY(gemm(s_new, (T + 1) * H, Wss_, H, sp_.as<double>(), H, N, H, H, nullptr, s));
+    scores_kernel<<<dim3(L + 1, N), 128, 0, s>>>(P, hp_.as<double>(), sp_.as<double>(), Va_, e_.as<double>(), L, H);
+    softmax_kernel<<<N, 256, 0, s>>>(e_.as<double>(), alpha_.as<double>(), beta_.as<double>(), i, T, L);
+    context_kernel<<<N, 256, 0, s>>>(Vf, alpha_.as<double>(), beta_.as<double>(), s_.as<double>(), ctx_.as<double>(),
+                                     chat_.as<double>(), h1_.as<double>(), td ? nullptr : hc_.as<double>(), i, T, L, H);
+    launches_ += 6;
+    if (td) {
+      build_xh2_kernel<<<N, 256, 0, s>>>(XH2_.as<double>(), chat_.as<double>(), h1_.as<double>(), h2_.as<double>(), i, T, H);
+      LRPCAP_TRY(gemm(XH2_.as<double>() + (size_t)i * Kin2_, T * Kin2_, Wcat2_, 4 * H, Z_.as<double>(), 4 * H, N, 4 * H,
+                      Kin2_, b2_, s));
+      lstm_point_kernel<<<N, 256, 0, s>>>(Z_.as<double>(), h2_.as<double>(), c2_.as<double>(), zg2_.as<double>(),
+                                          ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(), i, T, H);
+      gridtd_hc_kernel<<<N, 256, 0, s>>>(h2_.as<double>(), chat_.as<double>(), hc_.as<double>(), i, T, H, keras_logits_);
+      launches_ += 3;
+    }
+    if (greedy) {
+      LRPCAP_TRY(gemm(hc_.as<double>(), H, Wo_, V, logits_.as<double>(), V, N, V, H, bo_, s));
+      argmax_kernel<<<N, 256, 0, s>>>(logits_.as<double>(), V, eos_token >= 1 ? eos_token - 1 : -1, tok,
+                                      logitk_.as<double>(), i, T);
+    } else {
+      logitk_kernel<<<N, 128, 0, s>>>(hc_.as<double>(), WoT_, bo_, tok, logitk_.as<double>(), i, T, H);
+    }
+    ++launches_;
+  }
+  LRPCAP_CUDA(cudaGetLastError());
+  if (greedy) {
+    LRPCAP_CUDA(cudaMemcpyAsync(h_captions, tok, (size_t)N * T * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LRPCAP_CUDA(cudaStreamSynchronize(s));
+  }
+  N_ = N; T_ = T; L_ = L;
+  return kOk;
+}
+
+int Decoder::caption_logits(double* h_logit) {
+  LRPCAP_REQUIRE(N_ > 0 && h_logit, kErrState, "decoder_caption_logits: call decoder_forward first");
+  LRPCAP_CUDA(cudaMemcpy(h_logit, logitk_.p, (size_t)N_ * T_ * 8, cudaMemcpyDeviceToHost));
+  return kOk;
+}
+
+int Decoder::attention(float* h_alpha, float* h_beta) {
+  LRPCAP_REQUIRE(N_ > 0, kErrState, "decoder_attention: call decoder_forward first");
+  if (h_alpha) {
+    std::vector<double> al((size_t)N_ * (T_ + 1) * L_);
+    LRPCAP_CUDA(cudaMemcpy(al.data(), alpha_.p, al.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < al.size(); ++i) h_alpha[i] = (float)al[i];
+  }
+  if (h_beta) {
+    std::vector<double> be((size_t)N_ * (T_ + 1));
+    LRPCAP_CUDA(cudaMemcpy(be.data(), beta_.p, be.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < be.size(); ++i) h_beta[i] = (float)be[i];
+  }
+  return kOk;
+}
+
+// Words sorted by position (descending) so that at time-step i the active words (t > i) are a prefix.
+int Decoder::sort_words(const int* h_word_img, const int* h_word_t, int W, cudaStream_t s) {
+  LRPCAP_REQUIRE(N_ > 0, kErrState, "decoder: call decoder_forward first");
+  LRPCAP_REQUIRE(h_word_img && h_word_t && W > 0, kErrInvalidArg, "decoder: bad word list");
+  for (int w = 0; w < W; ++w) {
+    LRPCAP_REQUIRE(h_word_img[w] >= 0 && h_word_img[w] < N_, kErrInvalidArg, "decoder: word %d image %d out of range", w, h_word_img[w]);
+    // reference: NotImplementedError('index out of range of captions') when t > len(xt) (explainers.py:538-539)
+    LRPCAP_REQUIRE(h_word_t[w] >= 1 && h_word_t[w] <= T_, kErrInvalidArg, "decoder: index out of range of captions (t=%d, T=%d)", h_word_t[w], T_);
+  }
+  order_.resize(W);
+  std::iota(order_.begin(), order_.end(), 0);
+  std::stable_sort(order_.begin(), order_.end(), [&](int a, int b) { return h_word_t[a] > h_word_t[b]; });
+  wimg_.resize(W); wt_.resize(W);
+  for (int p = 0; p < W; ++p) { wimg_[p] = h_word_img[order_[p]]; wt_[p] = h_word_t[order_[p]]; }
+  nact_.assign(T_, 0);
+  for (int i = 0; i < T_; ++i) {
+    int c = 0;
+    while (c < W && wt_[c] > i) ++c;
+    nact_[i] = c;
+  }
+  LRPCAP_TRY(d_wimg_.ensure((size_t)W * sizeof(int)));
+  LRPCAP_TRY(d_wt_.ensure((size_t)W * sizeof(int)));
+  LRPCAP_TRY(d_order_.ensure((size_t)W * sizeof(int)));
+  LRPCAP_CUDA(cudaMemcpyAsync(d_wimg_.p, wimg_.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, s));
+  LRPCAP_CUDA(cudaMemcpyAsync(d_wt_.p, wt_.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, s));
+  LRPCAP_CUDA(cudaMemcpyAsync(d_order_.p, order_.data(), (size_t)W * sizeof(int), cudaMemcpyHostToDevice, s));
+  return kOk;
+}
+
+int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float* d_R_head, double* h_r_words,
+                       float* h_attention, cudaStream_t s) {
+  LRPCAP_REQUIRE(d_R_head != nullptr, kErrInvalidArg, "decoder_relevance: null output");
+  LRPCAP_TRY(sort_words(h_word_img, h_word_t, W, s));
+  const int H = H_, E = E_, D = D_, L = L_, T = T_;
+  const bool td = kind_ == LRPCAP_DECODER_GRIDTD;
+  const size_t WH = (size_t)W * H;
+  DevBuf* rb[] = {&Rh1_, &Rc1_, &Rctx_};
+  for (DevBuf* b : rb) LRPCAP_TRY(b->ensure(WH * 8));
+  LRPCAP_TRY(U_.ensure((size_t)W * std::max(H, E) * 8));
+  LRPCAP_TRY(Rglob_.ensure((size_t)W * E * 8));
+  LRPCAP_TRY(rword_.ensure((size_t)W * T * 8));
+  LRPCAP_TRY(Y_.ensure((size_t)W * std::max(Kin1_, std::max(Kin2_, D)) * 8));
+  LRPCAP_TRY(ra_.ensure((size_t)W * D * 8));
+  LRPCAP_CUDA(cudaMemsetAsync(Rglob_.p, 0, (size_t)W * E * 8, s));
+  LRPCAP_CUDA(cudaMemsetAsync(rword_.p, 0, (size_t)W * T * 8, s));
+  LRPCAP_CUDA(cudaMemsetAsync(Rc1_.p, 0, WH * 8, s));
+  if (td) {
+    DevBuf* rb2[] = {&Rh2_, &Rh2n_, &Rc2_, &Rchat_};
+    for (DevBuf* b : rb2) LRPCAP_TRY(b->ensure(WH * 8));
+    LRPCAP_TRY(Q_.ensure((size_t)W * T * H * 8));
+    LRPCAP_CUDA(cudaMemsetAsync(Rc2_.p, 0, WH * 8, s));
+    LRPCAP_CUDA(cudaMemsetAsync(Rh1_.p, 0, WH * 8, s));
+  }
+  WordRef wr{d_wimg_.as<int>(), d_wt_.as<int>()};
+  const int* tok = tok_.as<int>();
+
+  if (!td) {
+    lrp_init_kernel<<<W, 256, 0, s>>>(wr, h1_.as<double>(), chat_.as<double>(), ctx_.as<double>(), s_.as<double>(),
+                                      beta_.as<double>(), logitk_.as<double>(), WoT_, tok, Rh1_.as<double>(),
+                                      Rc1_.as<double>(), Rctx_.as<double>(), nullptr, T, H, 0);
+    ++launches_;
+    for (int i = T - 1; i >= 0; --i) {
+      const int na = nact_[i];
+      if (na == 0) continue;
+      lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), zg1_.as<double>(), c1_.as<double>(),
+                                         Rc1_.as<double>(), Rh1_.as<double>(), nullptr, U_.as<double>(), T, H);
+      LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
+      lrp_scatter_adaptive_kernel<<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh1_.as<double>(),
+                                                     Rglob_.as<double>(), rword_.as<double>(), T, H, E);
+      launches_ += 2;
+    }
+  } else {
+    lrp_init_kernel<<<W, 256, 0, s>>>(wr, h2_.as<double>(), chat_.as<double>(), ctx_.as<double>(), s_.as<double>(),
+                                      beta_.as<double>(), logitk_.as<double>(), WoT_, tok, Rh2_.as<double>(), nullptr,
+                                      nullptr, Rchat_.as<double>(), T, H, 1);
+    ++launches_;
+    for (int i = T - 1; i >= 0; --i) {
+      const int na = nact_[i];
+      if (na == 0) continue;
+      lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia2_.as<double>(), fa2_.as<double>(), zg2_.as<double>(), c2_.as<double>(),
+                                         Rc2_.as<double>(), Rh2_.as<double>(), nullptr, U_.as<double>(), T, H);
+      LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, H, nullptr, s));
+      // Rctx_ doubles as the "extra" (r_s + R_h1) buffer of the top-down cell
+      lrp_scatter_lang_kernel<<<na, 256, 0, s>>>(wr, i, XH2_.as<double>(), Y_.as<double>(), chat_.as<double>(),
+                                                 ctx_.as<double>(), s_.as<double>(), beta_.as<double>(),
+                                                 Rchat_.as<double>(), Rh1_.as<double>(), Rh2n_.as<double>(),
+                                                 Rctx_.as<double>(), Q_.as<double>(), T, H);
+      // top-down cell: Rc1 += extra (Rh1 is already folded into extra, so pass a zero-free "Rh" = extra, extra = null)
+      lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), zg1_.as<double>(), c1_.as<double>(),
+                                         Rc1_.as<double>(), Rctx_.as<double>(), nullptr, U_.as<double>(), T, H);
+      LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
+      lrp_scatter_td_kernel<<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh2n_.as<double>(),
+                                               Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
+                                               rword_.as<double>(), T, H, E);
+      launches_ += 4;
+    }
+  }
+  // global feature -> average feature (explainers.py:634-639)
+  uglob_kernel<<<W, 256, 0, s>>>(wr, Rglob_.as<double>(), gp_.as<double>(), U_.as<double>(), E);
+  LRPCAP_TRY(gemm(U_.as<double>(), E, WgfT_, D, Y_.as<double>(), D, W, D, E, nullptr, s));
+  ra_kernel<<<W, 256, 0, s>>>(wr, Y_.as<double>(), a_.as<double>(), ra_.as<double>(), D);
+  launches_ += 2;
+  // image_features dense over all grid cells, in word chunks (explainers.py:641-659)
+  const int CH = std::min(W, 512);
+  LRPCAP_TRY(UV_.ensure(std::max((size_t)CH, (size_t)N_) * L * H * 8));
+  LRPCAP_TRY(YF_.ensure((size_t)CH * L * D * 8));
+  for (int p0 = 0; p0 < W; p0 += CH) {
+    const int m = std::min(CH, W - p0);
+    if (!td)
+      uv_adaptive_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), ctx_.as<double>(),
+                                                    Rctx_.as<double>(), UV_.as<double>(), T, L, H);
+    else
+      uv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
+                                                  UV_.as<double>(), T, L, H);
+    LRPCAP_TRY(gemm(UV_.as<double>(), H, WifT_, D, YF_.as<double>(), D, m * L, D, H, nullptr, s));
+    final_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F_.as<double>(), ra_.as<double>(),
+                                            YF_.as<double>(), d_R_head, L, D);
+    launches_ += 2;
+  }
+  LRPCAP_CUDA(cudaGetLastError());
+
+  if (h_r_words || h_attention) {
+    LRPCAP_CUDA(cudaStreamSynchronize(s));
+    if (h_r_words) {
+      std::vector<double> rw((size_t)W * T);
+      LRPCAP_CUDA(cudaMemcpy(rw.data(), rword_.p, rw.size() * 8, cudaMemcpyDeviceToHost));
+      for (int p = 0; p < W; ++p) {
+        double* o = h_r_words + (size_t)order_[p] * T;
+        const double* r = rw.data() + (size_t)p * T;
+        const int t = wt_[p];
+        for (int j = 0; j < T; ++j) o[j] = 0.0;
+        if (td) {
+          for (int j = 0; j < t; ++j) o[j] = r[j];                 // raw (explainers.py:1320)
+        } else {                                                    // explainers.py:660-665
+          double mx = 0.0;
+          for (int j = 1; j < t; ++j) mx = std::max(mx, std::fabs(r[j]));
+          for (int j = 1; j < t; ++j) o[j - 1] = (mx != 0.0) ? r[j] / mx : r[j];
+        }
+      }
+    }
+    if (h_attention) {
+      std::vector<double> al((size_t)N_ * (T + 1) * L);
+      LRPCAP_CUDA(cudaMemcpy(al.data(), alpha_.p, al.size() * 8, cudaMemcpyDeviceToHost));
+      for (int w = 0; w < W; ++w)
+        for (int l = 0; l < L; ++l)
+          h_attention[(size_t)w * L + l] = (float)al[((size_t)h_word_img[w] * (T + 1) + h_word_t[w]) * L + l];
+    }
+  }
+  return kOk;
+}
+
+int Decoder::backward(const int*, const int*, int, float*, double*, cudaStream_t) {
+  set_last_error("decoder_backward: the frozen-attention gradient decoder is not built yet");
+  return kErrUnsupported;
+}
+
+}  // namespace lrpcap

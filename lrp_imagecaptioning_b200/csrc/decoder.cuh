@@ -1,0 +1,73 @@
+// Attention-LSTM decoder: batched teacher-forced forward that stores every intermediate, and batched
+// word-level relevance (epsilon-LRP) / frozen-attention gradient back to the CNN grid features.
+//
+// Reference: /root/reference/models/explainers.py
+//   adaptive  forward :370-436   LRP :537-666    gradient :690-832
+//   grid-TD   forward :1092-1178 LRP :1180-1321  gradient :1344-1532
+//   helper    _propagate_relevance_linear_lrp :156-165, _get_sign_stabilizer :141-144 (eps = 1e-7)
+//
+// The reference runs one word at a time with 6+3t+3L (adaptive) / 4+t(8+L)+2L (grid-TD) helper calls per
+// word, each materialising a dense attribution matrix (identity matrices for element-wise steps).  Here all
+// (image, word) pairs advance together: the time loop i = T-1..0 runs once for the whole batch (words sorted
+// by position so the active ones are a prefix), every element-wise rule is one fused kernel over [words, H],
+// and every dense step is one GEMM whose M dimension is the number of active words (or words x L).
+// Arithmetic is fp64 (the reference computes this stage in NumPy float64 almost everywhere),
+// with the reference's float32 stores (r_V, r_img_feature_input) reproduced.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "encoder.cuh"   // DevBuf
+
+struct lrpcap_decoder_weights;
+
+namespace lrpcap {
+
+class Decoder {
+ public:
+  ~Decoder();
+  static int create(Decoder** out, const lrpcap_decoder_weights* w, int sos_token, int keras_logits);
+  int forward(const float* d_features, int n_images, int L, int* h_captions, int T, int greedy, int eos_token,
+              cudaStream_t s);
+  int relevance(const int* h_word_img, const int* h_word_t, int n_words, float* d_R_head, double* h_r_words,
+                float* h_attention, cudaStream_t s);
+  int backward(const int* h_word_img, const int* h_word_t, int n_words, float* d_R_head, double* h_r_words,
+               cudaStream_t s);
+  int caption_logits(double* h_logit);
+  int attention(float* h_alpha, float* h_beta);
+  long long launches() const { return launches_; }
+  int n_images() const { return N_; }
+  int T() const { return T_; }
+  int L() const { return L_; }
+  int D() const { return D_; }
+
+ private:
+  int upload(const float* h, size_t n, double** out);                        // fp32 host -> fp64 device
+  int upload_t(const float* h, int rows, int cols, double** out);            // transposed copy
+  int upload_cat(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, bool transpose,
+                 double** out);
+  int gemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+           const double* bias, cudaStream_t s);
+  int sort_words(const int* h_word_img, const int* h_word_t, int n_words, cudaStream_t s);
+
+  int kind_ = 0, V_ = 0, H_ = 0, E_ = 0, D_ = 0, L_ = 0, N_ = 0, T_ = 0, sos_ = 1, keras_logits_ = 0;
+  int Kin1_ = 0, Kin2_ = 0;   // LSTM input widths incl. recurrent part (adaptive: Kin1 = 2E+H)
+  long long launches_ = 0;
+  std::vector<void*> owned_;
+  // weights (fp64, device)
+  double *Wif_ = nullptr, *bif_ = nullptr, *WifT_ = nullptr, *Wgf_ = nullptr, *bgf_ = nullptr, *WgfT_ = nullptr;
+  double *Emb_ = nullptr, *Wo_ = nullptr, *WoT_ = nullptr, *bo_ = nullptr;
+  double *Wcat1_ = nullptr, *b1_ = nullptr, *Wcat2_ = nullptr, *b2_ = nullptr;     // [x;h] -> 4H
+  double *Wgate1T_ = nullptr, *Wgate2T_ = nullptr;                                 // g-gate slice, transposed [H, Kin]
+  double *Wp_ = nullptr, *Whp_ = nullptr, *Wsx_ = nullptr, *Wss_ = nullptr, *Va_ = nullptr;
+  // forward state
+  DevBuf F_, Vp_, P_, a_, gp_, tok_, logitk_, logits_;
+  DevBuf h1_, c1_, zg1_, ia1_, fa1_, ga1_, oa1_, h2_, c2_, zg2_, ia2_, fa2_, ga2_, oa2_;
+  DevBuf ctx_, s_, chat_, alpha_, beta_, XH1_, XH2_;
+  DevBuf Z_, hp_, sg_, sp_, e_, hc_;
+  // word batch
+  std::vector<int> order_, wimg_, wt_, nact_;
+  DevBuf d_wimg_, d_wt_, d_order_;
+  DevBuf Rh1_, Rh2_, Rh2n_, Rc1_, Rc2_, Rchat_, Rctx_, Rglob_, rword_, U_, Y_, Q_, UV_, YF_, ra_;
+};
+
+}  // namespace lrpcap

@@ -1,0 +1,476 @@
+// fp64 kernels of the decoder stage (element-wise LRP rules, attention, LSTM cell, DGEMM).
+// Included only by decoder.cu.
+#pragma once
+#include "common.cuh"
+
+namespace lrpcap {
+namespace dk {
+
+constexpr double kEps = 1e-7;   // keras.backend.epsilon(): default eps of explainers.py:157
+
+__device__ __forceinline__ double stabd(double z) { return z + (z >= 0.0 ? kEps : -kEps); }   // explainers.py:141-144
+__device__ __forceinline__ double sigm(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double f32r(double x) { return (double)(float)x; }                   // a float32 store
+
+// ------------------------------------------------------------------ DGEMM  C = A B (+ bias), row-major
+constexpr int GM = 64, GN = 64, GK = 16;
+__global__ void __launch_bounds__(256)
+dgemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, double* __restrict__ C,
+             int ldc, int M, int N, int K, const double* __restrict__ bias) {
+  __shared__ double As[GK][GM + 1];
+  __shared__ double Bs[GK][GN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;          // 64 x 16
+      const int mm = idx >> 4, kk = idx & 15;
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.0;
+      const int kb = idx >> 6, nn = idx & 63;  // 16 x 64
+      const int gn = n0 + nn, gkb = k0 + kb;
+      Bs[kb][nn] = (gn < N && gkb < K) ? B[(size_t)gkb * ldb + gn] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) C[(size_t)gm * ldc + gn] = acc[i][j] + (bias ? bias[gn] : 0.0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ forward: per-image features
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+// a[n,d] = mean_l F[n,l,d], kept at float32 precision like np.mean of a float32 array (explainers.py:382)
+__global__ void mean_feat_kernel(const double* __restrict__ F, double* __restrict__ a, int L, int D) {
+  const int n = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    double s = 0.0;
+    for (int l = 0; l < L; ++l) s += F[((size_t)n * L + l) * D + d];
+    a[(size_t)n * D + d] = f32r(s / L);
+  }
+}
+__global__ void round_f32_kernel(double* x, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = f32r(x[i]);
+}
+__global__ void relu_copy_kernel(const double* __restrict__ in, double* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmax(in[i], 0.0);
+}
+
+// ------------------------------------------------------------------ forward: one decoder step
+// adaptive: XH[n,i] = [emb(tok_prev), g, h_i]                       (explainers.py:400-409)
+// grid-TD : XH1[n,i] = [h2_i, g, emb(tok_prev), h1_i]               (explainers.py:1131-1136)
+__global__ void build_xh_kernel(double* __restrict__ XH, const double* __restrict__ Emb, const double* __restrict__ gp,
+                                const double* __restrict__ h1, const double* __restrict__ h2,
+                                const int* __restrict__ tok, int i, int T, int H, int E, int sos, int gridtd) {
+  const int n = blockIdx.x;
+  const int Kin = gridtd ? (2 * H + 2 * E) : (2 * E + H);
+  const int t = (i == 0) ? sos : tok[n * T + i - 1];
+  double* x = XH + ((size_t)n * T + i) * Kin;
+  const size_t so = ((size_t)n * (T + 1) + i) * H;
+  for (int j = threadIdx.x; j < Kin; j += blockDim.x) {
+    double v;
+    if (!gridtd) {
+      if (j < E) v = Emb[(size_t)(t - 1) * E + j];
+      else if (j < 2 * E) v = fmax(gp[(size_t)n * E + j - E], 0.0);
+      else v = h1[so + j - 2 * E];
+    } else {
+      if (j < H) v = h2[so + j];
+      else if (j < H + E) v = fmax(gp[(size_t)n * E + j - H], 0.0);
+      else if (j < H + 2 * E) v = Emb[(size_t)(t - 1) * E + j - H - E];
+      else v = h1[so + j - H - 2 * E];
+    }
+    x[j] = v;
+  }
+}
+// grid-TD: XH2[n,i] = [c_hat_{i+1}, h1_{i+1}, h2_i]                  (explainers.py:1151)
+__global__ void build_xh2_kernel(double* __restrict__ XH2, const double* __restrict__ chat,
+                                 const double* __restrict__ h1, const double* __restrict__ h2, int i, int T, int H) {
+  const int n = blockIdx.x;
+  double* x = XH2 + ((size_t)n * T + i) * 3 * H;
+  const size_t s0 = ((size_t)n * (T + 1) + i) * H, s1 = s0 + H;
+  for (int j = threadIdx.x; j < 3 * H; j += blockDim.x)
+    x[j] = (j < H) ? chat[s1 + j] : (j < 2 * H ? h1[s1 + j - H] : h2[s0 + j - 2 * H]);
+}
+// LSTM cell point-wise part, Keras gate order i, f, c, o              (explainers.py:125-139)
+__global__ void lstm_point_kernel(const double* __restrict__ Z, double* __restrict__ h, double* __restrict__ c,
+                                  double* __restrict__ zg, double* __restrict__ ia, double* __restrict__ fa,
+                                  double* __restrict__ ga, double* __restrict__ oa, int i, int T, int H) {
+  const int n = blockIdx.x;
+  const size_t s0 = ((size_t)n * (T + 1) + i) * H, s1 = s0 + H;
+  const double* z = Z + (size_t)n * 4 * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const double i_ = sigm(z[j]), f_ = sigm(z[H + j]), g_ = tanh(z[2 * H + j]), o_ = sigm(z[3 * H + j]);
+    const double cn = f_ * c[s0 + j] + i_ * g_;
+    c[s1 + j] = cn;
+    h[s1 + j] = o_ * tanh(cn);
+    zg[s1 + j] = z[2 * H + j];
+    ia[s1 + j] = i_;
+    fa[s1 + j] = f_;
+    ga[s1 + j] = g_;
+    oa[s1 + j] = o_;
+  }
+}
+// sentinel: s = tanh(c_{i+1}) * sigmoid(x W_x + h_i W_h)              (explainers.py:415, 1145)
+__global__ void sentinel_kernel(const double* __restrict__ sg, const double* __restrict__ c, double* __restrict__ s,
+                                int i, int T, int H) {
+  const int n = blockIdx.x;
+  const size_t s1 = ((size_t)n * (T + 1) + i + 1) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) s[s1 + j] = tanh(c[s1 + j]) * sigm(sg[(size_t)n * H + j]);
+}
+// attention scores e[n,l] = tanh(P[n,l] + hp[n]) . V  (l < L);  e[n,L] = tanh(sp[n] + hp[n]) . V   (explainers.py:413-417)
+__global__ void __launch_bounds__(128)
+scores_kernel(const double* __restrict__ P, const double* __restrict__ hp, const double* __restrict__ sp,
+              const double* __restrict__ Va, double* __restrict__ e, int L, int H) {
+  const int l = blockIdx.x, n = blockIdx.y;
+  const double* base = (l < L) ? P + ((size_t)n * L + l) * H : sp + (size_t)n * H;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < H; j += 128) acc += tanh(base[j] + hp[(size_t)n * H + j]) * Va[j];
+  __shared__ double red[128];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 64; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) e[(size_t)n * (L + 1) + l] = red[0];
+}
+// alpha = softmax(e[0:L]);  beta = softmax(e[0:L+1])[L]              (explainers.py:414, 418)
+__global__ void __launch_bounds__(256)
+softmax_kernel(const double* __restrict__ e, double* __restrict__ alpha, double* __restrict__ beta, int i, int T, int L) {
+  const int n = blockIdx.x;
+  const double* en = e + (size_t)n * (L + 1);
+  __shared__ double red[256];
+  double m = -1e300;
+  for (int l = threadIdx.x; l < L; l += 256) m = fmax(m, en[l]);
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + st]);
+    __syncthreads();
+  }
+  const double m1 = red[0];
+  __syncthreads();
+  double s = 0.0;
+  for (int l = threadIdx.x; l < L; l += 256) s += exp(en[l] - m1);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  const double s1 = red[0];
+  double* an = alpha + ((size_t)n * (T + 1) + i + 1) * L;
+  for (int l = threadIdx.x; l < L; l += 256) an[l] = exp(en[l] - m1) / s1;
+  if (threadIdx.x == 0) {
+    const double m2 = fmax(m1, en[L]);
+    beta[(size_t)n * (T + 1) + i + 1] = exp(en[L] - m2) / (s1 * exp(m1 - m2) + exp(en[L] - m2));
+  }
+}
+// ctx = sum_l alpha_l Vf_l ; c_hat = beta s + (1-beta) ctx ; hc = h_last + c_hat (optional)   (explainers.py:419-421)
+__global__ void context_kernel(const double* __restrict__ Vf, const double* __restrict__ alpha,
+                               const double* __restrict__ beta, const double* __restrict__ s, double* __restrict__ ctx,
+                               double* __restrict__ chat, const double* __restrict__ hlast, double* __restrict__ hc,
+                               int i, int T, int L, int H) {
+  const int n = blockIdx.x;
+  const size_t s1 = ((size_t)n * (T + 1) + i + 1) * H;
+  const double* an = alpha + ((size_t)n * (T + 1) + i + 1) * L;
+  const double b = beta[(size_t)n * (T + 1) + i + 1];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    double acc = 0.0;
+    for (int l = 0; l < L; ++l) acc += an[l] * Vf[((size_t)n * L + l) * H + j];
+    ctx[s1 + j] = acc;
+    const double ch = b * s[s1 + j] + (1.0 - b) * acc;
+    chat[s1 + j] = ch;
+    if (hc) hc[(size_t)n * H + j] = hlast[s1 + j] + ch;
+  }
+}
+// hc = h2_{i+1} (+ c_hat_{i+1} in keras-logits mode)
+__global__ void gridtd_hc_kernel(const double* __restrict__ h2, const double* __restrict__ chat, double* __restrict__ hc,
+                                 int i, int T, int H, int add_chat) {
+  const int n = blockIdx.x;
+  const size_t s1 = ((size_t)n * (T + 1) + i + 1) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) hc[(size_t)n * H + j] = h2[s1 + j] + (add_chat ? chat[s1 + j] : 0.0);
+}
+// teacher-forced: logit of the caption token only (the relevance pass reads nothing else of the logits)
+__global__ void __launch_bounds__(128)
+logitk_kernel(const double* __restrict__ hc, const double* __restrict__ WoT, const double* __restrict__ bo,
+              const int* __restrict__ tok, double* __restrict__ logitk, int i, int T, int H) {
+  const int n = blockIdx.x;
+  const int k = tok[n * T + i] - 1;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < H; j += 128) acc += hc[(size_t)n * H + j] * WoT[(size_t)k * H + j];
+  __shared__ double red[128];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = 64; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) logitk[n * T + i] = red[0] + bo[k];
+}
+// greedy: token = arg-max of the logits (first maximum), optionally never the EOS id
+__global__ void __launch_bounds__(256)
+argmax_kernel(const double* __restrict__ logits, int V, int eos_index, int* __restrict__ tok, double* __restrict__ logitk,
+              int i, int T) {
+  const int n = blockIdx.x;
+  const double* ln = logits + (size_t)n * V;
+  double best = -1e300;
+  int bi = V;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    if (v == eos_index) continue;
+    const double x = ln[v];
+    if (x > best) { best = x; bi = v; }
+  }
+  __shared__ double rb[256];
+  __shared__ int ri[256];
+  rb[threadIdx.x] = best;
+  ri[threadIdx.x] = bi;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      const double ob = rb[threadIdx.x + st];
+      const int oi = ri[threadIdx.x + st];
+      if (ob > rb[threadIdx.x] || (ob == rb[threadIdx.x] && oi < ri[threadIdx.x])) {
+        rb[threadIdx.x] = ob;
+        ri[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    tok[n * T + i] = ri[0] + 1;   // model index -> tokenizer id (explainers.py:92)
+    logitk[n * T + i] = rb[0];
+  }
+}
+
+// ------------------------------------------------------------------ relevance: element-wise rules
+// ew(R, a, z) = a * R / stab(z)  (identity-weight helper call);  all kernels: one block per active word.
+struct WordRef {
+  const int* img;   // [W] image of sorted word p
+  const int* t;     // [W] 1-based position of sorted word p
+};
+
+// output layer + merge split (explainers.py:569-602 / 1212-1229)
+__global__ void lrp_init_kernel(WordRef w, const double* __restrict__ hlast, const double* __restrict__ chat,
+                                const double* __restrict__ ctx, const double* __restrict__ s,
+                                const double* __restrict__ beta, const double* __restrict__ logitk,
+                                const double* __restrict__ WoT, const int* __restrict__ tok, double* __restrict__ Rh,
+                                double* __restrict__ Rc, double* __restrict__ Rctx, double* __restrict__ Rchat, int T,
+                                int H, int gridtd) {
+  const int p = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const int k = tok[n * T + t - 1] - 1;
+  const double lk = logitk[n * T + t - 1];
+  const double coef = lk / stabd(lk);
+  const size_t st = ((size_t)n * (T + 1) + t) * H;
+  const double b = beta[(size_t)n * (T + 1) + t];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const double hv = hlast[st + j], cv = chat[st + j];
+    const double hc = hv + cv;
+    const double r_hc = hc * WoT[(size_t)k * H + j] * coef;
+    Rh[(size_t)p * H + j] = hv * r_hc / stabd(hc);
+    const double r_chat = cv * r_hc / stabd(hc);
+    if (gridtd) {
+      Rchat[(size_t)p * H + j] = r_chat;
+    } else {
+      Rctx[(size_t)p * H + j] = (1.0 - b) * ctx[st + j] * r_chat / stabd(cv);
+      Rc[(size_t)p * H + j] = b * s[st + j] * r_chat / stabd(cv);
+    }
+  }
+}
+// LSTM cell, gate pass-through (explainers.py:605-619): Rc += Rh (+extra); U = R_g / stab(zg); Rc <- forget branch
+__global__ void lrp_cell_kernel(WordRef w, int i, const double* __restrict__ ia, const double* __restrict__ fa,
+                                const double* __restrict__ zg, const double* __restrict__ c, double* __restrict__ Rc,
+                                const double* __restrict__ Rh, const double* __restrict__ extra,
+                                double* __restrict__ U, int T, int H) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  const size_t s0 = ((size_t)n * (T + 1) + i) * H, s1 = s0 + H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const size_t q = (size_t)p * H + j;
+    const double rc = Rc[q] + Rh[q] + (extra ? extra[q] : 0.0);
+    const double den = stabd(c[s1 + j]);
+    const double rg = ia[s1 + j] * tanh(zg[s1 + j]) * rc / den;
+    Rc[q] = fa[s1 + j] * c[s0 + j] * rc / den;
+    U[q] = rg / stabd(zg[s1 + j]);
+  }
+}
+// adaptive: R_xh = [x_i, h_i] * Y -> word / global / hidden parts (explainers.py:620-630)
+__global__ void __launch_bounds__(256)
+lrp_scatter_adaptive_kernel(WordRef w, int i, const double* __restrict__ XH, const double* __restrict__ Y,
+                            double* __restrict__ Rh, double* __restrict__ Rglob, double* __restrict__ rword, int T,
+                            int H, int E) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  const int Kin = 2 * E + H;
+  const double* x = XH + ((size_t)n * T + i) * Kin;
+  const double* y = Y + (size_t)p * Kin;
+  double wsum = 0.0;
+  for (int j = threadIdx.x; j < Kin; j += 256) {
+    const double v = x[j] * y[j];
+    if (j < E) wsum += v;
+    else if (j < 2 * E) Rglob[(size_t)p * E + j - E] += v;
+    else Rh[(size_t)p * H + j - 2 * E] = v;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = wsum;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rword[(size_t)p * T + i] = red[0];
+}
+// grid-TD, language LSTM input split + sentinel/context split (explainers.py:1252-1269)
+//   R_x2 = [c_hat_{i+1}, h1_{i+1}, h2_i] * Y2 ; Rchat_i = (i == t-1 ? init : 0) + R_x2[:H] ; Rh1 += R_x2[H:2H] ;
+//   Rh2n = R_x2[2H:] ; extra = r_s + Rh1 (added to Rc1 by the next cell kernel) ; Q = R_ctx / stab(ctx_{i+1})
+__global__ void lrp_scatter_lang_kernel(WordRef w, int i, const double* __restrict__ XH2, const double* __restrict__ Y2,
+                                        const double* __restrict__ chat, const double* __restrict__ ctx,
+                                        const double* __restrict__ s, const double* __restrict__ beta,
+                                        const double* __restrict__ Rchat_init, double* __restrict__ Rh1,
+                                        double* __restrict__ Rh2n, double* __restrict__ extra, double* __restrict__ Q,
+                                        int T, int H) {
+  const int p = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const double* x = XH2 + ((size_t)n * T + i) * 3 * H;
+  const double* y = Y2 + (size_t)p * 3 * H;
+  const size_t s1 = ((size_t)n * (T + 1) + i + 1) * H;
+  const double b = beta[(size_t)n * (T + 1) + i + 1];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const size_t q = (size_t)p * H + j;
+    const double rchat = ((i == t - 1) ? Rchat_init[q] : 0.0) + x[j] * y[j];
+    const double rh1 = Rh1[q] + x[H + j] * y[H + j];
+    Rh2n[q] = x[2 * H + j] * y[2 * H + j];
+    const double den = stabd(chat[s1 + j]);
+    const double r_s = b * s[s1 + j] * rchat / den;
+    const double r_ctx = ctx[s1 + j] * (1.0 - b) * rchat / den;
+    extra[q] = r_s + rh1;
+    Q[((size_t)p * T + i) * H + j] = r_ctx / stabd(ctx[s1 + j]);
+  }
+}
+// grid-TD, top-down LSTM input split (explainers.py:1288-1300): [h2_i, g, emb, h1_i]
+__global__ void __launch_bounds__(256)
+lrp_scatter_td_kernel(WordRef w, int i, const double* __restrict__ XH1, const double* __restrict__ Y1,
+                      const double* __restrict__ Rh2n, double* __restrict__ Rh2, double* __restrict__ Rh1,
+                      double* __restrict__ Rglob, double* __restrict__ rword, int T, int H, int E) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  const int Kin = 2 * H + 2 * E;
+  const double* x = XH1 + ((size_t)n * T + i) * Kin;
+  const double* y = Y1 + (size_t)p * Kin;
+  double wsum = 0.0;
+  for (int j = threadIdx.x; j < Kin; j += 256) {
+    const double v = x[j] * y[j];
+    if (j < H) Rh2[(size_t)p * H + j] = Rh2n[(size_t)p * H + j] + v;
+    else if (j < H + E) Rglob[(size_t)p * E + j - H] += v;
+    else if (j < H + 2 * E) wsum += v;
+    else Rh1[(size_t)p * H + j - H - 2 * E] = v;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = wsum;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) rword[(size_t)p * T + i] = red[0];
+}
+
+// ------------------------------------------------------------------ relevance: tail (global feature, image features)
+__global__ void uglob_kernel(WordRef w, const double* __restrict__ Rglob, const double* __restrict__ gp,
+                             double* __restrict__ Ug, int E) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  for (int j = threadIdx.x; j < E; j += blockDim.x) Ug[(size_t)p * E + j] = Rglob[(size_t)p * E + j] / stabd(gp[(size_t)n * E + j]);
+}
+// ra[p,d] = (a * Ya) / stab(a)   -- r_average_img_feature already divided for the mean-pool split (explainers.py:634-647)
+__global__ void ra_kernel(WordRef w, const double* __restrict__ Ya, const double* __restrict__ a, double* __restrict__ ra,
+                          int D) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double av = a[(size_t)n * D + d];
+    ra[(size_t)p * D + d] = av * Ya[(size_t)p * D + d] / stabd(av);
+  }
+}
+// adaptive: UV[p,l,:] = float32(Vf_l * alpha_t[l] * R_ctx / stab(ctx_t)) / stab(Vp_l)     (explainers.py:648-659)
+__global__ void uv_adaptive_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
+                                   const double* __restrict__ ctx, const double* __restrict__ Rctx,
+                                   double* __restrict__ UV, int T, int L, int H) {
+  const int p = p0 + blockIdx.y, l = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const double al = alpha[((size_t)n * (T + 1) + t) * L + l];
+  const size_t st = ((size_t)n * (T + 1) + t) * H;
+  const double* vp = Vp + ((size_t)n * L + l) * H;
+  double* o = UV + ((size_t)blockIdx.y * L + l) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const double rv = f32r(fmax(vp[j], 0.0) * al * Rctx[(size_t)p * H + j] / stabd(ctx[st + j]));
+    o[j] = rv / stabd(vp[j]);
+  }
+}
+// grid-TD: r_V accumulates over every step <= t in a float32 buffer (explainers.py:1292-1299)
+__global__ void uv_gridtd_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
+                                 const double* __restrict__ Q, double* __restrict__ UV, int T, int L, int H) {
+  const int p = p0 + blockIdx.y, l = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const double* vp = Vp + ((size_t)n * L + l) * H;
+  double* o = UV + ((size_t)blockIdx.y * L + l) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const double vf = fmax(vp[j], 0.0);
+    float acc = 0.f;
+    for (int i = t - 1; i >= 0; --i) {
+      const double al = alpha[((size_t)n * (T + 1) + i + 1) * L + l];
+      acc = (float)((double)acc + vf * al * Q[((size_t)p * T + i) * H + j]);
+    }
+    o[j] = (double)acc / stabd(vp[j]);
+  }
+}
+// R_F[word, l, d] = float32( float32(F/L * ra) + F * YF )      (explainers.py:641-659)
+__global__ void final_kernel(WordRef w, int p0, const int* __restrict__ order, const double* __restrict__ F,
+                             const double* __restrict__ ra, const double* __restrict__ YF, float* __restrict__ out, int L,
+                             int D) {
+  const int p = p0 + blockIdx.y, l = blockIdx.x;
+  const int n = w.img[p];
+  const double* f = F + ((size_t)n * L + l) * D;
+  const double* yf = YF + ((size_t)blockIdx.y * L + l) * D;
+  float* o = out + ((size_t)order[p] * L + l) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float first = (float)(f[d] / L * ra[(size_t)p * D + d]);
+    o[d] = (float)((double)first + f[d] * yf[d]);
+  }
+}
+
+}  // namespace dk
+}  // namespace lrpcap

@@ -68,7 +68,7 @@ def decoder_weights(kind, V=10000, H=512, E=512, D=512, seed=2, bias_std=0.01, o
     """Decoder weight dict. Names are ours; the mapping to the Keras tensors is in
     SURVEY.md Appendix A.1 and in ``model.py`` of this package."""
     g = rng(seed)
-    d = {"kind": kind, "hidden_dim": H, "embedding_dim": E, "D": D, "V": V}
+    d = {"kind": kind, "hidden_dim": H, "embedding_dim": E, "D": D, "vocab_size": V}
     d["image_features_w"] = _glorot(g, (D, H))
     d["image_features_b"] = (g.standard_normal(H) * bias_std).astype(np.float32)
     d["global_w"] = _glorot(g, (D, E))

@@ -1,47 +1,88 @@
-"""Shared parity metrics (BASELINE.json north_star tolerances)."""
+"""Shared parity metrics (BASELINE.json north_star tolerances) and a JSON-lines parity report.
+
+Relevance maps are consumed after abs-max normalisation (reference: innvestigate/utils/visualizations.py:36-54
+`project`, models/model.py:1676-1680 `hp /= max|hp|`), and their values span many orders of magnitude, so the
+per-pixel / per-feature relative error is measured against the map's absolute maximum:
+
+    linf_rel = max|got - ref| / max|ref|        l2_rel = ||got - ref||_2 / ||ref||_2
+
+`floor_rel` (denominator |ref| + 1e-3 max|ref|) is also recorded in the report; it is dominated by near-zero
+pixels and is informative only for the rules whose arithmetic has no cancellation (alpha-beta family).
+"""
+import json
+import os
+
 import numpy as np
 
-REL_TOL = 1e-3      # per-pixel / per-feature relative error
+REL_TOL = 1e-3      # per-pixel / per-feature error relative to the map's abs-max, and relative L2
 SUM_TOL = 1e-4      # relevance-conservation sums (relative to the sum of |R|)
-FLOOR = 1e-3        # rel-err denominator floor, as a fraction of max|ref| (SURVEY.md §7 "Precision vs. tolerance")
+
+_REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
 
-def rel_err(got, ref):
-    """max over elements of |got - ref| / (|ref| + FLOOR * max|ref|)."""
-    got = np.asarray(got, dtype=np.float64)
-    ref = np.asarray(ref, dtype=np.float64)
+def _f64(a):
+    return np.asarray(a, dtype=np.float64)
+
+
+def linf_rel(got, ref):
+    got, ref = _f64(got), _f64(ref)
     assert got.shape == ref.shape, (got.shape, ref.shape)
     assert np.all(np.isfinite(got)), "non-finite values in result"
     scale = np.max(np.abs(ref))
+    return float(np.max(np.abs(got - ref)) / scale) if scale > 0 else float(np.max(np.abs(got)))
+
+
+def l2_rel(got, ref):
+    got, ref = _f64(got), _f64(ref)
+    n = np.linalg.norm(ref.ravel())
+    return float(np.linalg.norm((got - ref).ravel()) / n) if n > 0 else float(np.linalg.norm(got.ravel()))
+
+
+def floor_rel(got, ref, floor=1e-3):
+    got, ref = _f64(got), _f64(ref)
+    scale = np.max(np.abs(ref))
     if scale == 0:
         return float(np.max(np.abs(got)))
-    return float(np.max(np.abs(got - ref) / (np.abs(ref) + FLOOR * scale)))
+    return float(np.max(np.abs(got - ref) / (np.abs(ref) + floor * scale)))
 
 
 def sum_err(got, ref):
-    got = np.asarray(got, dtype=np.float64)
-    ref = np.asarray(ref, dtype=np.float64)
+    got, ref = _f64(got), _f64(ref)
     return float(abs(got.sum() - ref.sum()) / (np.abs(ref).sum() + 1e-300))
 
 
 def topk_cells(R, k=10, cell=16):
-    """Indices of the k most relevant grid regions: R [H, W, C] pooled over cell x cell blocks and channels."""
-    R = np.asarray(R, dtype=np.float64)
+    """Indices of the k most relevant grid regions: R [H, W, C] summed over cell x cell blocks and channels."""
+    R = _f64(R)
     H, W = R.shape[0], R.shape[1]
     g = R.reshape(H // cell, cell, W // cell, cell, -1).sum(axis=(1, 3, 4))
     order = np.argsort(-g.reshape(-1), kind="stable")
-    return list(order[:min(k, order.size)])
+    return [int(i) for i in order[:min(k, order.size)]]
 
 
 def topk_features(R, k=10):
-    """Top-k grid cells of a feature-level relevance map R [h, w, D] (summed over D)."""
-    g = np.asarray(R, dtype=np.float64).sum(axis=-1).reshape(-1)
-    return list(np.argsort(-g, kind="stable")[:min(k, g.size)])
+    """Top-k grid cells of a feature-level relevance map R [L, D] or [h, w, D] (summed over D)."""
+    g = _f64(R).sum(axis=-1).reshape(-1)
+    return [int(i) for i in np.argsort(-g, kind="stable")[:min(k, g.size)]]
 
 
-def assert_parity(got, ref, what="", rel_tol=REL_TOL, sum_tol=SUM_TOL):
-    r = rel_err(got, ref)
-    s = sum_err(got, ref)
-    assert r <= rel_tol, "%s: rel-err %.3e > %.1e" % (what, r, rel_tol)
-    assert s <= sum_tol, "%s: sum-err %.3e > %.1e" % (what, s, sum_tol)
-    return r, s
+def record(what, got, ref, **extra):
+    m = {"what": what, "linf_rel": linf_rel(got, ref), "l2_rel": l2_rel(got, ref), "floor_rel": floor_rel(got, ref),
+         "sum_err": sum_err(got, ref)}
+    m.update(extra)
+    try:
+        os.makedirs(os.path.dirname(_REPORT), exist_ok=True)
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps(m) + "\n")
+    except OSError:
+        pass
+    return m
+
+
+def assert_parity(got, ref, what="", rel_tol=REL_TOL, sum_tol=SUM_TOL, **extra):
+    m = record(what, got, ref, rel_tol=rel_tol, **extra)
+    assert m["linf_rel"] <= rel_tol, "%s: linf-rel %.3e > %.1e (l2 %.3e)" % (what, m["linf_rel"], rel_tol, m["l2_rel"])
+    assert m["l2_rel"] <= rel_tol, "%s: l2-rel %.3e > %.1e" % (what, m["l2_rel"], rel_tol)
+    if sum_tol is not None:
+        assert m["sum_err"] <= sum_tol, "%s: sum-err %.3e > %.1e" % (what, m["sum_err"], sum_tol)
+    return m

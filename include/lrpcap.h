@@ -79,6 +79,11 @@ int lrpcap_encoder_relevance_host(lrpcap_encoder_t* enc, const int* h_img_index,
                                   float* h_R_pix, void* stream);
 int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words);
 long long lrpcap_encoder_launches(lrpcap_encoder_t* enc);
+/* Kernel timing (CUDA events on the launching stream around every convolution launch) for roofline reporting.
+ * h_out9: per class {0: tcgen05 transposed conv (relevance), 1: tcgen05 forward conv, 2: fp32 SIMT conv}
+ * [total ms, algorithmic FLOPs, launches]; reading synchronises and resets the counters. */
+int lrpcap_encoder_profile(lrpcap_encoder_t* enc, int enable);
+int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out9);
 
 /* ----------------------------------------------------------------------------------------------- decoder */
 

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "lrpcap_encoder_relevance_host": (ctypes.c_int, [c_void_p, c_int_p, c_float_p, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_encoder_set_chunk_words": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "lrpcap_encoder_launches": (ctypes.c_longlong, [c_void_p]),
+    "lrpcap_encoder_profile": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "lrpcap_encoder_profile_read": (ctypes.c_int, [c_void_p, c_double_p]),
     "lrpcap_decoder_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(DecoderWeights), ctypes.c_int, ctypes.c_int]),
     "lrpcap_decoder_destroy": (ctypes.c_int, [c_void_p]),
     "lrpcap_decoder_forward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p]),

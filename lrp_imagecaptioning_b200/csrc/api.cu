@@ -108,6 +108,17 @@ int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words) {
 
 long long lrpcap_encoder_launches(lrpcap_encoder_t* enc) { return (enc && enc->impl) ? enc->impl->launches() : 0; }
 
+int lrpcap_encoder_profile(lrpcap_encoder_t* enc, int enable) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_profile: null handle");
+  enc->impl->set_profile(enable != 0);
+  return kOk;
+}
+
+int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out9) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_profile_read: null handle");
+  return enc->impl->profile_read(h_out9);
+}
+
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out) {
   LRPCAP_REQUIRE(h_A && h_B && h_out, kErrInvalidArg, "debug_conv: null argument");

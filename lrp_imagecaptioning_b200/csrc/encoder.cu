@@ -96,21 +96,53 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
   const int Nout = backward ? L.cin : L.cout;
   void* B = nullptr;
   ++launches_;
-  if (split() && C % 64 == 0 && Nout % 64 == 0) {
-    LRPCAP_TRY(get_weights(l, backward ? WF_TC_BWD : WF_TC_FWD, sign, &B, s));
+  const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
+  if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
+  LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : WF_TC_FWD) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  ProfRec rec{};
+  if (profile_) {
+    LRPCAP_CUDA(cudaEventCreate(&rec.a));
+    LRPCAP_CUDA(cudaEventCreate(&rec.b));
+    rec.cls = tc ? (backward ? 0 : 1) : 2;
+    rec.flops = 2.0 * 9.0 * (double)n_items * L.hw * L.hw * (double)L.cin * L.cout;
+    LRPCAP_CUDA(cudaEventRecord(rec.a, s));
+  }
+  int st;
+  if (tc) {
     TcConvArgs a;
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout; a.taps = 9; a.Nout = Nout;
     a.epi = epi;
-    return tc_conv_launch(a, s);
+    st = tc_conv_launch(a, s);
+  } else {
+    SimtConvArgs a;
+    a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
+    a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout; a.split_out = split();
+    a.epi = epi;
+    st = simt_conv_launch(a, s);
   }
-  LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
-  LRPCAP_TRY(get_weights(l, backward ? WF_SIMT_BWD : WF_SIMT_FWD, sign, &B, s));
-  SimtConvArgs a;
-  a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
-  a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout; a.split_out = split();
-  a.epi = epi;
-  return simt_conv_launch(a, s);
+  if (profile_) {
+    LRPCAP_CUDA(cudaEventRecord(rec.b, s));
+    prof_.push_back(rec);
+  }
+  return st;
+}
+
+int Encoder::profile_read(double* out) {
+  LRPCAP_REQUIRE(out != nullptr, kErrInvalidArg, "profile_read: null output");
+  for (int i = 0; i < 9; ++i) out[i] = 0.0;
+  for (ProfRec& r : prof_) {
+    LRPCAP_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    LRPCAP_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    out[3 * r.cls + 0] += ms;
+    out[3 * r.cls + 1] += r.flops;
+    out[3 * r.cls + 2] += 1.0;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  prof_.clear();
+  return kOk;
 }
 
 int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cudaStream_t s) {

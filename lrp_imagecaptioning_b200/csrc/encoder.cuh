@@ -60,8 +60,20 @@ class Encoder {
   void set_chunk_words(int n) { chunk_words_ = n > 0 ? n : 1; }
   // kernels launched by this object since construction (bench.py's gpu_launches)
   long long launches() const { return launches_; }
+  // Kernel timing with CUDA events on the launching stream (bench.py roofline): when enabled every conv launch is
+  // bracketed by two events. profile_read() synchronises and returns, per class {tc_bwd, tc_fwd, simt}:
+  // out[3*c + 0] = total ms, out[3*c + 1] = algorithmic FLOPs (2*MAC), out[3*c + 2] = launches; then resets.
+  void set_profile(bool on) { profile_ = on; }
+  int profile_read(double* out9);
 
  private:
+  struct ProfRec {
+    cudaEvent_t a, b;
+    int cls;
+    double flops;
+  };
+  bool profile_ = false;
+  std::vector<ProfRec> prof_;
   struct Layer {
     int cin, cout, hw;        // hw: spatial size of the conv's input == output
     bool pool_after;

@@ -78,6 +78,7 @@ class ImageModel(object):
     # -- compute
     def forward(self, images, rule):
         """images: [N, hw, hw, 3] float32 (numpy or torch); builds features + the rule's per-image state."""
+        self.handle()   # fails loudly first when there is no CUDA device / library
         x = _as_cuda_f32(images, self.device)
         if x.dim() != 4 or x.shape[1] != self.image_hw or x.shape[2] != self.image_hw or x.shape[3] != 3:
             raise ValueError("images must be [N, %d, %d, 3], got %s" % (self.image_hw, self.image_hw, tuple(x.shape)))
@@ -114,6 +115,15 @@ class ImageModel(object):
 
     def set_chunk_words(self, n):
         _lib.check(_lib.load().lrpcap_encoder_set_chunk_words(self.handle(), int(n)))
+
+    def profile(self, enable=True):
+        _lib.check(_lib.load().lrpcap_encoder_profile(self.handle(), int(bool(enable))))
+
+    def profile_read(self):
+        """{class: (ms, algorithmic FLOPs, launches)} for classes tc_bwd / tc_fwd / simt; resets the counters."""
+        out = np.zeros(9, dtype=np.float64)
+        _lib.check(_lib.load().lrpcap_encoder_profile_read(self.handle(), _lib.dptr(out)))
+        return {k: tuple(out[3 * i:3 * i + 3]) for i, k in enumerate(("tc_bwd", "tc_fwd", "simt"))}
 
     def launches(self):
         return int(_lib.load().lrpcap_encoder_launches(self.handle()))

@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/decoder_<kind>.npz by executing the REFERENCE's own NumPy decoder
+(/root/reference/models/explainers.py, imported under the Keras stub of oracle/refstub.py) on seeded synthetic weights.
+Run in the build container (the reference tree does not exist on the GPU box):
+
+    python oracle/make_golden.py
+
+Stored per kind: the weights/inputs and, for every word t, the reference's feature relevance, attention, r_words
+(LRP classes) and decoder gradient (Gradient classes), plus the forward logits.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lrp_imagecaptioning_b200 import synth  # noqa: E402
+from oracle import refstub  # noqa: E402
+
+CFG = dict(V=30, H=16, E=16, D=24, L=9, T=5)
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for kind in ("adaptive", "gridtd"):
+        dec = synth.decoder_weights(kind, V=CFG["V"], H=CFG["H"], E=CFG["E"], D=CFG["D"], seed=41)
+        F = synth.features(1, L=CFG["L"], D=CFG["D"], seed=42)[0]
+        cap = [int(c) for c in synth.captions(1, CFG["T"], CFG["V"], seed=43)[0]]
+        store = {"F": F, "caption": np.array(cap, dtype=np.int32)}
+        for k, v in dec.items():
+            if isinstance(v, np.ndarray):
+                store["w_" + k] = v
+        ref = refstub.make_reference_explainer(kind, "lrp", dec, F)
+        ref._forward_beam_search((None, None), cap)
+        store["logits"] = np.asarray(ref.caption_preds, dtype=np.float64)
+        for t in range(1, CFG["T"] + 1):
+            r, att = ref._explain_lstm_single_word_sequence(t)
+            store["lrp_R_%d" % t] = np.asarray(r)
+            store["lrp_att_%d" % t] = np.asarray(att, dtype=np.float64)
+            store["lrp_rwords_%d" % t] = np.asarray(ref.r_words, dtype=np.float64)
+        refg = refstub.make_reference_explainer(kind, "gradient", dec, F)
+        refg._forward_beam_search((None, None), cap)
+        for t in range(1, CFG["T"] + 1):
+            store["grad_R_%d" % t] = np.asarray(refg._lstm_decoder_backward(t))
+            store["grad_rwords_%d" % t] = np.asarray(refg.r_words, dtype=np.float64)
+        path = os.path.join(out_dir, "decoder_%s.npz" % kind)
+        np.savez_compressed(path, **store)
+        print(path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,104 @@
+"""CPU: host-side mirror of the reference interfaces (parameter validation, registries, sharding, weight files)."""
+import numpy as np
+import pytest
+import torch
+
+
+def _image_model():
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.encoder import ImageModel
+    return ImageModel(synth.vgg16_weights(0), image_hw=32, precision="fp32")
+
+
+def test_analyzer_registry_and_parameter_errors():
+    """Same names and ValueErrors as innvestigate (analyzer/__init__.py:35-99, relevance_based/utils.py:52-129)."""
+    from lrp_imagecaptioning_b200 import analyzers as A
+    m = _image_model()
+    for name in ("lrp.epsilon", "lrp.z", "lrp.alpha_beta", "lrp.alpha_1_beta_0", "lrp.alpha_2_beta_1", "lrp.z_plus",
+                 "lrp.z_plus_fast", "lrp.sequential_preset_a", "gradient", "input_t_gradient", "guided_backprop"):
+        assert name in A.analyzers
+    with pytest.raises(ValueError):
+        A.create_analyzer("lrp.epsilon", m, epsilon=0)
+    with pytest.raises(ValueError):
+        A.LRPAlphaBeta(m)
+    with pytest.raises(ValueError):
+        A.LRPAlphaBeta(m, alpha=0.5)
+    with pytest.raises(ValueError):
+        A.LRPAlphaBeta(m, alpha=2, beta=0.5)
+    with pytest.raises(ValueError):
+        A.Gradient(m, neuron_selection_mode="bogus")
+    with pytest.raises(ValueError):
+        A.Gradient(m, postprocess="cube")
+    a = A.LRPAlphaBeta(m, beta=1)
+    assert (a._alpha, a._beta) == (2, 1)
+    r = A.LRPSequentialPresetA(m, epsilon=0.01, neuron_selection_mode="replace")._rule()
+    assert (r.alpha, r.beta, r.bias) == (1.0, 0.0, True)
+    with pytest.raises(A.NotAnalyzeableModelException):
+        A.LRPEpsilon(object())
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from lrp_imagecaptioning_b200 import _lib, synth
+    from lrp_imagecaptioning_b200.analyzers import LRPEpsilon
+    m = _image_model()
+    with pytest.raises(_lib.LrpcapError):
+        LRPEpsilon(m, epsilon=0.01).analyze([synth.images(1, 32), np.zeros((1, 2, 2, 512), np.float32)])
+
+
+def test_image_model_shape_checks():
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.encoder import ImageModel
+    w = synth.vgg16_weights(0)
+    with pytest.raises(ValueError):
+        ImageModel(w[:12])
+    bad = list(w)
+    bad[3] = (bad[3][0][..., :5], bad[3][1])
+    with pytest.raises(ValueError):
+        ImageModel(bad)
+
+
+def test_shard_images_partitions_everything_once():
+    from lrp_imagecaptioning_b200.engine import shard_images, word_list
+    for n in (0, 1, 7, 64, 513):
+        for ws in (1, 2, 3, 8):
+            parts = [shard_images(n, r, ws) for r in range(ws)]
+            assert np.array_equal(np.concatenate(parts), np.arange(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    wi, wt = word_list(3, 4, lengths=[2, 0, 4])
+    assert list(wi) == [0, 0, 2, 2, 2, 2] and list(wt) == [1, 2, 1, 2, 3, 4]
+    with pytest.raises(ValueError):
+        shard_images(4, 2, 2)
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_weight_file_roundtrip_uses_keras_names(kind, tmp_path):
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.model import CaptioningModel, ADAPTIVE_LAYER, GRIDTD_LAYER
+    vgg = synth.vgg16_weights(0)
+    dec = synth.decoder_weights(kind, V=50, H=16, E=16, D=512, seed=1)
+    m = CaptioningModel(kind, vgg, dec, image_hw=32, precision="fp32")
+    sd = m.state_dict()
+    assert "block5_conv3/kernel" in sd and "image_features/kernel" in sd and "embedding_1/embeddings" in sd
+    assert ((ADAPTIVE_LAYER if kind == "adaptive" else GRIDTD_LAYER) + "/recurrent_kernel") in sd
+    p = str(tmp_path / "w.npz")
+    m.save_weights(p)
+    dec2 = synth.decoder_weights(kind, V=50, H=16, E=16, D=512, seed=99)
+    m2 = CaptioningModel(kind, synth.vgg16_weights(5), dec2, image_hw=32, precision="fp32").load_weights(p)
+    for k, v in m.state_dict().items():
+        assert np.array_equal(m2.state_dict()[k], v)
+    assert (m2.L, m2.D, m2._hidden_dim, m2._embedding_dim, m2.img_encoder) == (4, 512, 16, 16, "vgg16")
+
+
+def test_explainer_classes_exist_with_reference_signatures():
+    import inspect
+    from lrp_imagecaptioning_b200 import explainers as E
+    for name in ("ExplainImgCaptioningAdaptiveAttention", "ExplainImgCaptioningAdaptiveAttentionGradient",
+                 "ExplainImgCaptioningAdaptiveAttentionInputTimesGradient", "ExplainImgCaptioningAdaptiveAttentionGuidedGradcam",
+                 "ExplainImgCaptioningGridTDModel", "ExplainImgCaptioningGridTDGradient",
+                 "ExplainImgCaptioningGridTDGradientTimesInput", "ExplainImgCaptioningGridTDGuidedGradcam"):
+        cls = getattr(E, name)
+        assert list(inspect.signature(cls.__init__).parameters)[:5] == ["self", "model", "weight_path", "dataset_provider", "max_caption_length"]
+        for meth in ("_forward_beam_search", "_explain_sentence", "_explain_CNN", "_beam_search"):
+            assert hasattr(cls, meth)
+    assert E.EPS == 0.01

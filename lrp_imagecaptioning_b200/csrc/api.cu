@@ -137,19 +137,20 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
     EpiParams ep;
     ep.mode = EPI_RAW;
     ep.out_f32 = dO.as<float>();
-    if (precision == PREC_BF16X3_TC) {
-      LRPCAP_TRY(sA.ensure(nA * 4));
-      LRPCAP_TRY(sB.ensure(nB * 4));
-      LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0));
-      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps));
+    if (precision == PREC_BF16X3_TC || precision == 2) {   // 2: three bf16 planes (the forward pass's arithmetic)
+      const int planes = precision == 2 ? 3 : 2;
+      LRPCAP_TRY(sA.ensure(nA * 2 * planes));
+      LRPCAP_TRY(sB.ensure(nB * 2 * planes));
+      LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0, planes));
+      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps, planes));
       TcConvArgs a;
       a.A = sA.p; a.A_elems = nA; a.n_items = items; a.H = H; a.W = W; a.C = C;
-      a.B = sB.p; a.B_elems = nB; a.taps = taps; a.Nout = Nout; a.epi = ep;
+      a.B = sB.p; a.B_elems = nB; a.taps = taps; a.Nout = Nout; a.planes = planes; a.epi = ep;
       LRPCAP_TRY(tc_conv_launch(a, 0));
     } else {
       SimtConvArgs a;
       a.A = dA.as<float>(); a.n_items = items; a.H = H; a.W = W; a.C = C;
-      a.B = dB.as<float>(); a.taps = taps; a.Nout = Nout; a.split_out = false; a.epi = ep;
+      a.B = dB.as<float>(); a.taps = taps; a.Nout = Nout; a.out_planes = 0; a.epi = ep;
       LRPCAP_TRY(simt_conv_launch(a, 0));
     }
     LRPCAP_CUDA(cudaDeviceSynchronize());

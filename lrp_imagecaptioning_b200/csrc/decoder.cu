@@ -1,6 +1,9 @@
 // Decoder: batched forward with stored state + batched word-level relevance (see decoder.cuh).
 #include "decoder.cuh"
 #include "decoder_kernels.cuh"
+#include "tc_conv.cuh"
+#include <cmath>
+#include <cstdlib>
 #include "../../include/lrpcap.h"
 #include <algorithm>
 #include <numeric>
@@ -18,7 +21,7 @@ Decoder::~Decoder() {
   DevBuf* bufs[] = {&F_, &Vp_, &P_, &a_, &gp_, &tok_, &logitk_, &logits_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_,
                     &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
                     &Z_, &hp_, &sg_, &sp_, &e_, &hc_, &d_wimg_, &d_wt_, &d_order_, &Rh1_, &Rh2_, &Rh2n_, &Rc1_, &Rc2_,
-                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_};
+                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_};
   for (DevBuf* b : bufs) b->release();
 }
 
@@ -86,6 +89,7 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
     UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat1_));
     UP(d->upload(w->lstm_b, 4 * H, &d->b1_));
     UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, true, &d->Wgate1T_));
+    UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, true, &d->Wcat1T_));
     UP(d->upload(w->Wv, (size_t)H * H, &d->Wp_));
     UP(d->upload(w->Wg, (size_t)H * H, &d->Whp_));
     UP(d->upload_cat(w->Wx, 2 * E, w->Wh, H, H, 0, H, false, &d->Wsx_));
@@ -97,14 +101,36 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
     UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat1_));
     UP(d->upload(w->td_b, 4 * H, &d->b1_));
     UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, true, &d->Wgate1T_));
+    UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, true, &d->Wcat1T_));
     UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat2_));
     UP(d->upload(w->lang_b, 4 * H, &d->b2_));
     UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, true, &d->Wgate2T_));
+    UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, true, &d->Wcat2T_));
     UP(d->upload(w->W_va, (size_t)H * H, &d->Wp_));
     UP(d->upload(w->W_ha, (size_t)H * H, &d->Whp_));
     UP(d->upload_cat(w->W_x, H + 2 * E, w->W_h, H, H, 0, H, false, &d->Wsx_));
     UP(d->upload(w->W_s, (size_t)H * H, &d->Wss_));
     UP(d->upload(w->W_a, H, &d->Va_));
+  }
+  if (H % 64 == 0 && D % 64 == 0 && !getenv("LRPCAP_DECODER_FP64_GEMM")) {
+    // B operand of the [words*L, H] x [H, D] relevance GEMM: B[d][h] = W_if[d][h] -- the Keras (D, H) layout as is
+    const size_t n = (size_t)D * H;
+    std::vector<__nv_bfloat16> sp(2 * n);
+    for (size_t i = 0; i < n; ++i) {
+      const float v = w->image_features_w[i];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      sp[i] = hi;
+      sp[n + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, 2 * n * sizeof(__nv_bfloat16)) != cudaSuccess ||
+        cudaMemcpy(p, sp.data(), 2 * n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_last_error("decoder_create: device allocation failed");
+      return fail(kErrCuda);
+    }
+    d->owned_.push_back(p);
+    d->WifTC_ = p;
+    d->tc_features_ = true;
   }
 #undef UP
   *out = d;
@@ -115,7 +141,24 @@ int Decoder::gemm(const double* A, int lda, const double* B, int ldb, double* C,
                   const double* bias, cudaStream_t s) {
   if (M <= 0) return kOk;
   dim3 grid(nblk(N, GN), nblk(M, GM));
-  dgemm_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, bias);
+  const int blocks = (int)(grid.x * grid.y);
+  int splits = 1;
+  if (blocks < 148 && K >= 256) {   // skinny (decoder forward, M = #images): spread K over the SMs
+    splits = (296 + blocks - 1) / blocks;
+    if (splits > K / 64) splits = K / 64;
+  }
+  if (splits > 1) {
+    const int kper = ((K + splits - 1) / splits + GK - 1) / GK * GK;
+    splits = (K + kper - 1) / kper;
+    LRPCAP_TRY(gemm_ws_.ensure((size_t)splits * M * N * 8));
+    grid.z = splits;
+    dgemm_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, gemm_ws_.as<double>(), N, M, N, K, nullptr, kper);
+    splitk_reduce_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(gemm_ws_.as<double>(), splits, C, ldc, M, N, bias);
+    launches_ += 2;
+    LRPCAP_CUDA(cudaGetLastError());
+    return kOk;
+  }
+  dgemm_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, K);
   ++launches_;
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
@@ -246,6 +289,29 @@ int Decoder::attention(float* h_alpha, float* h_beta) {
   return kOk;
 }
 
+int Decoder::features_gemm(int m, cudaStream_t s) {
+  const int H = H_, D = D_, L = L_;
+  const int fh = (int)std::lround(std::sqrt((double)L));
+  if (tc_features_ && fh * fh == L) {
+    const size_t nA = (size_t)m * L * H, nO = (size_t)m * L * D;
+    LRPCAP_TRY(UVs_.ensure(nA * 4));
+    LRPCAP_TRY(YF32_.ensure(nO * 4));
+    __nv_bfloat16* hi = UVs_.as<__nv_bfloat16>();
+    f64_to_split_kernel<<<nblk(nA, 256), 256, 0, s>>>(UV_.as<double>(), hi, hi + nA, nA);
+    TcConvArgs a;
+    a.A = UVs_.p; a.A_elems = nA; a.n_items = m; a.H = fh; a.W = fh; a.C = H;
+    a.B = WifTC_; a.B_elems = (size_t)D * H; a.taps = 1; a.Nout = D;
+    a.epi.mode = EPI_RAW;
+    a.epi.out_f32 = YF32_.as<float>();
+    LRPCAP_TRY(tc_conv_launch(a, s));
+    f32_to_f64_kernel<<<nblk(nO, 256), 256, 0, s>>>(YF32_.as<float>(), YF_.as<double>(), nO);
+    launches_ += 3;
+    LRPCAP_CUDA(cudaGetLastError());
+    return kOk;
+  }
+  return gemm(UV_.as<double>(), H, WifT_, D, YF_.as<double>(), D, m * L, D, H, nullptr, s);
+}
+
 // Words sorted by position (descending) so that at time-step i the active words (t > i) are a prefix.
 int Decoder::sort_words(const int* h_word_img, const int* h_word_t, int W, cudaStream_t s) {
   LRPCAP_REQUIRE(N_ > 0, kErrState, "decoder: call decoder_forward first");
@@ -360,7 +426,7 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
     else
       uv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
                                                   UV_.as<double>(), T, L, H);
-    LRPCAP_TRY(gemm(UV_.as<double>(), H, WifT_, D, YF_.as<double>(), D, m * L, D, H, nullptr, s));
+    LRPCAP_TRY(features_gemm(m, s));
     final_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F_.as<double>(), ra_.as<double>(),
                                             YF_.as<double>(), d_R_head, L, D);
     launches_ += 2;
@@ -397,9 +463,88 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
   return kOk;
 }
 
-int Decoder::backward(const int*, const int*, int, float*, double*, cudaStream_t) {
-  set_last_error("decoder_backward: the frozen-attention gradient decoder is not built yet");
-  return kErrUnsupported;
+int Decoder::backward(const int* h_word_img, const int* h_word_t, int W, float* d_R_head, double* h_r_words,
+                      cudaStream_t s) {
+  LRPCAP_REQUIRE(d_R_head != nullptr, kErrInvalidArg, "decoder_backward: null output");
+  LRPCAP_TRY(sort_words(h_word_img, h_word_t, W, s));
+  const int H = H_, E = E_, D = D_, L = L_, T = T_;
+  const bool td = kind_ == LRPCAP_DECODER_GRIDTD;
+  const size_t WH = (size_t)W * H;
+  // buffer roles: Rh1_/Rh2_ = d_h1/d_h2, Rc1_/Rc2_ = d_c1/d_c2, U_ = gate gradients [W,4H], Rchat_ = d_c_hat seed,
+  // Rctx_ = d_h1 increment from the language LSTM, Q_ = d_ctx per step, Rglob_ = d_global, rword_ = d_words
+  DevBuf* rb[] = {&Rh1_, &Rc1_, &Rctx_, &Rh2_, &Rc2_, &Rchat_};
+  for (DevBuf* b : rb) {
+    LRPCAP_TRY(b->ensure(WH * 8));
+    LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, WH * 8, s));
+  }
+  LRPCAP_TRY(U_.ensure((size_t)W * std::max(4 * H, E) * 8));
+  LRPCAP_TRY(Rglob_.ensure((size_t)W * E * 8));
+  LRPCAP_TRY(rword_.ensure((size_t)W * T * 8));
+  LRPCAP_TRY(Y_.ensure((size_t)W * std::max(Kin1_, std::max(Kin2_, D)) * 8));
+  LRPCAP_TRY(ra_.ensure((size_t)W * D * 8));
+  LRPCAP_CUDA(cudaMemsetAsync(Rglob_.p, 0, (size_t)W * E * 8, s));
+  LRPCAP_CUDA(cudaMemsetAsync(rword_.p, 0, (size_t)W * T * 8, s));
+  if (td) LRPCAP_TRY(Q_.ensure((size_t)W * T * H * 8));
+  WordRef wr{d_wimg_.as<int>(), d_wt_.as<int>()};
+  const int* tok = tok_.as<int>();
+
+  grad_init_kernel<<<W, 256, 0, s>>>(wr, WoT_, tok, td ? Rh2_.as<double>() : Rh1_.as<double>(),
+                                     td ? Rchat_.as<double>() : nullptr, T, H);
+  ++launches_;
+  for (int i = T - 1; i >= 0; --i) {
+    const int na = nact_[i];
+    if (na == 0) continue;
+    if (!td) {
+      grad_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(),
+                                          c1_.as<double>(), Rh1_.as<double>(), nullptr, Rc1_.as<double>(), U_.as<double>(), T, H);
+      LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, 4 * H, nullptr, s));
+      grad_scatter_adaptive_kernel<<<na, 256, 0, s>>>(i, Y_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
+                                                      rword_.as<double>(), T, H, E);
+      launches_ += 2;
+    } else {
+      grad_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(),
+                                          c2_.as<double>(), Rh2_.as<double>(), nullptr, Rc2_.as<double>(), U_.as<double>(), T, H);
+      LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, 4 * H, nullptr, s));
+      grad_scatter_lang_kernel<<<na, 256, 0, s>>>(wr, i, Y_.as<double>(), beta_.as<double>(), Rchat_.as<double>(),
+                                                  Rctx_.as<double>(), Rh2_.as<double>(), Q_.as<double>(), T, H);
+      grad_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(),
+                                          c1_.as<double>(), Rh1_.as<double>(), Rctx_.as<double>(), Rc1_.as<double>(),
+                                          U_.as<double>(), T, H);
+      LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, 4 * H, nullptr, s));
+      grad_scatter_td_kernel<<<na, 256, 0, s>>>(i, Y_.as<double>(), Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
+                                                rword_.as<double>(), T, H, E);
+      launches_ += 4;
+    }
+  }
+  grad_glob_mask_kernel<<<W, 256, 0, s>>>(wr, Rglob_.as<double>(), gp_.as<double>(), E, td ? 0 : 1);
+  LRPCAP_TRY(gemm(Rglob_.as<double>(), E, WgfT_, D, ra_.as<double>(), D, W, D, E, nullptr, s));
+  ++launches_;
+  const int CH = std::min(W, 512);
+  LRPCAP_TRY(UV_.ensure(std::max((size_t)CH, (size_t)N_) * L * H * 8));
+  LRPCAP_TRY(YF_.ensure((size_t)CH * L * D * 8));
+  for (int p0 = 0; p0 < W; p0 += CH) {
+    const int m = std::min(CH, W - p0);
+    if (!td)
+      gv_adaptive_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), WoT_, tok,
+                                                    UV_.as<double>(), T, L, H);
+    else
+      gv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
+                                                  UV_.as<double>(), T, L, H);
+    LRPCAP_TRY(features_gemm(m, s));
+    grad_final_kernel<<<dim3(L, m), 256, 0, s>>>(p0, d_order_.as<int>(), ra_.as<double>(), YF_.as<double>(), d_R_head, L, D);
+    launches_ += 2;
+  }
+  LRPCAP_CUDA(cudaGetLastError());
+  if (h_r_words) {
+    LRPCAP_CUDA(cudaStreamSynchronize(s));
+    std::vector<double> rw((size_t)W * T);
+    LRPCAP_CUDA(cudaMemcpy(rw.data(), rword_.p, rw.size() * 8, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < W; ++p) {
+      double* o = h_r_words + (size_t)order_[p] * T;
+      for (int j = 0; j < T; ++j) o[j] = (j < wt_[p]) ? rw[(size_t)p * T + j] : 0.0;   // raw sums (explainers.py:831, 1527)
+    }
+  }
+  return kOk;
 }
 
 }  // namespace lrpcap

@@ -47,17 +47,22 @@ class Decoder {
                  double** out);
   int gemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
            const double* bias, cudaStream_t s);
+  int features_gemm(int m, cudaStream_t s);   // YF_[m*L, D] = UV_[m*L, H] * W_if^T (tensor cores when shapes allow)
   int sort_words(const int* h_word_img, const int* h_word_t, int n_words, cudaStream_t s);
 
   int kind_ = 0, V_ = 0, H_ = 0, E_ = 0, D_ = 0, L_ = 0, N_ = 0, T_ = 0, sos_ = 1, keras_logits_ = 0;
   int Kin1_ = 0, Kin2_ = 0;   // LSTM input widths incl. recurrent part (adaptive: Kin1 = 2E+H)
   long long launches_ = 0;
+  bool tc_features_ = false;
+  void* WifTC_ = nullptr;   // split-bf16 [D][H]: K-major B operand of the image_features relevance GEMM
+  DevBuf UVs_, YF32_, gemm_ws_;
   std::vector<void*> owned_;
   // weights (fp64, device)
   double *Wif_ = nullptr, *bif_ = nullptr, *WifT_ = nullptr, *Wgf_ = nullptr, *bgf_ = nullptr, *WgfT_ = nullptr;
   double *Emb_ = nullptr, *Wo_ = nullptr, *WoT_ = nullptr, *bo_ = nullptr;
   double *Wcat1_ = nullptr, *b1_ = nullptr, *Wcat2_ = nullptr, *b2_ = nullptr;     // [x;h] -> 4H
   double *Wgate1T_ = nullptr, *Wgate2T_ = nullptr;                                 // g-gate slice, transposed [H, Kin]
+  double *Wcat1T_ = nullptr, *Wcat2T_ = nullptr;                                   // [4H, Kin] for the gradient decoder
   double *Wp_ = nullptr, *Whp_ = nullptr, *Wsx_ = nullptr, *Wss_ = nullptr, *Va_ = nullptr;
   // forward state
   DevBuf F_, Vp_, P_, a_, gp_, tok_, logitk_, logits_;

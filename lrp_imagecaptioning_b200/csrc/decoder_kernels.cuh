@@ -16,18 +16,23 @@ __device__ __forceinline__ double f32r(double x) { return (double)(float)x; }   
 constexpr int GM = 64, GN = 64, GK = 16;
 __global__ void __launch_bounds__(256)
 dgemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, double* __restrict__ C,
-             int ldc, int M, int N, int K, const double* __restrict__ bias) {
+             int ldc, int M, int N, int Ktot, const double* __restrict__ bias, int k_per_split) {
+  // blockIdx.z = K split: slice z covers [z*k_per_split, min(Ktot, (z+1)*k_per_split)) and writes partial sums to
+  // C + z*M*ldc (deterministic two-pass split-K for skinny problems; k_per_split == Ktot when not split)
   __shared__ double As[GK][GM + 1];
   __shared__ double Bs[GK][GN];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  const int kb = blockIdx.z * k_per_split;
+  const int K = (kb + k_per_split < Ktot) ? kb + k_per_split : Ktot;
+  C += (size_t)blockIdx.z * M * ldc;
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  for (int k0 = kb; k0 < K; k0 += GK) {
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -35,9 +40,9 @@ dgemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B
       const int mm = idx >> 4, kk = idx & 15;
       const int gm = m0 + mm, gk = k0 + kk;
       As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.0;
-      const int kb = idx >> 6, nn = idx & 63;  // 16 x 64
-      const int gn = n0 + nn, gkb = k0 + kb;
-      Bs[kb][nn] = (gn < N && gkb < K) ? B[(size_t)gkb * ldb + gn] : 0.0;
+      const int kr = idx >> 6, nn = idx & 63;  // 16 x 64
+      const int gn = n0 + nn, gkb = k0 + kr;
+      Bs[kr][nn] = (gn < N && gkb < K) ? B[(size_t)gkb * ldb + gn] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -65,6 +70,16 @@ dgemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B
   }
 }
 
+__global__ void splitk_reduce_kernel(const double* __restrict__ ws, int splits, double* __restrict__ C, int ldc, int M,
+                                     int N, const double* __restrict__ bias) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  const int m = i / N, n = i - (size_t)m * N;
+  double acc = 0.0;
+  for (int z = 0; z < splits; ++z) acc += ws[((size_t)z * M + m) * N + n];
+  C[(size_t)m * ldc + n] = acc + (bias ? bias[n] : 0.0);
+}
+
 // ------------------------------------------------------------------ forward: per-image features
 __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,6 +93,15 @@ __global__ void mean_feat_kernel(const double* __restrict__ F, double* __restric
     for (int l = 0; l < L; ++l) s += F[((size_t)n * L + l) * D + d];
     a[(size_t)n * D + d] = f32r(s / L);
   }
+}
+__global__ void f64_to_split_kernel(const double* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  __nv_bfloat16 h, l;
+  split_bf16((float)in[i], h, l);
+  hi[i] = h;
+  lo[i] = l;
 }
 __global__ void round_f32_kernel(double* x, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,6 +494,156 @@ __global__ void final_kernel(WordRef w, int p0, const int* __restrict__ order, c
     const float first = (float)(f[d] / L * ra[(size_t)p * D + d]);
     o[d] = (float)((double)first + f[d] * yf[d]);
   }
+}
+
+// ------------------------------------------------------------------ frozen-attention gradient decoder
+// (explainers.py:780-832 adaptive, :1452-1532 grid-TD).  The reference keeps d_h / d_c / gate gradients in float32
+// arrays; f32r() reproduces those stores.
+
+// d_h[t] = d_(h+c_hat) = W_o[:, k]; grid-TD also seeds d_c_hat[t-1] with it.
+__global__ void grad_init_kernel(WordRef w, const double* __restrict__ WoT, const int* __restrict__ tok,
+                                 double* __restrict__ dh, double* __restrict__ dchat_init, int T, int H) {
+  const int p = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const int k = tok[n * T + t - 1] - 1;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const double v = WoT[(size_t)k * H + j];
+    dh[(size_t)p * H + j] = f32r(v);
+    if (dchat_init) dchat_init[(size_t)p * H + j] = v;
+  }
+}
+// One LSTM BPTT step (explainers.py:811-821): gates = [d_i, d_f, d_g, d_o] pre-activation gradients, dc <- d_c[i].
+__global__ void grad_cell_kernel(WordRef w, int i, const double* __restrict__ ia, const double* __restrict__ fa,
+                                 const double* __restrict__ ga, const double* __restrict__ oa,
+                                 const double* __restrict__ c, const double* __restrict__ dh, const double* __restrict__ dh_add,
+                                 double* __restrict__ dc, double* __restrict__ gates, int T, int H) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  const size_t s0 = ((size_t)n * (T + 1) + i) * H, s1 = s0 + H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const size_t q = (size_t)p * H + j;
+    const double dhv = dh_add ? f32r(dh[q] + dh_add[q]) : dh[q];
+    const double th = tanh(c[s1 + j]);
+    const double i_ = ia[s1 + j], f_ = fa[s1 + j], g_ = ga[s1 + j], o_ = oa[s1 + j];
+    const double d_oa = f32r(dhv * th);
+    const double dcn = f32r(dc[q] + dhv * o_ * (1.0 - th * th));
+    const double d_fa = f32r(dcn * c[s0 + j]);
+    const double d_ia = f32r(dcn * g_);
+    const double d_ga = f32r(dcn * i_);
+    dc[q] = f32r(dcn * f_);
+    double* gt = gates + (size_t)p * 4 * H;
+    gt[j] = f32r(d_ia * i_ * (1.0 - i_));
+    gt[H + j] = f32r(d_fa * f_ * (1.0 - f_));
+    gt[2 * H + j] = f32r(d_ga * (1.0 - g_ * g_));
+    gt[3 * H + j] = f32r(d_oa * o_ * (1.0 - o_));
+  }
+}
+// adaptive: Yg = gates [W_i ; W_h]^T -> d_x (float32 store) and d_h (explainers.py:822-825)
+__global__ void __launch_bounds__(256)
+grad_scatter_adaptive_kernel(int i, const double* __restrict__ Yg, double* __restrict__ dh, double* __restrict__ dglob,
+                             double* __restrict__ dwords, int T, int H, int E) {
+  const int p = blockIdx.x;
+  const int Kin = 2 * E + H;
+  const double* y = Yg + (size_t)p * Kin;
+  double wsum = 0.0;
+  for (int j = threadIdx.x; j < Kin; j += 256) {
+    const double v = f32r(y[j]);
+    if (j < E) wsum += v;
+    else if (j < 2 * E) dglob[(size_t)p * E + j - E] += v;
+    else dh[(size_t)p * H + j - 2 * E] = v;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = wsum;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dwords[(size_t)p * T + i] = red[0];
+}
+// grid-TD language LSTM input split (explainers.py:1501-1505): Y2 = gates2 [W_i2 ; W_h2]^T over [c_hat, h1, h2]
+//   d_c_hat[i] = (i == t-1 ? seed : 0) + Y2[:H]; d_ctx = d_c_hat (1 - beta_{i+1}) -> Q; dh1_add = Y2[H:2H]; dh2 = f32(Y2[2H:])
+__global__ void grad_scatter_lang_kernel(WordRef w, int i, const double* __restrict__ Y2, const double* __restrict__ beta,
+                                         const double* __restrict__ dchat_init, double* __restrict__ dh1_add,
+                                         double* __restrict__ dh2, double* __restrict__ Q, int T, int H) {
+  const int p = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const double* y = Y2 + (size_t)p * 3 * H;
+  const double b = beta[(size_t)n * (T + 1) + i + 1];
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    const size_t q = (size_t)p * H + j;
+    const double dchat = ((i == t - 1) ? dchat_init[q] : 0.0) + y[j];
+    Q[((size_t)p * T + i) * H + j] = dchat * (1.0 - b);
+    dh1_add[q] = y[H + j];
+    dh2[q] = f32r(y[2 * H + j]);
+  }
+}
+// grid-TD top-down LSTM input split (explainers.py:1517-1523): Y1 over [h2, g, emb, h1]
+__global__ void __launch_bounds__(256)
+grad_scatter_td_kernel(int i, const double* __restrict__ Y1, double* __restrict__ dh2, double* __restrict__ dh1,
+                       double* __restrict__ dglob, double* __restrict__ dwords, int T, int H, int E) {
+  const int p = blockIdx.x;
+  const int Kin = 2 * H + 2 * E;
+  const double* y = Y1 + (size_t)p * Kin;
+  double wsum = 0.0;
+  for (int j = threadIdx.x; j < Kin; j += 256) {
+    const double v = y[j];
+    if (j < H) dh2[(size_t)p * H + j] = f32r(dh2[(size_t)p * H + j] + v);
+    else if (j < H + E) dglob[(size_t)p * E + j - H] += v;
+    else if (j < H + 2 * E) wsum += v;
+    else dh1[(size_t)p * H + j - H - 2 * E] = f32r(v);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = wsum;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dwords[(size_t)p * T + i] = red[0];
+}
+// ReLU mask of the global feature: adaptive tests element 0 only (quirk B3, explainers.py:826); grid-TD element-wise (:1524)
+__global__ void grad_glob_mask_kernel(WordRef w, double* __restrict__ dglob, const double* __restrict__ gp, int E,
+                                      int scalar_test) {
+  const int p = blockIdx.x;
+  const int n = w.img[p];
+  for (int j = threadIdx.x; j < E; j += blockDim.x) {
+    const double ref = scalar_test ? gp[(size_t)n * E] : gp[(size_t)n * E + j];
+    if (ref <= 0.0) dglob[(size_t)p * E + j] = 0.0;
+  }
+}
+// d_V rows as the A operand of the image_features GEMM, masked where relu(Vp) <= 0
+__global__ void gv_adaptive_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
+                                   const double* __restrict__ WoT, const int* __restrict__ tok, double* __restrict__ UV,
+                                   int T, int L, int H) {
+  const int p = p0 + blockIdx.y, l = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const int k = tok[n * T + t - 1] - 1;
+  const double al = alpha[((size_t)n * (T + 1) + t) * L + l];
+  const double* vp = Vp + ((size_t)n * L + l) * H;
+  double* o = UV + ((size_t)blockIdx.y * L + l) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) o[j] = vp[j] > 0.0 ? f32r(WoT[(size_t)k * H + j] * al) : 0.0;
+}
+__global__ void gv_gridtd_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
+                                 const double* __restrict__ Q, double* __restrict__ UV, int T, int L, int H) {
+  const int p = p0 + blockIdx.y, l = blockIdx.x;
+  const int n = w.img[p], t = w.t[p];
+  const double* vp = Vp + ((size_t)n * L + l) * H;
+  double* o = UV + ((size_t)blockIdx.y * L + l) * H;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    double acc = 0.0;
+    for (int i = t - 1; i >= 0; --i) acc += Q[((size_t)p * T + i) * H + j] * alpha[((size_t)n * (T + 1) + i + 1) * L + l];
+    o[j] = vp[j] > 0.0 ? acc : 0.0;
+  }
+}
+// d_F[word, l, :] = float32(d_a / L) (+) float32(d_V[l] W_if^T)   (explainers.py:828-830 / 1528-1530)
+__global__ void grad_final_kernel(int p0, const int* __restrict__ order, const double* __restrict__ da,
+                                  const double* __restrict__ YF, float* __restrict__ out, int L, int D) {
+  const int p = p0 + blockIdx.y, l = blockIdx.x;
+  const double* yf = YF + ((size_t)blockIdx.y * L + l) * D;
+  float* o = out + ((size_t)order[p] * L + l) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x)
+    o[d] = (float)((double)(float)(da[(size_t)p * D + d] / L) + (double)(float)yf[d]);
 }
 
 }  // namespace dk

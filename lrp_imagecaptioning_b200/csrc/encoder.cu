@@ -80,9 +80,10 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
   Layer& L = L_[l];
   if (!L.prepared[fmt][sign]) {
     void* p = nullptr;
-    LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * sizeof(float)));
+    LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * (fmt == WF_TC_FWD3 ? 6 : 4)));
     L.prepared[fmt][sign] = p;
-    LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, fmt, sign, s));
+    if (fmt == WF_TC_FWD3) LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, 3));
+    else LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, fmt, sign, s));
     ++launches_;
   }
   *out = L.prepared[fmt][sign];
@@ -98,7 +99,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
   ++launches_;
   const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
   if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
-  LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : WF_TC_FWD) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : WF_TC_FWD3) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
   ProfRec rec{};
   if (profile_) {
     LRPCAP_CUDA(cudaEventCreate(&rec.a));
@@ -112,12 +113,14 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     TcConvArgs a;
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout; a.taps = 9; a.Nout = Nout;
+    a.planes = backward ? 2 : 3;
     a.epi = epi;
     st = tc_conv_launch(a, s);
   } else {
     SimtConvArgs a;
     a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
-    a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout; a.split_out = split();
+    a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout;
+    a.out_planes = split() ? (backward ? 2 : 3) : 0;
     a.epi = epi;
     st = simt_conv_launch(a, s);
   }
@@ -172,7 +175,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
   LRPCAP_TRY(Mseed_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
   LRPCAP_TRY(F_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
   const int FC = n < kForwardChunk ? n : kForwardChunk;
-  const size_t act_bytes = (size_t)FC * hw_ * hw_ * 64 * sizeof(float);
+  const size_t act_bytes = (size_t)FC * hw_ * hw_ * 64 * (split() ? 6 : 4);
   for (auto& a : act_) LRPCAP_TRY(a.ensure(act_bytes));
 
   const bool ab = rule.kind == RULE_ALPHA_BETA, zpf = rule.kind == RULE_ZPLUS_FAST;
@@ -235,7 +238,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
           LRPCAP_TRY(make_posneg(img, posneg_.as<float>(), (size_t)m * hw_ * hw_, s));
           SimtConvArgs a;
           a.A = posneg_.as<float>(); a.n_items = m; a.H = hw_; a.W = hw_; a.C = 6;
-          a.B = w0_pm_; a.taps = 9; a.Nout = 64; a.split_out = split();
+          a.B = w0_pm_; a.taps = 9; a.Nout = 64; a.out_planes = fwd_planes();
           a.epi = ez;
           LRPCAP_TRY(simt_conv_launch(a, s));
           launches_ += 2;
@@ -247,7 +250,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
       if (L.pool_after) {
         int bp = 0;
         while (bp == bx || bp == by) ++bp;
-        LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, split(), act_[bp].p, (size_t)m * oe / 4, Gl, m, L.hw, L.hw, L.cout, s));
+        LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), act_[bp].p, (size_t)m * oe / 4, Gl, m, L.hw, L.hw, L.cout, s));
         ++launches_;
         X = act_[bp].p;
         X_elems = (size_t)m * oe / 4;

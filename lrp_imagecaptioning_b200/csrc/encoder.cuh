@@ -79,12 +79,16 @@ class Encoder {
     bool pool_after;
     float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
     float* bias = nullptr;    // device fp32 [cout]
-    void* prepared[4][3] = {};  // [WeightFormat][WeightSign]
+    void* prepared[5][3] = {};  // [WeightFormat][WeightSign]
   };
   int get_weights(int l, int fmt, int sign, void** out, cudaStream_t s);
   int conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const struct EpiParams& epi,
            cudaStream_t s);
   bool split() const { return precision_ == PREC_BF16X3_TC; }
+  // storage planes of forward activations: 3 bf16 planes (fp32-exact operands) in tensor-core mode, fp32 otherwise.
+  // The per-image forward decides ReLU signs / pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level
+  // errors downstream, while the per-word backward is insensitive to them.
+  int fwd_planes() const { return split() ? 3 : 0; }
   size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
 
   int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256;

@@ -13,7 +13,7 @@ inline unsigned grid_for(size_t n, int block) {
 
 // ------------------------------------------------------------------ weight preparation
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out_f32,
-                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int cin,
+                                    __nv_bfloat16* __restrict__ out_hi, int planes, int cin,
                                     int cout, int fmt, int sign, int taps) {
   const size_t total = (size_t)taps * cin * cout;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,10 +34,11 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
   if (fmt == WF_SIMT_FWD || fmt == WF_SIMT_BWD) {
     out_f32[idx] = v;
   } else {
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    out_hi[idx] = h;
-    out_lo[idx] = l;
+    for (int p = 0; p < planes; ++p) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out_hi[(size_t)p * total + idx] = h;
+      v -= __bfloat162float(h);
+    }
   }
 }
 
@@ -104,65 +105,73 @@ __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict
 }
 
 // ------------------------------------------------------------------ last transposed conv (C -> 3) + re-weighting
-constexpr int kLT = 16;   // tile side
-constexpr int kLC = 16;   // channel chunk
+// HBM-bound (12.85 MB in, 0.6 MB out per word at 224x224). Weights sit in constant memory so every FMA takes its
+// weight as a uniform constant operand; a thread owns two horizontally adjacent pixels and re-uses its 3x4 window.
+constexpr int kLTY = 16, kLTX = 32;   // tile (rows x cols), 256 threads x 2 pixels
+constexpr int kLC = 16;               // channel chunk staged in shared memory
+constexpr int kLastMaxC = 64;
+__constant__ float c_wlast[2][9 * kLastMaxC * 3];
 
 template <class ST, bool DUAL>
-__global__ void __launch_bounds__(kLT * kLT)
-last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* __restrict__ Wa,
-                  const float* __restrict__ Wb, const float* __restrict__ images, const int* __restrict__ img_index,
-                  float* __restrict__ out, int H, int W, int C, int tiles_x, int tiles_y, int mult) {
-  constexpr int PS = kLT + 2;
-  __shared__ float S[kLC][PS * PS + 1];
-  __shared__ float wa[9][kLC][3];
-  __shared__ float wb[DUAL ? 9 : 1][kLC][3];
+__global__ void __launch_bounds__(256)
+last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* __restrict__ images,
+                  const int* __restrict__ img_index, float* __restrict__ out, int H, int W, int C, int tiles_x,
+                  int tiles_y, int mult) {
+  constexpr int PSX = kLTX + 2, PSY = kLTY + 2;
+  __shared__ float S[kLC][PSX * PSY + 1];
 
   int bid = blockIdx.x;
   const int tiles = tiles_x * tiles_y;
   const int item = bid / tiles;
   bid -= item * tiles;
-  const int y0 = (bid / tiles_x) * kLT, x0 = (bid % tiles_x) * kLT;
+  const int y0 = (bid / tiles_x) * kLTY, x0 = (bid % tiles_x) * kLTX;
   const int tid = threadIdx.x;
-  const int ty = tid / kLT, tx = tid % kLT;
+  const int ty = tid >> 4, tx = (tid & 15) * 2;
 
-  float ca[3] = {0.f, 0.f, 0.f}, cb[3] = {0.f, 0.f, 0.f};
+  float ca[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, cb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
   for (int c0 = 0; c0 < C; c0 += kLC) {
     __syncthreads();
-    for (int idx = tid; idx < PS * PS * (kLC / 4); idx += kLT * kLT) {
-      const int k4 = idx % (kLC / 4);
-      const int pix = idx / (kLC / 4);
-      const int py = pix / PS, px = pix - py * PS;
+    for (int pix = tid; pix < PSX * PSY; pix += 256) {     // one halo pixel (16 channels = 4 x 16 B loads) per thread
+      const int py = pix / PSX, px = pix - py * PSX;
       const int gy = y0 + py - 1, gx = x0 + px - 1;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-        ST::template load<4>(msg, msg_elems, (((size_t)item * H + gy) * W + gx) * C + c0 + k4 * 4, v);
+      float v[kLC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) S[k4 * 4 + i][pix] = v[i];
-    }
-    for (int idx = tid; idx < 9 * kLC * 3; idx += kLT * kLT) {
-      const int ci = idx % 3;
-      const int k = (idx / 3) % kLC;
-      const int tap = idx / (3 * kLC);
-      wa[tap][k][ci] = __ldg(Wa + ((size_t)tap * C + c0 + k) * 3 + ci);
-      if (DUAL) wb[tap][k][ci] = __ldg(Wb + ((size_t)tap * C + c0 + k) * 3 + ci);
+      for (int i = 0; i < kLC; ++i) v[i] = 0.f;
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+        ST::template load<kLC>(msg, msg_elems, (((size_t)item * H + gy) * W + gx) * C + c0, v);
+#pragma unroll
+      for (int i = 0; i < kLC; ++i) S[i][pix] = v[i];
     }
     __syncthreads();
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int p = (ty + tap / 3) * PS + tx + tap % 3;
+    for (int k = 0; k < kLC; ++k) {
+      float win[3][4];
 #pragma unroll
-      for (int k = 0; k < kLC; ++k) {
-        const float sv = S[k][p];
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          ca[ci] = fmaf(sv, wa[tap][k][ci], ca[ci]);
-          if (DUAL) cb[ci] = fmaf(sv, wb[tap][k][ci], cb[ci]);
+        for (int q = 0; q < 4; ++q) win[r][q] = S[k][(ty + r) * PSX + tx + q];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float* wa = &c_wlast[0][(tap * C + c0 + k) * 3];
+        const float* wb = &c_wlast[1][(tap * C + c0 + k) * 3];
+#pragma unroll
+        for (int px = 0; px < 2; ++px) {
+          const float sv = win[tap / 3][tap % 3 + px];
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            ca[px][ci] = fmaf(sv, wa[ci], ca[px][ci]);
+            if (DUAL) cb[px][ci] = fmaf(sv, wb[ci], cb[px][ci]);
+          }
         }
       }
     }
   }
-  const int y = y0 + ty, x = x0 + tx;
-  if (y < H && x < W) {
+  const int y = y0 + ty;
+  if (y >= H) return;
+#pragma unroll
+  for (int px = 0; px < 2; ++px) {
+    const int x = x0 + tx + px;
+    if (x >= W) continue;
     const size_t pix = (size_t)y * W + x;
     float* o = out + ((size_t)item * H * W + pix) * 3;
     if (mult) {
@@ -171,11 +180,11 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) {
         const float xv = __ldg(xi + ci);
-        o[ci] = DUAL ? (xv >= 0.f ? xv * ca[ci] : xv * cb[ci]) : xv * ca[ci];
+        o[ci] = DUAL ? (xv >= 0.f ? xv * ca[px][ci] : xv * cb[px][ci]) : xv * ca[px][ci];
       }
     } else {
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) o[ci] = ca[ci];
+      for (int ci = 0; ci < 3; ++ci) o[ci] = ca[px][ci];
     }
   }
 }
@@ -191,13 +200,15 @@ __global__ void posneg_kernel(const float* __restrict__ x, float* __restrict__ o
   }
 }
 
-__global__ void f32_to_split_kernel(const float* __restrict__ in, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t n) {
+__global__ void f32_to_split_kernel(const float* __restrict__ in, __nv_bfloat16* hi, int planes, size_t n) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
-  __nv_bfloat16 h, l;
-  split_bf16(in[idx], h, l);
-  hi[idx] = h;
-  lo[idx] = l;
+  float v = in[idx];
+  for (int p = 0; p < planes; ++p) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[(size_t)p * n + idx] = h;
+    v -= __bfloat162float(h);
+  }
 }
 __global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                     float* out, size_t n) {
@@ -208,20 +219,23 @@ __global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const 
 
 }  // namespace
 
-int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps) {
+int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps,
+                 int planes) {
   const size_t total = (size_t)taps * cin * cout;
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out);
-  prep_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, reinterpret_cast<float*>(out), hi, hi + total, cin,
-                                                           cout, fmt, sign, taps);
+  prep_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, reinterpret_cast<float*>(out), hi, planes, cin, cout,
+                                                           fmt, sign, taps);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 
-int pool_mask(const void* act, size_t act_elems, bool split, void* pooled, size_t pooled_elems, float* G, int items,
+int pool_mask(const void* act, size_t act_elems, int planes, void* pooled, size_t pooled_elems, float* G, int items,
               int H, int W, int C, cudaStream_t s) {
   LRPCAP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, kErrShape, "pool_mask: H, W must be even and C %% 4 == 0");
   const size_t total = (size_t)items * (H / 2) * (W / 2) * (C / 4);
-  if (split)
+  if (planes == 3)
+    pool_mask_kernel<StoreSplit3><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, items, H, W, C);
+  else if (planes == 2)
     pool_mask_kernel<StoreSplit><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, items, H, W, C);
   else
     pool_mask_kernel<StoreF32><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, items, H, W, C);
@@ -244,13 +258,17 @@ int seed_message(const float* R, const float* M, const int* img_index, void* msg
 
 int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, const float* Wb, const float* images,
                const int* img_index, float* out, int items, int H, int W, int C, int mult, cudaStream_t s) {
-  LRPCAP_REQUIRE(C % kLC == 0, kErrShape, "last_dgrad: C must be a multiple of %d", kLC);
-  const int tiles_x = ceil_div(W, kLT), tiles_y = ceil_div(H, kLT);
+  LRPCAP_REQUIRE(C % kLC == 0 && C <= kLastMaxC, kErrShape, "last_dgrad: C must be a multiple of %d and <= %d", kLC, kLastMaxC);
+  const int tiles_x = ceil_div(W, kLTX), tiles_y = ceil_div(H, kLTY);
   const long long blocks = (long long)items * tiles_x * tiles_y;
   LRPCAP_REQUIRE(blocks > 0 && blocks < (1ll << 31), kErrShape, "last_dgrad: grid out of range");
   const unsigned g = (unsigned)blocks;
+  const size_t wbytes = (size_t)9 * C * 3 * sizeof(float);
+  // stream-ordered refresh of the constant bank (one encoder stream at a time uses it)
+  LRPCAP_CUDA(cudaMemcpyToSymbolAsync(c_wlast, Wa, wbytes, 0, cudaMemcpyDeviceToDevice, s));
+  if (Wb) LRPCAP_CUDA(cudaMemcpyToSymbolAsync(c_wlast, Wb, wbytes, sizeof(float) * 9 * kLastMaxC * 3, cudaMemcpyDeviceToDevice, s));
 #define LRPCAP_LAUNCH_LAST(ST, DUAL) \
-  last_dgrad_kernel<ST, DUAL><<<g, kLT * kLT, 0, s>>>(msg, msg_elems, Wa, Wb, images, img_index, out, H, W, C, tiles_x, tiles_y, mult)
+  last_dgrad_kernel<ST, DUAL><<<g, 256, 0, s>>>(msg, msg_elems, images, img_index, out, H, W, C, tiles_x, tiles_y, mult)
   if (split) {
     if (Wb) LRPCAP_LAUNCH_LAST(StoreSplit, true); else LRPCAP_LAUNCH_LAST(StoreSplit, false);
   } else {
@@ -267,9 +285,9 @@ int make_posneg(const float* x, float* out, size_t pixels, cudaStream_t s) {
   return kOk;
 }
 
-int f32_to_split(const float* in, void* out, size_t n, cudaStream_t s) {
+int f32_to_split(const float* in, void* out, size_t n, cudaStream_t s, int planes) {
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out);
-  f32_to_split_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, hi, hi + n, n);
+  f32_to_split_kernel<<<grid_for(n, 256), 256, 0, s>>>(in, hi, planes, n);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }

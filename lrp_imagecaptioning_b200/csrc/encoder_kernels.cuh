@@ -9,16 +9,19 @@ enum WeightFormat : int {
   WF_SIMT_BWD = 1,  // fp32 [tap'][cout][cin], tap' = flipped (transposed conv)
   WF_TC_FWD = 2,    // split-bf16 [tap][cout][cin]           (K-major B operand of the forward GEMM)
   WF_TC_BWD = 3,    // split-bf16 [tap'][cin][cout]          (K-major B operand of the dgrad GEMM)
+  WF_TC_FWD3 = 4,   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
 };
 enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
 
 // w_hwio: device fp32 [3,3,cin,cout]. out: 9*cin*cout elements in `fmt`.
-int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps = 9);
+// planes: bf16 planes written for the tensor-core formats (2 or 3; ignored for the fp32 formats).
+int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps = 9,
+                 int planes = 2);
 
 // 2x2/2 max-pool of `act` [items,H,W,C] (storage-typed). If `pooled` != null writes [items,H/2,W/2,C];
 // if `G` != null zeroes every G entry that is not the first maximum of its window (TF MaxPoolGrad routing,
 // innvestigate relevance_analyzer.py:459-480).
-int pool_mask(const void* act, size_t act_elems, bool split, void* pooled, size_t pooled_elems, float* G, int items,
+int pool_mask(const void* act, size_t act_elems, int planes /*0 = fp32, 2, 3*/, void* pooled, size_t pooled_elems, float* G, int items,
               int H, int W, int C, cudaStream_t s);
 
 // msg[item] = (relu?)(R[item]) * M[img_index[item]]   ([items, hw, hw, C]); msg storage-typed.
@@ -35,7 +38,7 @@ int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, c
 // [x] (3 ch) -> [x+, x-] (6 ch), fp32 NHWC.
 int make_posneg(const float* x, float* out, size_t pixels, cudaStream_t s);
 
-int f32_to_split(const float* in, void* out, size_t n, cudaStream_t s);
+int f32_to_split(const float* in, void* out, size_t n, cudaStream_t s, int planes = 2);
 int split_to_f32(const void* in, float* out, size_t n, cudaStream_t s);
 
 }  // namespace lrpcap

@@ -61,14 +61,68 @@ struct StoreSplit {
     static_assert(NV % 4 == 0, "split storage moves 4 or 8 elements per vector");
     const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(base);
     const __nv_bfloat16* lo = hi + elems;
+    if constexpr (NV % 8 == 0) {
+#pragma unroll
+      for (int j = 0; j < NV / 8; ++j) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + off) + j);
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + off) + j);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[8 * j + 2 * i] = bf16lo_to_float(aw[i]) + bf16lo_to_float(bw[i]);
+          v[8 * j + 2 * i + 1] = bf16hi_to_float(aw[i]) + bf16hi_to_float(bw[i]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV / 4; ++j) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi + off) + j);
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(lo + off) + j);
+        v[4 * j + 0] = bf16lo_to_float(a.x) + bf16lo_to_float(b.x);
+        v[4 * j + 1] = bf16hi_to_float(a.x) + bf16hi_to_float(b.x);
+        v[4 * j + 2] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y);
+        v[4 * j + 3] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y);
+      }
+    }
+  }
+};
+
+struct StoreSplit3 {
+  template <int NV>
+  static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "split storage moves 4 elements per vector");
+    __nv_bfloat16* p0 = reinterpret_cast<__nv_bfloat16*>(base);
 #pragma unroll
     for (int j = 0; j < NV / 4; ++j) {
-      const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi + off) + j);
-      const uint2 b = __ldg(reinterpret_cast<const uint2*>(lo + off) + j);
-      v[4 * j + 0] = bf16lo_to_float(a.x) + bf16lo_to_float(b.x);
-      v[4 * j + 1] = bf16hi_to_float(a.x) + bf16hi_to_float(b.x);
-      v[4 * j + 2] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y);
-      v[4 * j + 3] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y);
+      uint32_t w[3][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float a = v[4 * j + 2 * i], b = v[4 * j + 2 * i + 1];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+          w[p][i] = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+          a -= __bfloat162float(ah);
+          b -= __bfloat162float(bh);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 3; ++p) reinterpret_cast<uint2*>(p0 + (size_t)p * elems + off)[j] = make_uint2(w[p][0], w[p][1]);
+    }
+  }
+  template <int NV>
+  static __device__ __forceinline__ void load(const void* base, size_t elems, size_t off, float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "split storage moves 4 elements per vector");
+    const __nv_bfloat16* p0 = reinterpret_cast<const __nv_bfloat16*>(base);
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(p0 + off) + j);
+      const uint2 b = __ldg(reinterpret_cast<const uint2*>(p0 + elems + off) + j);
+      const uint2 c = __ldg(reinterpret_cast<const uint2*>(p0 + 2 * elems + off) + j);
+      v[4 * j + 0] = bf16lo_to_float(a.x) + bf16lo_to_float(b.x) + bf16lo_to_float(c.x);
+      v[4 * j + 1] = bf16hi_to_float(a.x) + bf16hi_to_float(b.x) + bf16hi_to_float(c.x);
+      v[4 * j + 2] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y) + bf16lo_to_float(c.y);
+      v[4 * j + 3] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y) + bf16hi_to_float(c.y);
     }
   }
 };

@@ -124,10 +124,10 @@ int simt_conv_launch(const SimtConvArgs& a, cudaStream_t stream) {
   LRPCAP_REQUIRE(a.taps == 9 || a.taps == 1, kErrShape, "simt_conv: taps must be 1 or 9");
   LRPCAP_REQUIRE(a.n_items > 0 && a.H > 0 && a.W > 0 && a.C > 0, kErrShape, "simt_conv: empty problem");
   LRPCAP_REQUIRE(a.Nout > 0 && a.Nout % 4 == 0, kErrShape, "simt_conv: Nout=%d must be a multiple of 4", a.Nout);
-  if (a.split_out) LRPCAP_REQUIRE(a.Nout % 8 == 0, kErrShape, "simt_conv: split output needs Nout %% 8 == 0");
   EpiDev e;
   LRPCAP_TRY(make_epi_dev(a.epi, &e));
-  if (a.split_out) return launch_mode<StoreSplit>(a, e, stream);
+  if (a.out_planes == 2) return launch_mode<StoreSplit>(a, e, stream);
+  if (a.out_planes == 3) return launch_mode<StoreSplit3>(a, e, stream);
   return launch_mode<StoreF32>(a, e, stream);
 }
 

@@ -5,15 +5,16 @@
 //   iNNvestigate GradientWRT on a conv layer  (innvestigate/layers.py:138-157 -> utils/keras/backend.py:58-60)
 // and, with taps == 1, the dense contractions of the decoder relevance (explainers.py:156-165).
 //
-// Structure per CTA (128 threads, one 128-pixel x BN-channel output tile):
-//   thread 0      : TMA producer. Per k-step (tap, 64-channel block) four cp.async.bulk.tensor loads
+// Structure per CTA (persistent, 192 threads, tiles of 128 pixels x BN channels):
+//   warp 0 lane 0 : TMA producer. Per k-step (tap, 64-channel block) four cp.async.bulk.tensor loads
 //                   (A_hi, A_lo as 4-D boxes shifted by the tap offset -- OOB rows/cols are zero-filled,
 //                   which *is* the 'same' padding -- and B_hi, B_lo as 2-D boxes), 128B-swizzled.
-//   thread 32     : MMA issuer. 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per k-step into one
-//                   TMEM accumulator (128 lanes x BN fp32 columns); tcgen05.commit frees the smem stage.
-//   all 4 warps   : epilogue. tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic -> global.
+//   warp 1 lane 0 : MMA issuer. 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per k-step into one
+//                   of two TMEM accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem stage.
+//   warps 2..9    : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic -> global.
 #include "epilogue.cuh"
 #include <cuda.h>
+#include <type_traits>
 
 namespace lrpcap {
 
@@ -21,7 +22,7 @@ namespace {
 
 constexpr int kBlockK = 64;                       // channels per k-step: 64 bf16 = 128 B = one swizzle row
 constexpr int kATileBytes = 128 * 128;            // 128 rows x 128 B
-constexpr uint32_t kSpinLimit = 1u << 26;
+constexpr uint64_t kWaitLimitNs = 4000000000ull;   // 4 s of wall clock on one barrier = protocol bug -> trap
 
 struct Geom {
   int H, W, TW, TH, tiles_x, tiles_y, cblocks, taps, Nout, n_items, n_tiles_n;
@@ -49,10 +50,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
+    if (global_ns() - t0 > kWaitLimitNs) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2,
@@ -124,130 +131,188 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-template <int BN>
+// NS = number of bf16 planes per operand: 2 -> products (0,0)(0,1)(1,0); 3 -> additionally (0,2)(2,0)(1,1).
+template <int BN, int NS>
 struct Cfg {
   static constexpr int kBTileBytes = BN * 128;
-  static constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;
-  static constexpr int kStages = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int kStageBytes = NS * kATileBytes + NS * kBTileBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes;
+  static_assert(kStages >= 2, "tile too large for a double-buffered shared-memory ring");
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+struct Maps {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
 };
 
 // ------------------------------------------------------------------ the kernel
-template <int BN, int MODE>
-__global__ void __launch_bounds__(128, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const Geom g,
-               const EpiDev e) {
-  using C = Cfg<BN>;
+// Persistent, warp-specialised: grid = #SMs, each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
+//   warp 0 (one lane) : TMA producer      -- smem ring runs across tile boundaries, never drains
+//   warp 1 (one lane) : MMA issuer        -- accumulators double-buffered in TMEM (2 x BN columns)
+//   warps 2..9        : epilogue          -- tcgen05.ld -> fused rule arithmetic -> global, overlapping the next tile's MMAs
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int item, x0, y0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN) {
+  TileCoord t;
+  const int n_tile = tile % g.n_tiles_n;
+  int m = tile / g.n_tiles_n;
+  const int tiles_per_item = g.tiles_x * g.tiles_y;
+  t.item = m / tiles_per_item;
+  m -= t.item * tiles_per_item;
+  t.x0 = (m % g.tiles_x) * g.TW;
+  t.y0 = (m / g.tiles_x) * g.TH;
+  t.n0 = n_tile * BN;
+  return t;
+}
+
+template <int BN, int MODE, int NS>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
+  using C = Cfg<BN, NS>;
+  using ST = typename std::conditional<NS == 3, StoreSplit3, StoreSplit>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* accum_bar = empty_bar + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* tfull_bar = empty_bar + C::kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
-
-  // tile coordinates: n-tile fastest, then spatial tile, then item
-  int bid = blockIdx.x;
-  const int n_tile = bid % g.n_tiles_n;
-  bid /= g.n_tiles_n;
-  const int tiles_per_item = g.tiles_x * g.tiles_y;
-  const int item = bid / tiles_per_item;
-  const int t_in = bid - item * tiles_per_item;
-  const int x0 = (t_in % g.tiles_x) * g.TW;
-  const int y0 = (t_in / g.tiles_x) * g.TH;
-  const int n0 = n_tile * BN;
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmA_hi);
-    prefetch_tmap(&tmA_lo);
-    prefetch_tmap(&tmB_hi);
-    prefetch_tmap(&tmB_lo);
+    for (int p = 0; p < NS; ++p) {
+      prefetch_tmap(&tm.a[p]);
+      prefetch_tmap(&tm.b[p]);
+    }
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], kEpiWarps);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_k = g.taps * g.cblocks;
-  const uint32_t stage_tx = 2u * (uint32_t)(g.TW * g.TH) * 128u + 2u * (uint32_t)C::kBTileBytes;
+  const uint32_t stage_tx = (uint32_t)NS * ((uint32_t)(g.TW * g.TH) * 128u + (uint32_t)C::kBTileBytes);
 
-  if (threadIdx.x == 0) {
-    // ---------------- TMA producer ----------------
-    for (int it = 0; it < num_k; ++it) {
-      const int s = it % C::kStages;
-      const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      uint8_t* st = smem + s * C::kStageBytes;
-      mbar_expect_tx(&full_bar[s], stage_tx);
-      const int tap = it / g.cblocks;
-      const int cb = it - tap * g.cblocks;
-      int dy = 0, dx = 0;
-      if (g.taps == 9) {
-        dy = tap / 3 - 1;
-        dx = tap % 3 - 1;
-      }
-      tma_load_4d(&tmA_hi, st, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, item);
-      tma_load_4d(&tmA_lo, st + kATileBytes, &full_bar[s], cb * kBlockK, x0 + dx, y0 + dy, item);
-      tma_load_2d(&tmB_hi, st + 2 * kATileBytes, &full_bar[s], cb * kBlockK, tap * g.Nout + n0);
-      tma_load_2d(&tmB_lo, st + 2 * kATileBytes + C::kBTileBytes, &full_bar[s], cb * kBlockK, tap * g.Nout + n0);
-    }
-  } else if (threadIdx.x == 32) {
-    // ---------------- MMA issuer ----------------
-    constexpr uint32_t idesc = make_idesc(128, BN);
-    for (int it = 0; it < num_k; ++it) {
-      const int s = it % C::kStages;
-      const uint32_t ph = (uint32_t)(it / C::kStages) & 1u;
-      mbar_wait(&full_bar[s], ph);
-      tc_fence_after();
-      const uint32_t a_hi = smem_u32(smem + s * C::kStageBytes);
-      const uint64_t da_hi = make_desc_sw128(a_hi);
-      const uint64_t da_lo = make_desc_sw128(a_hi + kATileBytes);
-      const uint64_t db_hi = make_desc_sw128(a_hi + 2 * kATileBytes);
-      const uint64_t db_lo = make_desc_sw128(a_hi + 2 * kATileBytes + C::kBTileBytes);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(g, tile, BN);
+        for (int kk = 0; kk < num_k; ++kk, ++it) {
+          const uint32_t s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = smem + s * C::kStageBytes;
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          const int tap = kk / g.cblocks;
+          const int cb = kk - tap * g.cblocks;
+          int dy = 0, dx = 0;
+          if (g.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
 #pragma unroll
-      for (int k = 0; k < kBlockK / 16; ++k) {
-        const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
-        umma_bf16(tmem_base, da_hi + adv, db_hi + adv, idesc, (it | k) != 0 ? 1u : 0u);
-        umma_bf16(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
-        umma_bf16(tmem_base, da_lo + adv, db_hi + adv, idesc, 1u);
+          for (int p = 0; p < NS; ++p) {
+            tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], cb * kBlockK, tc.x0 + dx, tc.y0 + dy, tc.item);
+            tma_load_2d(&tm.b[p], st + NS * kATileBytes + p * C::kBTileBytes, &full_bar[s], cb * kBlockK,
+                        tap * g.Nout + tc.n0);
+          }
+        }
       }
-      umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
     }
-    umma_commit(accum_bar);        // accumulator complete
-  }
-  __syncwarp();
-
-  // ---------------- epilogue (all 4 warps; warp w owns TMEM lanes [32w, 32w+32)) ----------------
-  mbar_wait(accum_bar, 0);
-  tc_fence_after();
-
-  const int r = threadIdx.x;
-  const int ty = r / g.TW;
-  const int tx = r - ty * g.TW;
-  const int y = y0 + ty, x = x0 + tx;
-  const bool valid = (r < g.TW * g.TH) && (y < g.H) && (x < g.W);
-  const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = make_idesc(128, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1u;
+        mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kk = 0; kk < num_k; ++kk, ++it) {
+          const uint32_t s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + s * C::kStageBytes);
+          uint64_t da[NS], db[NS];
+#pragma unroll
+          for (int p = 0; p < NS; ++p) {
+            da[p] = make_desc_sw128(sbase + p * kATileBytes);
+            db[p] = make_desc_sw128(sbase + NS * kATileBytes + p * C::kBTileBytes);
+          }
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
+            umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, (kk | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, 1u);
+            umma_bf16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
+            if (NS == 3) {
+              umma_bf16(tmem_d, da[0] + adv, db[NS - 1] + adv, idesc, 1u);
+              umma_bf16(tmem_d, da[NS - 1] + adv, db[0] + adv, idesc, 1u);
+              umma_bf16(tmem_d, da[1] + adv, db[1] + adv, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+        }
+        umma_commit(&tfull_bar[buf]);  // accumulator of this tile complete
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (warp w owns TMEM lanes [32 (w % 4), +32)) ----------------
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int ty = r / g.TW;
+    const int tx = r - ty * g.TW;
+    const bool row_ok = r < g.TW * g.TH;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord tc = tile_coord(g, tile, BN);
+      const uint32_t buf = tl & 1u;
+      mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
+      tc_fence_after();
+      const int y = tc.y0 + ty, x = tc.x0 + tx;
+      const bool valid = row_ok && (y < g.H) && (x < g.W);
+      const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-  for (int c = 0; c < BN / 16; ++c) {
-    float v[16];
-    __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-    tmem_ld16(lane_base + (uint32_t)(c * 16), v);
-    if (valid) epi_apply<MODE, 16, StoreSplit>(e, g.H, g.W, g.Nout, item, y, x, n0 + c * 16, v);
+      for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
+        float v[16];
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+        tmem_ld16(lane_base + (uint32_t)(c * 16), v);
+        if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ------------------------------------------------------------------ host side
@@ -295,31 +360,48 @@ int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
   return kOk;
 }
 
-template <int BN, int MODE>
-int launch_t(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-             const Geom& g, const EpiDev& e, cudaStream_t stream) {
-  using C = Cfg<BN>;
+template <int BN, int MODE, int NS>
+int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  using C = Cfg<BN, NS>;
   static bool configured = false;
   if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
     configured = true;
   }
-  const long long blocks = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
-  LRPCAP_REQUIRE(blocks > 0 && blocks < (1ll << 31), kErrShape, "tc_conv: grid of %lld blocks out of range", blocks);
-  tc_conv_kernel<BN, MODE><<<(unsigned)blocks, 128, C::kSmemBytes, stream>>>(a_hi, a_lo, b_hi, b_lo, g, e);
+  const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
+  LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv: %lld tiles out of range", tiles);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LRPCAP_CUDA(cudaGetDevice(&dev));
+    LRPCAP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
+  tc_conv_kernel<BN, MODE, NS><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 
+// Instantiated combinations: 2 planes -> every epilogue, BN in {64,128,256}; 3 planes (forward / raw only) -> BN in {64,128}.
 template <int BN>
-int launch_mode(int mode, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                const CUtensorMap& b_lo, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+int launch_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  if (planes == 3) {
+    if constexpr (BN <= 128) {
+      switch (mode) {
+        case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 3>(tm, g, e, stream);
+        case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 3>(tm, g, e, stream);
+        case EPI_RAW: return launch_t<BN, EPI_RAW, 3>(tm, g, e, stream);
+      }
+    }
+    set_last_error("tc_conv: 3-plane operands support forward / raw epilogues with BN <= 128 only (mode %d, BN %d)", mode, BN);
+    return kErrUnsupported;
+  }
   switch (mode) {
-    case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE>(a_hi, a_lo, b_hi, b_lo, g, e, stream);
-    case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT>(a_hi, a_lo, b_hi, b_lo, g, e, stream);
-    case EPI_BWD: return launch_t<BN, EPI_BWD>(a_hi, a_lo, b_hi, b_lo, g, e, stream);
-    case EPI_RAW: return launch_t<BN, EPI_RAW>(a_hi, a_lo, b_hi, b_lo, g, e, stream);
+    case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 2>(tm, g, e, stream);
+    case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 2>(tm, g, e, stream);
+    case EPI_BWD: return launch_t<BN, EPI_BWD, 2>(tm, g, e, stream);
+    case EPI_RAW: return launch_t<BN, EPI_RAW, 2>(tm, g, e, stream);
   }
   set_last_error("tc_conv: unknown epilogue mode %d", mode);
   return kErrInvalidArg;
@@ -352,7 +434,8 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   LRPCAP_REQUIRE(a.Nout > 0 && a.Nout % 64 == 0, kErrShape, "tc_conv: Nout=%d must be a positive multiple of 64", a.Nout);
   LRPCAP_REQUIRE(a.taps == 9 || a.taps == 1, kErrShape, "tc_conv: taps must be 1 or 9");
   LRPCAP_REQUIRE(a.n_items > 0 && a.H > 0 && a.W > 0, kErrShape, "tc_conv: empty problem");
-  const int BN = (a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
+  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3, kErrInvalidArg, "tc_conv: planes must be 2 or 3");
+  const int BN = (a.planes == 2 && a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
   Geom g;
   g.H = a.H;
   g.W = a.W;
@@ -365,22 +448,23 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
 
-  const __nv_bfloat16* A_hi = reinterpret_cast<const __nv_bfloat16*>(a.A);
-  const __nv_bfloat16* B_hi = reinterpret_cast<const __nv_bfloat16*>(a.B);
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  LRPCAP_TRY(make_map_act(&ma_hi, A_hi, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
-  LRPCAP_TRY(make_map_act(&ma_lo, A_hi + a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
-  LRPCAP_TRY(make_map_w(&mb_hi, B_hi, a.taps * a.Nout, a.C, BN));
-  LRPCAP_TRY(make_map_w(&mb_lo, B_hi + a.B_elems, a.taps * a.Nout, a.C, BN));
+  const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
+  const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
+  Maps tm;
+  for (int pl = 0; pl < 3; ++pl) {
+    const int q = pl < a.planes ? pl : 0;   // unused third slot aliases plane 0
+    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)q * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
+    LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)q * a.B_elems, a.taps * a.Nout, a.C, BN));
+  }
 
   const EpiParams& p = a.epi;
   EpiDev e;
   LRPCAP_TRY(make_epi_dev(p, &e));
 
   switch (BN) {
-    case 256: return launch_mode<256>(p.mode, ma_hi, ma_lo, mb_hi, mb_lo, g, e, stream);
-    case 128: return launch_mode<128>(p.mode, ma_hi, ma_lo, mb_hi, mb_lo, g, e, stream);
-    default: return launch_mode<64>(p.mode, ma_hi, ma_lo, mb_hi, mb_lo, g, e, stream);
+    case 256: return launch_mode<256>(p.mode, a.planes, tm, g, e, stream);
+    case 128: return launch_mode<128>(p.mode, a.planes, tm, g, e, stream);
+    default: return launch_mode<64>(p.mode, a.planes, tm, g, e, stream);
   }
 }
 

@@ -53,6 +53,8 @@ struct TcConvArgs {
   const void* B = nullptr;  // split storage [taps * Nout, C]
   size_t B_elems = 0;
   int taps = 9, Nout = 0;
+  int planes = 2;           // bf16 planes of A, B and of the forward epilogue's activation tensors: 2 (hi, lo: 3 MMA
+                            // products, 16-bit operands) or 3 (hi, mid, lo: 6 products, fp32-exact operands; forward only)
   EpiParams epi;
 };
 
@@ -61,13 +63,12 @@ int tc_conv_launch(const TcConvArgs& args, cudaStream_t stream);
 
 // fp32 SIMT implicit-GEMM convolution with the same epilogues (exact-fp32 precision mode, and the
 // 3-channel first layer in both modes). A: fp32 [n_items, H, W, C]; B: fp32 [taps][C][Nout].
-// `split_out`: storage of out_act / out_msg / x_act (true = split-bf16 planes, false = fp32).
 struct SimtConvArgs {
   const float* A = nullptr;
   int n_items = 0, H = 0, W = 0, C = 0;
   const float* B = nullptr;
   int taps = 9, Nout = 0;
-  bool split_out = false;
+  int out_planes = 0;       // storage of out_act / out_msg / x_act: 0 = fp32, 2 or 3 = split-bf16 planes
   EpiParams epi;
 };
 int simt_conv_launch(const SimtConvArgs& args, cudaStream_t stream);

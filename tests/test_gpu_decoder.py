@@ -52,6 +52,35 @@ def test_decoder_lrp_matches_oracle(kind, size):
 
 
 @pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+@pytest.mark.parametrize("size", ["small", "full"])
+def test_decoder_gradient_matches_oracle(kind, size):
+    """_lstm_decoder_backward (manual BPTT, frozen attention; explainers.py:780-832, 1452-1532)."""
+    from lrp_imagecaptioning_b200.decoder import DecoderEngine
+    from oracle.decoder_ref import DecoderRef
+    cfg = SMALL if size == "small" else FULL
+    if kind == "adaptive" and cfg["E"] != cfg["H"]:
+        pytest.skip("the reference's adaptive gradient assumes E == H")
+    dec, F, cap = _setup(kind, cfg, seed=31)
+    eng = DecoderEngine(dec)
+    eng.forward(F, cap)
+    N, T = cfg["N"], cfg["T"]
+    wi = np.repeat(np.arange(N), T).astype(np.int32)
+    wt = np.tile(np.arange(1, T + 1), N).astype(np.int32)
+    R, rw = eng.backward(wi, wt)
+    R = R.cpu().numpy()
+    for n in range(N):
+        o = DecoderRef(dec).forward(F[n], list(cap[n]))
+        for t in range(1, T + 1):
+            w = n * T + t - 1
+            g = o.backward(t)
+            assert_parity(R[w], g.reshape(cfg["L"], cfg["D"]), "%s %s grad d_F img %d t %d" % (kind, size, n, t),
+                          sum_tol=None, kind=kind, size=size)
+            ref_rw = np.zeros(T)
+            ref_rw[:len(o.r_words)] = o.r_words
+            assert_parity(rw[w], ref_rw, "%s %s grad r_words img %d t %d" % (kind, size, n, t), sum_tol=None)
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
 def test_greedy_caption_is_oracle_argmax(kind):
     from lrp_imagecaptioning_b200.decoder import DecoderEngine
     from oracle.decoder_ref import DecoderRef

@@ -37,7 +37,7 @@ cases = [  # (items, H, W, C, Nout, taps)
     (1, 14, 14, 128, 256, 9), (1, 14, 14, 512, 512, 9), (3, 28, 28, 256, 256, 9), (1, 56, 56, 128, 64, 9),
     (1, 4, 4, 64, 128, 9), (1, 2, 2, 512, 512, 9), (2, 32, 32, 64, 64, 9), (5, 7, 7, 64, 64, 1), (1, 224, 224, 64, 64, 9),
 ]
-for prec, pname in ((_lib.PREC_FP32_SIMT, "simt"), (_lib.PREC_BF16X3_TC, "tc")):
+for prec, pname in ((_lib.PREC_FP32_SIMT, "simt"), (_lib.PREC_BF16X3_TC, "tc"), (2, "tc3")):
     for (items, H, W, C, Nout, taps) in cases:
         A = rng.standard_normal((items, H, W, C)).astype(np.float32)
         B = (rng.standard_normal((taps, C, Nout)) / np.sqrt(taps * C)).astype(np.float32)
@@ -71,6 +71,7 @@ try:
     B2 = (rng.standard_normal((9, 512, 64)) / 68.0).astype(np.float32)
     r2 = ref_conv(A2, B2, 9)
     report["precision_probe"] = {"tc": stats(_lib.debug_conv(_lib.PREC_BF16X3_TC, A2, B2, 9), r2),
+                                 "tc3": stats(_lib.debug_conv(2, A2, B2, 9), r2),
                                  "simt": stats(_lib.debug_conv(_lib.PREC_FP32_SIMT, A2, B2, 9), r2)}
 except Exception as e:  # noqa
     report["probe_error"] = repr(e)

@@ -138,6 +138,8 @@ def run_ours(args, rank, local_rank, world):
     model = CaptioningModel.synthetic("gridtd", vocab_size=VOCAB, image_hw=HW, seed=0, precision=args.precision, device=dev)
     eng = ExplainEngine(model, rule=RuleSpec(_lib.RULE_EPSILON, epsilon=0.01, bias=True))
     model.image_model.set_chunk_words(args.chunk_words)
+    if args.promote is not None:
+        model.image_model.set_promote(args.promote)
     x_host = torch.from_numpy(synth.images(N_IMG, HW, 100 + rank)).pin_memory()
     x_dev = x_host.to(dev)
     wi, wt = word_list(N_IMG, T_WORDS)
@@ -237,6 +239,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"])
     ap.add_argument("--chunk-words", type=int, default=640)
+    ap.add_argument("--promote", type=int, default=None, help="backward accumulator promotion interval (k-steps; 0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

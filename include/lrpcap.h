@@ -78,6 +78,10 @@ int lrpcap_encoder_relevance(lrpcap_encoder_t* enc, const int* h_img_index, cons
 int lrpcap_encoder_relevance_host(lrpcap_encoder_t* enc, const int* h_img_index, const float* h_R_head, int n_words,
                                   float* h_R_pix, void* stream);
 int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words);
+/* Tensor-core mode: the transposed-conv GEMMs move their TMEM accumulator into fp32 registers every `every_k_steps`
+ * k-steps (one k-step = 64 channels of one tap); 0 (default) disables it: measured to change nothing at the 1e-4 level
+ * (profiles/r01_promote_sweep.json) because the backward chain is insensitive to 1e-5 operand noise.  DESIGN.md section 5. */
+int lrpcap_encoder_set_promote(lrpcap_encoder_t* enc, int every_k_steps);
 long long lrpcap_encoder_launches(lrpcap_encoder_t* enc);
 /* Kernel timing (CUDA events on the launching stream around every convolution launch) for roofline reporting.
  * h_out9: per class {0: tcgen05 transposed conv (relevance), 1: tcgen05 forward conv, 2: fp32 SIMT conv}
@@ -144,6 +148,22 @@ long long lrpcap_decoder_launches(lrpcap_decoder_t* dec);
 int lrpcap_explain_batch_host(lrpcap_encoder_t* enc, lrpcap_decoder_t* dec, const float* h_images, int n_images,
                               int* h_captions, int T, int greedy, int eos_token, int method, int rule, float epsilon,
                               float alpha, float beta, int bias, float* h_R_pix, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- Grad-CAM
+ * Replaces `grad_cam(img_feature, grads)` (explainers.py:939-949, 1643-1653) for a batch of words:
+ *   weights = mean_xy grads; cam = sum_k weights_k F_k; pyramid_expand(cam, upscale, sigma); relu; / (max|cam| + 1e-6).
+ * d_features [n_images, fh*fh, D]; d_grads [n_words, fh*fh, D] (the decoder gradient); d_cam [n_words, fh*upscale, fh*upscale].
+ * The reference uses upscale = 16, sigma = 20.  Synchronous. */
+int lrpcap_gradcam(const float* d_features, const int* h_img_index, const float* d_grads, int n_words, int fh, int D,
+                   int upscale, float sigma, float* d_cam, void* stream);
+/* Guided-Grad-CAM (explainers.py:930-937): d_maps[w, y, x, c] *= d_cam[w, y, x]; d_maps [n_words, hw, hw, 3]. */
+int lrpcap_scale_maps(float* d_maps, const float* d_cam, int n_words, int hw, void* stream);
+
+/* ----------------------------------------------------------------------------------------------- LRP-inference
+ * Replaces the per-word score of `LRPInferenceLayer{Adaptive,gridTD}.call` (models/model.py:1673-1688, 2045-2060):
+ * hp = mean_c(map); hp /= max|hp|; score = mean(hp) (mode 0, 'mean') or mean(relu(hp)) (mode 1, 'pos_mean').
+ * d_maps [n_words, hw, hw, 3]; h_scores [n_words].  Synchronous. */
+int lrpcap_lrp_inference_scores(const float* d_maps, int n_words, int hw, int mode, float* h_scores, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- debug / tests
  * Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).

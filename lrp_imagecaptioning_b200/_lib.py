@@ -46,6 +46,7 @@ PROTOTYPES = {
     "lrpcap_encoder_relevance": (ctypes.c_int, [c_void_p, c_int_p, c_void_p, ctypes.c_int, c_void_p, c_void_p]),
     "lrpcap_encoder_relevance_host": (ctypes.c_int, [c_void_p, c_int_p, c_float_p, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_encoder_set_chunk_words": (ctypes.c_int, [c_void_p, ctypes.c_int]),
+    "lrpcap_encoder_set_promote": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "lrpcap_encoder_launches": (ctypes.c_longlong, [c_void_p]),
     "lrpcap_encoder_profile": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "lrpcap_encoder_profile_read": (ctypes.c_int, [c_void_p, c_double_p]),
@@ -58,6 +59,9 @@ PROTOTYPES = {
     "lrpcap_decoder_attention": (ctypes.c_int, [c_void_p, c_float_p, c_float_p]),
     "lrpcap_decoder_launches": (ctypes.c_longlong, [c_void_p]),
     "lrpcap_explain_batch_host": (ctypes.c_int, [c_void_p, c_void_p, c_float_p, ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_float_p, c_void_p]),
+    "lrpcap_gradcam": (ctypes.c_int, [c_void_p, c_int_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_void_p, c_void_p]),
+    "lrpcap_scale_maps": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p]),
+    "lrpcap_lrp_inference_scores": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_debug_conv": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p]),
 }
 

@@ -106,6 +106,12 @@ int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words) {
   return kOk;
 }
 
+int lrpcap_encoder_set_promote(lrpcap_encoder_t* enc, int every_k_steps) {
+  LRPCAP_REQUIRE(enc && enc->impl && every_k_steps >= 0, kErrInvalidArg, "encoder_set_promote: bad argument");
+  enc->impl->set_promote(every_k_steps);
+  return kOk;
+}
+
 long long lrpcap_encoder_launches(lrpcap_encoder_t* enc) { return (enc && enc->impl) ? enc->impl->launches() : 0; }
 
 int lrpcap_encoder_profile(lrpcap_encoder_t* enc, int enable) {

@@ -114,6 +114,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout; a.taps = 9; a.Nout = Nout;
     a.planes = backward ? 2 : 3;
+    a.promote_every = backward ? bwd_promote_ : 0;
     a.epi = epi;
     st = tc_conv_launch(a, s);
   } else {

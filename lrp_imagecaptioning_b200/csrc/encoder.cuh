@@ -58,6 +58,8 @@ class Encoder {
   // h_img_index[w] -> image of word w; d_R_head fp32 [n_words, fh, fh, 512]; d_R_pix fp32 [n_words, hw, hw, 3].
   int relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s);
   void set_chunk_words(int n) { chunk_words_ = n > 0 ? n : 1; }
+  // k-steps between fp32 promotions of the tensor-core accumulator in the backward GEMMs (0 = never)
+  void set_promote(int every) { bwd_promote_ = every > 0 ? every : 0; }
   // kernels launched by this object since construction (bench.py's gpu_launches)
   long long launches() const { return launches_; }
   // Kernel timing with CUDA events on the launching stream (bench.py roofline): when enabled every conv launch is
@@ -91,7 +93,7 @@ class Encoder {
   int fwd_planes() const { return split() ? 3 : 0; }
   size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
 
-  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256;
+  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0;
   long long launches_ = 0;
   EncoderRule rule_;
   Layer L_[kLayers];

@@ -64,6 +64,13 @@ simt_conv_kernel(const float* __restrict__ A, const float* __restrict__ B, int H
       Bs[tap][k][n] = val;
     }
     __syncthreads();
+    // two-level summation: this 8-channel chunk (<= 72 terms) is summed on its own and then added to the running
+    // total, so rounding error grows with the number of chunks rather than with K
+    float part[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) part[j][i] = 0.f;
     for (int tap = 0; tap < taps; ++tap) {
       const int dy = (taps == 9) ? tap / 3 - 1 : 0;
       const int dx = (taps == 9) ? tap % 3 - 1 : 0;
@@ -74,13 +81,17 @@ simt_conv_kernel(const float* __restrict__ A, const float* __restrict__ B, int H
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float a = As[rbase + j][k];
-          acc[j][0] = fmaf(a, b.x, acc[j][0]);
-          acc[j][1] = fmaf(a, b.y, acc[j][1]);
-          acc[j][2] = fmaf(a, b.z, acc[j][2]);
-          acc[j][3] = fmaf(a, b.w, acc[j][3]);
+          part[j][0] = fmaf(a, b.x, part[j][0]);
+          part[j][1] = fmaf(a, b.y, part[j][1]);
+          part[j][2] = fmaf(a, b.z, part[j][2]);
+          part[j][3] = fmaf(a, b.w, part[j][3]);
         }
       }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[j][i] += part[j][i];
   }
 
   const int y = y0 + prow;

@@ -25,7 +25,7 @@ constexpr int kATileBytes = 128 * 128;            // 128 rows x 128 B
 constexpr uint64_t kWaitLimitNs = 4000000000ull;   // 4 s of wall clock on one barrier = protocol bug -> trap
 
 struct Geom {
-  int H, W, TW, TH, tiles_x, tiles_y, cblocks, taps, Nout, n_items, n_tiles_n;
+  int H, W, TW, TH, tiles_x, tiles_y, cblocks, taps, Nout, n_items, n_tiles_n, group;   // group: k-steps per accumulator hand-over
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -173,7 +173,7 @@ __device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN)
   return t;
 }
 
-template <int BN, int MODE, int NS>
+template <int BN, int MODE, int NS, bool PROMO>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
   using C = Cfg<BN, NS>;
@@ -245,39 +245,48 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc(128, BN);
-      uint32_t it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t buf = tl & 1u;
-        mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        for (int kk = 0; kk < num_k; ++kk, ++it) {
-          const uint32_t s = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1u;
-          mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tl = 0;   // tl counts accumulator hand-overs: one per tile, or one per `group` k-steps (promotion)
+      const int gsz = PROMO ? g.group : num_k;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int kk0 = 0; kk0 < num_k; kk0 += gsz, ++tl) {
+          const uint32_t buf = tl & 1u;
+          mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + s * C::kStageBytes);
-          uint64_t da[NS], db[NS];
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          const int kk1 = (kk0 + gsz < num_k) ? kk0 + gsz : num_k;
+          for (int kk = kk0; kk < kk1; ++kk, ++it) {
+            const uint32_t s = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(smem + s * C::kStageBytes);
+            uint64_t da[NS], db[NS];
 #pragma unroll
-          for (int p = 0; p < NS; ++p) {
-            da[p] = make_desc_sw128(sbase + p * kATileBytes);
-            db[p] = make_desc_sw128(sbase + NS * kATileBytes + p * C::kBTileBytes);
-          }
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
-            umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, (kk | k) != 0 ? 1u : 0u);
-            umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, 1u);
-            umma_bf16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
-            if (NS == 3) {
-              umma_bf16(tmem_d, da[0] + adv, db[NS - 1] + adv, idesc, 1u);
-              umma_bf16(tmem_d, da[NS - 1] + adv, db[0] + adv, idesc, 1u);
-              umma_bf16(tmem_d, da[1] + adv, db[1] + adv, idesc, 1u);
+            for (int p = 0; p < NS; ++p) {
+              da[p] = make_desc_sw128(sbase + p * kATileBytes);
+              db[p] = make_desc_sw128(sbase + NS * kATileBytes + p * C::kBTileBytes);
             }
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
+              const uint32_t first = (kk != kk0 || k != 0) ? 1u : 0u;   // a fresh accumulator starts every group
+              if (NS == 3) {   // small terms first
+                umma_bf16(tmem_d, da[1] + adv, db[1] + adv, idesc, first);
+                umma_bf16(tmem_d, da[0] + adv, db[NS - 1] + adv, idesc, 1u);
+                umma_bf16(tmem_d, da[NS - 1] + adv, db[0] + adv, idesc, 1u);
+                umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, 1u);
+                umma_bf16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
+                umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
+              } else {
+                umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, first);
+                umma_bf16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
+                umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
+              }
+            }
+            umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
           }
-          umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+          umma_commit(&tfull_bar[buf]);  // (partial) accumulator complete
         }
-        umma_commit(&tfull_bar[buf]);  // accumulator of this tile complete
       }
     }
   } else {
@@ -289,24 +298,58 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     const int tx = r - ty * g.TW;
     const bool row_ok = r < g.TW * g.TH;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+    constexpr int kChunks = BN / 16 / (kEpiWarps / 4);   // 16-column chunks owned by this warp
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(g, tile, BN);
-      const uint32_t buf = tl & 1u;
-      mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
-      tc_fence_after();
       const int y = tc.y0 + ty, x = tc.x0 + tx;
       const bool valid = row_ok && (y < g.H) && (x < g.W);
-      const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+      if constexpr (PROMO) {
+        // promotion: sum the per-group partial accumulators in registers (IEEE fp32 adds); tensor-core accumulation
+        // drops low bits on every accumulate, which over hundreds of MMAs costs ~1e-5 relative
+        float acc[kChunks][16];
+#pragma unroll
+        for (int ci = 0; ci < kChunks; ++ci)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[ci][i] = 0.f;
+        for (int kk0 = 0; kk0 < num_k; kk0 += g.group, ++tl) {
+          const uint32_t buf = tl & 1u;
+          mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+          for (int ci = 0; ci < kChunks; ++ci) {
+            float v[16];
+            tmem_ld16(lane_base + (uint32_t)((half + ci * (kEpiWarps / 4)) * 16), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[ci][i] += v[i];
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int ci = 0; ci < kChunks; ++ci)
+            epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + (half + ci * (kEpiWarps / 4)) * 16, acc[ci]);
+        }
+        __syncwarp();
+      } else {
+        const uint32_t buf = tl & 1u;
+        mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
-        float v[16];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-        tmem_ld16(lane_base + (uint32_t)(c * 16), v);
-        if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+        for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
+          float v[16];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+          tmem_ld16(lane_base + (uint32_t)(c * 16), v);
+          if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        ++tl;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
   }
 
@@ -360,12 +403,12 @@ int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
   return kOk;
 }
 
-template <int BN, int MODE, int NS>
+template <int BN, int MODE, int NS, bool PROMO>
 int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   using C = Cfg<BN, NS>;
   static bool configured = false;
   if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE, NS, PROMO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
     configured = true;
   }
@@ -378,33 +421,39 @@ int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream
     LRPCAP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
-  tc_conv_kernel<BN, MODE, NS><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
+  tc_conv_kernel<BN, MODE, NS, PROMO><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 
-// Instantiated combinations: 2 planes -> every epilogue, BN in {64,128,256}; 3 planes (forward / raw only) -> BN in {64,128}.
+// Instantiated combinations: 2 planes -> every epilogue, BN in {64,128,256}, with and without promotion;
+// 3 planes (forward / raw only, always promoted) -> BN in {64,128}.
+template <int BN, bool PROMO>
+int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  switch (mode) {
+    case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 2, PROMO>(tm, g, e, stream);
+    case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 2, PROMO>(tm, g, e, stream);
+    case EPI_BWD: return launch_t<BN, EPI_BWD, 2, PROMO>(tm, g, e, stream);
+    case EPI_RAW: return launch_t<BN, EPI_RAW, 2, PROMO>(tm, g, e, stream);
+  }
+  set_last_error("tc_conv: unknown epilogue mode %d", mode);
+  return kErrInvalidArg;
+}
+
 template <int BN>
 int launch_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   if (planes == 3) {
     if constexpr (BN <= 128) {
       switch (mode) {
-        case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 3>(tm, g, e, stream);
-        case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 3>(tm, g, e, stream);
-        case EPI_RAW: return launch_t<BN, EPI_RAW, 3>(tm, g, e, stream);
+        case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 3, true>(tm, g, e, stream);
+        case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 3, true>(tm, g, e, stream);
+        case EPI_RAW: return launch_t<BN, EPI_RAW, 3, true>(tm, g, e, stream);
       }
     }
     set_last_error("tc_conv: 3-plane operands support forward / raw epilogues with BN <= 128 only (mode %d, BN %d)", mode, BN);
     return kErrUnsupported;
   }
-  switch (mode) {
-    case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 2>(tm, g, e, stream);
-    case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 2>(tm, g, e, stream);
-    case EPI_BWD: return launch_t<BN, EPI_BWD, 2>(tm, g, e, stream);
-    case EPI_RAW: return launch_t<BN, EPI_RAW, 2>(tm, g, e, stream);
-  }
-  set_last_error("tc_conv: unknown epilogue mode %d", mode);
-  return kErrInvalidArg;
+  return g.group > 0 ? launch_mode2<BN, true>(mode, tm, g, e, stream) : launch_mode2<BN, false>(mode, tm, g, e, stream);
 }
 
 }  // namespace
@@ -447,6 +496,7 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
+  g.group = a.planes == 3 ? 1 : (a.promote_every > 0 ? a.promote_every : 0);
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);

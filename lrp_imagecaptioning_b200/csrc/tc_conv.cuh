@@ -55,6 +55,9 @@ struct TcConvArgs {
   int taps = 9, Nout = 0;
   int planes = 2;           // bf16 planes of A, B and of the forward epilogue's activation tensors: 2 (hi, lo: 3 MMA
                             // products, 16-bit operands) or 3 (hi, mid, lo: 6 products, fp32-exact operands; forward only)
+  int promote_every = 0;    // 2-plane only: > 0 sums partial accumulators in fp32 registers every n k-steps (64 channels
+                            // of one tap each); tensor-core accumulation truncates, long chains cost ~1e-5 relative.
+                            // 3-plane launches always promote every k-step.
   EpiParams epi;
 };
 

@@ -116,6 +116,9 @@ class ImageModel(object):
     def set_chunk_words(self, n):
         _lib.check(_lib.load().lrpcap_encoder_set_chunk_words(self.handle(), int(n)))
 
+    def set_promote(self, every_k_steps):
+        _lib.check(_lib.load().lrpcap_encoder_set_promote(self.handle(), int(every_k_steps)))
+
     def profile(self, enable=True):
         _lib.check(_lib.load().lrpcap_encoder_profile(self.handle(), int(bool(enable))))
 

@@ -1,0 +1,108 @@
+"""GPU: the drop-in explainer classes (mirror of models/explainers.py) end to end against the oracle pipeline
+(reference call sequence: explain_image.py:45-87)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_parity, linf_rel
+
+pytestmark = pytest.mark.gpu
+
+HW, V, H = 64, 120, 64
+
+
+class _Pre(object):
+    SOS_TOKEN_LABEL_ENCODED = 1
+    EOS_TOKEN_LABEL_ENCODED = 2
+
+
+class _Provider(object):
+    caption_preprocessor = _Pre()
+
+
+def _model(kind, seed=0):
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.model import CaptioningModel
+    vgg = synth.vgg16_weights(seed)
+    dec = synth.decoder_weights(kind, V=V, H=H, E=H, D=512, seed=seed + 1)
+    return CaptioningModel(kind, vgg, dec, image_hw=HW, precision="bf16x3"), vgg, dec
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_lrp_explainer_matches_oracle_pipeline(kind, tmp_path):
+    from lrp_imagecaptioning_b200 import synth, explainers as E
+    from oracle import encoder_ref as ER
+    from oracle.decoder_ref import DecoderRef
+    model, vgg, dec = _model(kind)
+    path = str(tmp_path / "w.npz")
+    model.save_weights(path)
+    cls = E.ExplainImgCaptioningAdaptiveAttention if kind == "adaptive" else E.ExplainImgCaptioningGridTDModel
+    ex = cls(model, path, _Provider(), 20)
+    img = synth.images(1, HW, 5)
+    cap = [int(c) for c in synth.captions(1, 6, V, seed=6)[0]]
+    ex._forward_beam_search((None, img), cap)
+    rel, att = ex._explain_sentence()
+    assert len(rel) == len(cap) - 1 and att.shape == (len(cap) - 1, ex.L)
+    F = ER.features(img, vgg)[0].reshape(-1, 512)
+    o = DecoderRef(dec).forward(F, cap)
+    side = HW // 16
+    errs = []
+    for i, r in enumerate(rel):
+        assert r.shape == (1, side, side, 512) and r.dtype == np.float32
+        rF, a = o.explain(i + 1)
+        assert_parity(r, rF, "%s explainer R_F word %d" % (kind, i + 1), rel_tol=2e-3, sum_tol=None)
+        assert_parity(att[i], o.attention[1:-1][i], "%s explainer attention %d" % (kind, i + 1), rel_tol=1e-4, sum_tol=None)
+        heat = ex._explain_CNN(img, r)
+        assert heat.shape == (1, HW, HW, 3)
+        errs.append(linf_rel(heat, ER.analyze("lrp.sequential_preset_a", img, rF, vgg)))
+    assert np.median(errs) <= 2e-3 and max(errs) <= 8e-2, errs
+    r1, a1 = ex._explain_lstm_single_word_sequence(3)
+    assert np.array_equal(r1, rel[2])
+    rF, _ = o.explain(3)
+    if len(o.r_words):
+        assert_parity(ex.r_words, o.r_words, "%s r_words" % kind, sum_tol=None)
+    with pytest.raises(NotImplementedError):
+        ex._explain_lstm_single_word_sequence(len(cap) + 1)
+    batch = ex.explain_sentence_to_pixels()
+    assert batch.shape == (len(cap) - 1, HW, HW, 3)
+    assert np.array_equal(batch[0], ex._explain_CNN(img, rel[0])[0])
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_gradient_family_explainers(kind):
+    from lrp_imagecaptioning_b200 import synth, explainers as E
+    from oracle import encoder_ref as ER
+    from oracle.decoder_ref import DecoderRef
+    from oracle.gradcam_ref import grad_cam as ref_cam
+    model, vgg, dec = _model(kind, seed=3)
+    names = {"adaptive": ("ExplainImgCaptioningAdaptiveAttentionGradient", "ExplainImgCaptioningAdaptiveAttentionInputTimesGradient",
+                          "ExplainImgCaptioningAdaptiveAttentionGuidedGradcam"),
+             "gridtd": ("ExplainImgCaptioningGridTDGradient", "ExplainImgCaptioningGridTDGradientTimesInput",
+                        "ExplainImgCaptioningGridTDGuidedGradcam")}[kind]
+    img = synth.images(1, HW, 7)
+    cap = [int(c) for c in synth.captions(1, 5, V, seed=8)[0]]
+    F = ER.features(img, vgg)[0].reshape(-1, 512)
+    o = DecoderRef(dec).forward(F, cap)
+    for name, method in zip(names, ("gradient", "input_t_gradient", "guided_backprop")):
+        ex = getattr(E, name)(model, None, _Provider(), 20)
+        ex._forward_beam_search((None, img), cap)
+        rel = ex._explain_sentence()
+        assert len(rel) == len(cap) - 1
+        g = o.backward(2)
+        assert_parity(rel[1], g, "%s decoder gradient" % name, rel_tol=2e-3, sum_tol=None)
+        assert np.array_equal(ex._lstm_decoder_backward(2), rel[1])
+        heat = ex._explain_CNN(img, rel[1])
+        ref = ER.analyze(method, img, g, vgg)
+        if method == "guided_backprop":
+            ref = (ref[0] * ref_cam(F, g[0], F.shape[0], 512)[..., None])[None]
+        assert heat.shape == ref.shape
+        assert linf_rel(heat, ref) <= 8e-2
+
+
+def test_greedy_caption_via_beam_search_entry():
+    from lrp_imagecaptioning_b200 import synth, explainers as E
+    model, vgg, dec = _model("adaptive", seed=5)
+    ex = E.ExplainImgCaptioningAdaptiveAttention(model, None, _Provider(), 8)
+    caps = ex._beam_search((None, synth.images(2, HW, 9)), 1)
+    assert len(caps) == 2 and all(1 <= len(c) <= 8 for c in caps)
+    with pytest.raises(NotImplementedError):
+        ex._beam_search((None, synth.images(1, HW, 9)), 3)

@@ -137,6 +137,9 @@ int lrpcap_decoder_caption_logits(lrpcap_decoder_t* dec, double* h_logit);
 /* The `.attention` / `.beta` attributes the reference explainers expose after `_forward_beam_search`
  * (explainers.py:429-431): h_alpha [n_images, T+1, L] and h_beta [n_images, T+1], row 0 all zeros. Either may be NULL. */
 int lrpcap_decoder_attention(lrpcap_decoder_t* dec, float* h_alpha, float* h_beta);
+/* Full logits [n_images, V] (fp64) of the LAST step of the most recent decoder_forward: the quantity beam search ranks
+ * (`keras_model.predict_on_batch` + `preds[:, -1]`, explainers.py:73-76).  Synchronous. */
+int lrpcap_decoder_last_logits(lrpcap_decoder_t* dec, double* h_logits, void* stream);
 long long lrpcap_decoder_launches(lrpcap_decoder_t* dec);
 
 /* ----------------------------------------------------------------------------------------------- whole path

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "lrpcap_decoder_backward": (ctypes.c_int, [c_void_p, c_int_p, c_int_p, ctypes.c_int, c_void_p, c_double_p, c_void_p]),
     "lrpcap_decoder_caption_logits": (ctypes.c_int, [c_void_p, c_double_p]),
     "lrpcap_decoder_attention": (ctypes.c_int, [c_void_p, c_float_p, c_float_p]),
+    "lrpcap_decoder_last_logits": (ctypes.c_int, [c_void_p, c_double_p, c_void_p]),
     "lrpcap_decoder_launches": (ctypes.c_longlong, [c_void_p]),
     "lrpcap_explain_batch_host": (ctypes.c_int, [c_void_p, c_void_p, c_float_p, ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_gradcam": (ctypes.c_int, [c_void_p, c_int_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_void_p, c_void_p]),

@@ -274,6 +274,15 @@ int Decoder::caption_logits(double* h_logit) {
   return kOk;
 }
 
+int Decoder::last_logits(double* h_logits, cudaStream_t s) {
+  LRPCAP_REQUIRE(N_ > 0 && h_logits, kErrState, "decoder_last_logits: call decoder_forward first");
+  LRPCAP_TRY(logits_.ensure((size_t)N_ * V_ * 8));
+  LRPCAP_TRY(gemm(hc_.as<double>(), H_, Wo_, V_, logits_.as<double>(), V_, N_, V_, H_, bo_, s));
+  LRPCAP_CUDA(cudaMemcpyAsync(h_logits, logits_.p, (size_t)N_ * V_ * 8, cudaMemcpyDeviceToHost, s));
+  LRPCAP_CUDA(cudaStreamSynchronize(s));
+  return kOk;
+}
+
 int Decoder::attention(float* h_alpha, float* h_beta) {
   LRPCAP_REQUIRE(N_ > 0, kErrState, "decoder_attention: call decoder_forward first");
   if (h_alpha) {

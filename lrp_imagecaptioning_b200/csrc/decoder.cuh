@@ -34,6 +34,7 @@ class Decoder {
                cudaStream_t s);
   int caption_logits(double* h_logit);
   int attention(float* h_alpha, float* h_beta);
+  int last_logits(double* h_logits, cudaStream_t s);   // [N, V] logits of the last forward step
   long long launches() const { return launches_; }
   int n_images() const { return N_; }
   int T() const { return T_; }

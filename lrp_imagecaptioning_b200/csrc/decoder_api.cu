@@ -53,6 +53,11 @@ int lrpcap_decoder_attention(lrpcap_decoder_t* dec, float* h_alpha, float* h_bet
   return dec->impl->attention(h_alpha, h_beta);
 }
 
+int lrpcap_decoder_last_logits(lrpcap_decoder_t* dec, double* h_logits, void* stream) {
+  LRPCAP_REQUIRE(dec && dec->impl, kErrInvalidArg, "decoder_last_logits: null handle");
+  return dec->impl->last_logits(h_logits, reinterpret_cast<cudaStream_t>(stream));
+}
+
 long long lrpcap_decoder_launches(lrpcap_decoder_t* dec) { return (dec && dec->impl) ? dec->impl->launches() : 0; }
 
 int lrpcap_explain_batch_host(lrpcap_encoder_t* enc, lrpcap_decoder_t* dec, const float* h_images, int n_images,

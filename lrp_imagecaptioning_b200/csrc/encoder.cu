@@ -35,6 +35,14 @@ Encoder::~Encoder() {
         if (p) cudaFree(p);
   }
   if (w0_pm_) cudaFree(w0_pm_);
+  if (w0_mp_) cudaFree(w0_mp_);
+  if (w0_last_a_) cudaFree(w0_last_a_);
+  if (w0_last_b_) cudaFree(w0_last_b_);
+  Mseed2_.release();
+  for (auto& g : G2_) g.release();
+  for (auto& l : L_)
+    for (auto& p : l.dual)
+      if (p) cudaFree(p);
   X0_.release(); F_.release(); Mseed_.release(); posneg_.release(); idx_.release();
   for (auto& g : G_) g.release();
   for (auto& a : act_) a.release();
@@ -90,29 +98,43 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
   return kOk;
 }
 
+int Encoder::get_dual_weights(int l, bool tc, void** out, cudaStream_t s) {
+  Layer& L = L_[l];
+  void*& slot = L.dual[tc ? 1 : 0];
+  if (!slot) {
+    LRPCAP_CUDA(cudaMalloc(&slot, (size_t)9 * L.cin * 2 * L.cout * sizeof(float)));
+    LRPCAP_TRY(prep_weights_dual(L.w_hwio, slot, L.cin, L.cout, tc ? WF_TC_BWD : WF_SIMT_BWD, WS_PLUS, rule_.alpha, WS_MINUS,
+                                 -rule_.beta, s));
+    ++launches_;
+  }
+  *out = slot;
+  return kOk;
+}
+
 int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const EpiParams& epi,
-                  cudaStream_t s) {
+                  cudaStream_t s, bool dual) {
   const Layer& L = L_[l];
-  const int C = backward ? L.cout : L.cin;
+  const int C = backward ? (dual ? 2 * L.cout : L.cout) : L.cin;
   const int Nout = backward ? L.cin : L.cout;
   void* B = nullptr;
   ++launches_;
   const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
   if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
-  LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : WF_TC_FWD3) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  if (dual) LRPCAP_TRY(get_dual_weights(l, tc, &B, s));
+  else LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : WF_TC_FWD3) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
   ProfRec rec{};
   if (profile_) {
     LRPCAP_CUDA(cudaEventCreate(&rec.a));
     LRPCAP_CUDA(cudaEventCreate(&rec.b));
     rec.cls = tc ? (backward ? 0 : 1) : 2;
-    rec.flops = 2.0 * 9.0 * (double)n_items * L.hw * L.hw * (double)L.cin * L.cout;
+    rec.flops = 2.0 * 9.0 * (double)n_items * L.hw * L.hw * (double)L.cin * L.cout * (dual ? 2.0 : 1.0);
     LRPCAP_CUDA(cudaEventRecord(rec.a, s));
   }
   int st;
   if (tc) {
     TcConvArgs a;
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
-    a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout; a.taps = 9; a.Nout = Nout;
+    a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout * (dual ? 2 : 1); a.taps = 9; a.Nout = Nout;
     a.planes = backward ? 2 : 3;
     a.promote_every = backward ? bwd_promote_ : 0;
     a.epi = epi;
@@ -158,8 +180,6 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
     case RULE_ALPHA_BETA:
       LRPCAP_REQUIRE(rule.alpha >= 1.f && rule.beta >= 0.f && fabsf(rule.alpha - rule.beta - 1.f) < 1e-6f,
                      kErrInvalidArg, "encoder_forward: need alpha >= 1, beta >= 0, alpha - beta = 1");
-      LRPCAP_REQUIRE(rule.beta == 0.f, kErrUnsupported,
-                     "encoder_forward: alpha-beta with beta != 0 (inhibitor branch) is not built yet");
       break;
     case RULE_Z: case RULE_ZPLUS_FAST: case RULE_GRADIENT: case RULE_INPUT_T_GRADIENT: case RULE_GUIDED_BACKPROP:
       break;
@@ -180,6 +200,20 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
   for (auto& a : act_) LRPCAP_TRY(a.ensure(act_bytes));
 
   const bool ab = rule.kind == RULE_ALPHA_BETA, zpf = rule.kind == RULE_ZPLUS_FAST;
+  const bool inh = ab && rule.beta != 0.f;   // inhibitor branch f(W-, W+, x+, x-) (relevance_rule.py:314-320)
+  if (inh) {
+    for (int l = 0; l < kLayers - 1; ++l) LRPCAP_TRY(G2_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
+    LRPCAP_TRY(Mseed2_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
+    if (dual_alpha_ != rule.alpha || dual_beta_ != rule.beta) {   // cached stacked weights depend on (alpha, beta)
+      for (auto& L : L_)
+        for (auto& p : L.dual)
+          if (p) { cudaFree(p); p = nullptr; }
+      if (w0_last_a_) { cudaFree(w0_last_a_); w0_last_a_ = nullptr; }
+      if (w0_last_b_) { cudaFree(w0_last_b_); w0_last_b_ = nullptr; }
+      dual_alpha_ = rule.alpha;
+      dual_beta_ = rule.beta;
+    }
+  }
   int gmode = G_MASK;
   if (rule.kind == RULE_EPSILON) gmode = G_EPS;
   else if (rule.kind == RULE_Z) gmode = G_Z;
@@ -196,6 +230,15 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
         }
     LRPCAP_CUDA(cudaMalloc(&w0_pm_, pm.size() * sizeof(float)));
     LRPCAP_CUDA(cudaMemcpy(w0_pm_, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int tap = 0; tap < 9; ++tap)      // [W- ; W+]: z_inh = W- * x+ + W+ * x-
+      for (int ci = 0; ci < 3; ++ci)
+        for (int co = 0; co < 64; ++co) {
+          const float w = w0_host_[((size_t)tap * 3 + ci) * 64 + co];
+          pm[((size_t)tap * 6 + ci) * 64 + co] = w < 0.f ? w : 0.f;
+          pm[((size_t)tap * 6 + 3 + ci) * 64 + co] = w >= 0.f ? w : 0.f;
+        }
+    LRPCAP_CUDA(cudaMalloc(&w0_mp_, pm.size() * sizeof(float)));
+    LRPCAP_CUDA(cudaMemcpy(w0_mp_, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
 
   for (int i0 = 0; i0 < n; i0 += FC) {
@@ -246,6 +289,20 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
         } else {
           LRPCAP_TRY(conv(l, false, WS_PLUS, X, X_elems, m, ez, s));
         }
+        if (inh) {   // second multiplier: x / safe(z_inh), z_inh = W- * x+ + W+ * x- + b
+          ez.G = (l < kLayers - 1) ? G2_[l].as<float>() + (size_t)i0 * oe : nullptr;
+          ez.Mseed = (l == kLayers - 1) ? Mseed2_.as<float>() + (size_t)i0 * oe : nullptr;
+          if (l == 0) {
+            SimtConvArgs a;
+            a.A = posneg_.as<float>(); a.n_items = m; a.H = hw_; a.W = hw_; a.C = 6;
+            a.B = w0_mp_; a.taps = 9; a.Nout = 64; a.out_planes = fwd_planes();
+            a.epi = ez;
+            LRPCAP_TRY(simt_conv_launch(a, s));
+            ++launches_;
+          } else {
+            LRPCAP_TRY(conv(l, false, WS_MINUS, X, X_elems, m, ez, s));
+          }
+        }
       }
 
       if (L.pool_after) {
@@ -253,6 +310,10 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
         while (bp == bx || bp == by) ++bp;
         LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), act_[bp].p, (size_t)m * oe / 4, Gl, m, L.hw, L.hw, L.cout, s));
         ++launches_;
+        if (inh) {
+          LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), nullptr, 0, G2_[l].as<float>() + (size_t)i0 * oe, m, L.hw, L.hw, L.cout, s));
+          ++launches_;
+        }
         X = act_[bp].p;
         X_elems = (size_t)m * oe / 4;
         bx = bp;
@@ -276,7 +337,8 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
   LRPCAP_TRY(idx_.ensure((size_t)n_words * sizeof(int)));
   LRPCAP_CUDA(cudaMemcpyAsync(idx_.p, h_img_index, (size_t)n_words * sizeof(int), cudaMemcpyHostToDevice, s));
   const int CW = n_words < chunk_words_ ? n_words : chunk_words_;
-  const size_t msg_bytes = (size_t)CW * hw_ * hw_ * 64 * sizeof(float);
+  const bool inh = rule_.kind == RULE_ALPHA_BETA && rule_.beta != 0.f;
+  const size_t msg_bytes = (size_t)CW * hw_ * hw_ * 64 * sizeof(float) * (inh ? 2 : 1);
   for (auto& m : msg_) LRPCAP_TRY(m.ensure(msg_bytes));
 
   const bool ab = rule_.kind == RULE_ALPHA_BETA, zpf = rule_.kind == RULE_ZPLUS_FAST;
@@ -288,15 +350,28 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
   const size_t pix_elems = (size_t)hw_ * hw_ * 3;
 
   void *Wa = nullptr, *Wb = nullptr;
-  LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, sign, &Wa, s));
-  if (ab) LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, WS_MINUS, &Wb, s));
+  if (inh) {   // x >= 0: alpha W+^T s_a - beta W-^T s_i ;  x < 0: alpha W-^T s_a - beta W+^T s_i
+    if (!w0_last_a_) {
+      LRPCAP_CUDA(cudaMalloc(&w0_last_a_, (size_t)9 * 128 * 3 * sizeof(float)));
+      LRPCAP_CUDA(cudaMalloc(&w0_last_b_, (size_t)9 * 128 * 3 * sizeof(float)));
+      LRPCAP_TRY(prep_weights_dual(L_[0].w_hwio, w0_last_a_, 3, 64, WF_SIMT_BWD, WS_PLUS, rule_.alpha, WS_MINUS, -rule_.beta, s));
+      LRPCAP_TRY(prep_weights_dual(L_[0].w_hwio, w0_last_b_, 3, 64, WF_SIMT_BWD, WS_MINUS, rule_.alpha, WS_PLUS, -rule_.beta, s));
+      launches_ += 2;
+    }
+    Wa = w0_last_a_;
+    Wb = w0_last_b_;
+  } else {
+    LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, sign, &Wa, s));
+    if (ab) LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, WS_MINUS, &Wb, s));
+  }
+  const int mul = inh ? 2 : 1;
 
   for (int w0 = 0; w0 < n_words; w0 += CW) {
     const int m = (n_words - w0) < CW ? (n_words - w0) : CW;
     const int* idx = idx_.as<int>() + w0;
     int cur = 0;
-    LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), idx, msg_[cur].p, (size_t)m * head_elems,
-                            split(), m, fh * fh, 512, guided ? 1 : 0, s));
+    LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr, idx,
+                            msg_[cur].p, (size_t)m * head_elems * mul, split(), m, fh * fh, 512, guided ? 1 : 0, s));
     ++launches_;
     for (int l = kLayers - 1; l >= 1; --l) {
       EpiParams ep;
@@ -306,13 +381,14 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       ep.up = L_[l - 1].pool_after ? 2 : 1;
       ep.relu_acc = guided ? 1 : 0;
       ep.out_msg = msg_[cur ^ 1].p;
-      ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1);
-      LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l), m, ep, s));
+      ep.Gin2 = inh ? G2_[l - 1].as<float>() : nullptr;
+      ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1) * mul;
+      LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l) * mul, m, ep, s, inh));
       cur ^= 1;
     }
-    LRPCAP_TRY(last_dgrad(msg_[cur].p, (size_t)m * layer_out_elems(0), split(), reinterpret_cast<const float*>(Wa),
+    LRPCAP_TRY(last_dgrad(msg_[cur].p, (size_t)m * layer_out_elems(0) * mul, split(), reinterpret_cast<const float*>(Wa),
                           reinterpret_cast<const float*>(Wb), X0_.as<float>(), idx, d_R_pix + (size_t)w0 * pix_elems, m,
-                          hw_, hw_, 64, mult, s));
+                          hw_, hw_, 64 * mul, mult, s));
     ++launches_;
   }
   return kOk;

@@ -82,10 +82,12 @@ class Encoder {
     float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
     float* bias = nullptr;    // device fp32 [cout]
     void* prepared[5][3] = {};  // [WeightFormat][WeightSign]
+    void* dual[2] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC} backward layouts
   };
   int get_weights(int l, int fmt, int sign, void** out, cudaStream_t s);
   int conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const struct EpiParams& epi,
-           cudaStream_t s);
+           cudaStream_t s, bool dual = false);
+  int get_dual_weights(int l, bool tc, void** out, cudaStream_t s);
   bool split() const { return precision_ == PREC_BF16X3_TC; }
   // storage planes of forward activations: 3 bf16 planes (fp32-exact operands) in tensor-core mode, fp32 otherwise.
   // The per-image forward decides ReLU signs / pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level
@@ -99,7 +101,11 @@ class Encoder {
   Layer L_[kLayers];
   std::vector<float> w0_host_;       // first-layer kernel (host copy) for the signed-input alpha-beta path
   float* w0_pm_ = nullptr;           // device fp32 [9][6][64]: [W+ ; W-] stacked for the [x+, x-] input
+  float* w0_mp_ = nullptr;           // [W- ; W+] (inhibitor branch, beta != 0)
+  float *w0_last_a_ = nullptr, *w0_last_b_ = nullptr;   // dual last-layer weights [9][128][3] for x >= 0 / x < 0
+  float dual_alpha_ = 0.f, dual_beta_ = 0.f;            // (alpha, beta) the cached dual weights were built for
   DevBuf X0_, F_, Mseed_, G_[kLayers - 1];
+  DevBuf Mseed2_, G2_[kLayers - 1];   // inhibitor-branch multipliers (beta != 0)
   DevBuf act_[3], posneg_, msg_[2], idx_;
 };
 

@@ -42,6 +42,36 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+__global__ void prep_weights_dual_kernel(const float* __restrict__ w, float* __restrict__ out_f32,
+                                         __nv_bfloat16* __restrict__ out_hi, int cin, int cout, int fmt, int sign_a,
+                                         float scale_a, int sign_b, float scale_b) {
+  const size_t total = (size_t)9 * cin * 2 * cout;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int tapf, ci, k;
+  if (fmt == WF_SIMT_BWD) {
+    ci = idx % cin; k = (idx / cin) % (2 * cout); tapf = idx / ((size_t)cin * 2 * cout);
+  } else {
+    k = idx % (2 * cout); ci = (idx / (2 * cout)) % cin; tapf = idx / ((size_t)cin * 2 * cout);
+  }
+  const int co = k % cout;
+  const bool second = k >= cout;
+  float v = w[((size_t)(8 - tapf) * cin + ci) * cout + co];
+  const int sg = second ? sign_b : sign_a;
+  if (sg == WS_PLUS) v = v >= 0.f ? v : 0.f;
+  if (sg == WS_MINUS) v = v < 0.f ? v : 0.f;
+  v *= second ? scale_b : scale_a;
+  if (fmt == WF_SIMT_BWD) {
+    out_f32[idx] = v;
+  } else {
+    for (int p = 0; p < 2; ++p) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out_hi[(size_t)p * total + idx] = h;
+      v -= __bfloat162float(h);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ max-pool + arg-max masking
 template <class ST>
 __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems, void* pooled, size_t pooled_elems,
@@ -87,8 +117,9 @@ __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems,
 
 // ------------------------------------------------------------------ seed message
 template <class ST>
-__global__ void seed_kernel(const float* __restrict__ R, const float* __restrict__ M, const int* __restrict__ img_index,
-                            void* msg, size_t msg_elems, int items, size_t per_item, int relu) {
+__global__ void seed_kernel(const float* __restrict__ R, const float* __restrict__ M, const float* __restrict__ M2,
+                            const int* __restrict__ img_index, void* msg, size_t msg_elems, int items, size_t per_item,
+                            int C, int relu) {
   const size_t total4 = (size_t)items * per_item / 4;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total4) return;
@@ -101,7 +132,17 @@ __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict
   load_f32<4>(M + (size_t)img * per_item + in_item, m);
 #pragma unroll
   for (int i = 0; i < 4; ++i) o[i] = (relu ? fmaxf(r[i], 0.f) : r[i]) * m[i];
-  ST::template store<4>(msg, msg_elems, e, o);
+  if (!M2) {
+    ST::template store<4>(msg, msg_elems, e, o);
+    return;
+  }
+  const size_t pix = e / C;               // dual layout: [.., pixel, 2C] = [R*M | R*M2]
+  const int c = (int)(e - pix * C);
+  ST::template store<4>(msg, msg_elems, pix * 2 * C + c, o);
+  load_f32<4>(M2 + (size_t)img * per_item + in_item, m);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = r[i] * m[i];
+  ST::template store<4>(msg, msg_elems, pix * 2 * C + C + c, o);
 }
 
 // ------------------------------------------------------------------ last transposed conv (C -> 3) + re-weighting
@@ -109,13 +150,13 @@ __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict
 // weight as a uniform constant operand; a thread owns two horizontally adjacent pixels and re-uses its 3x4 window.
 constexpr int kLTY = 16, kLTX = 32;   // tile (rows x cols), 256 threads x 2 pixels
 constexpr int kLC = 16;               // channel chunk staged in shared memory
-constexpr int kLastMaxC = 64;
+constexpr int kLastMaxC = 128;   // 64 channels, or 2 x 64 for the dual (beta != 0) message
 __constant__ float c_wlast[2][9 * kLastMaxC * 3];
 
-template <class ST, bool DUAL>
+template <class ST, bool DUAL, int C>
 __global__ void __launch_bounds__(256)
 last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* __restrict__ images,
-                  const int* __restrict__ img_index, float* __restrict__ out, int H, int W, int C, int tiles_x,
+                  const int* __restrict__ img_index, float* __restrict__ out, int H, int W, int tiles_x,
                   int tiles_y, int mult) {
   constexpr int PSX = kLTX + 2, PSY = kLTY + 2;
   __shared__ float S[kLC][PSX * PSY + 1];
@@ -129,7 +170,8 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
   const int ty = tid >> 4, tx = (tid & 15) * 2;
 
   float ca[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, cb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  for (int c0 = 0; c0 < C; c0 += kLC) {
+#pragma unroll
+  for (int c0 = 0; c0 < C; c0 += kLC) {   // fully unrolled: every constant-bank offset below is an immediate
     __syncthreads();
     for (int pix = tid; pix < PSX * PSY; pix += 256) {     // one halo pixel (16 channels = 4 x 16 B loads) per thread
       const int py = pix / PSX, px = pix - py * PSX;
@@ -219,6 +261,17 @@ __global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const 
 
 }  // namespace
 
+int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign_a, float scale_a, int sign_b,
+                      float scale_b, cudaStream_t s) {
+  LRPCAP_REQUIRE(fmt == WF_SIMT_BWD || fmt == WF_TC_BWD, kErrInvalidArg, "prep_weights_dual: backward formats only");
+  const size_t total = (size_t)9 * cin * 2 * cout;
+  prep_weights_dual_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, reinterpret_cast<float*>(out),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), cin, cout, fmt,
+                                                                sign_a, scale_a, sign_b, scale_b);
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps,
                  int planes) {
   const size_t total = (size_t)taps * cin * cout;
@@ -243,15 +296,15 @@ int pool_mask(const void* act, size_t act_elems, int planes, void* pooled, size_
   return kOk;
 }
 
-int seed_message(const float* R, const float* M, const int* img_index, void* msg, size_t msg_elems, bool split,
-                 int items, int pix, int C, int relu, cudaStream_t s) {
+int seed_message(const float* R, const float* M, const float* M2, const int* img_index, void* msg, size_t msg_elems,
+                 bool split, int items, int pix, int C, int relu, cudaStream_t s) {
   const size_t per_item = (size_t)pix * C;
   LRPCAP_REQUIRE(per_item % 4 == 0, kErrShape, "seed_message: item size must be a multiple of 4");
   const size_t total4 = (size_t)items * per_item / 4;
   if (split)
-    seed_kernel<StoreSplit><<<grid_for(total4, 256), 256, 0, s>>>(R, M, img_index, msg, msg_elems, items, per_item, relu);
+    seed_kernel<StoreSplit><<<grid_for(total4, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu);
   else
-    seed_kernel<StoreF32><<<grid_for(total4, 256), 256, 0, s>>>(R, M, img_index, msg, msg_elems, items, per_item, relu);
+    seed_kernel<StoreF32><<<grid_for(total4, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -267,13 +320,17 @@ int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, c
   // stream-ordered refresh of the constant bank (one encoder stream at a time uses it)
   LRPCAP_CUDA(cudaMemcpyToSymbolAsync(c_wlast, Wa, wbytes, 0, cudaMemcpyDeviceToDevice, s));
   if (Wb) LRPCAP_CUDA(cudaMemcpyToSymbolAsync(c_wlast, Wb, wbytes, sizeof(float) * 9 * kLastMaxC * 3, cudaMemcpyDeviceToDevice, s));
-#define LRPCAP_LAUNCH_LAST(ST, DUAL) \
-  last_dgrad_kernel<ST, DUAL><<<g, 256, 0, s>>>(msg, msg_elems, images, img_index, out, H, W, C, tiles_x, tiles_y, mult)
+  LRPCAP_REQUIRE(C == 64 || C == 128, kErrShape, "last_dgrad: C must be 64 (or 128 for the dual message)");
+#define LRPCAP_LAUNCH_LAST(ST, DUAL, CC) \
+  last_dgrad_kernel<ST, DUAL, CC><<<g, 256, 0, s>>>(msg, msg_elems, images, img_index, out, H, W, tiles_x, tiles_y, mult)
+#define LRPCAP_LAUNCH_LAST_C(ST, DUAL) \
+  do { if (C == 64) LRPCAP_LAUNCH_LAST(ST, DUAL, 64); else LRPCAP_LAUNCH_LAST(ST, DUAL, 128); } while (0)
   if (split) {
-    if (Wb) LRPCAP_LAUNCH_LAST(StoreSplit, true); else LRPCAP_LAUNCH_LAST(StoreSplit, false);
+    if (Wb) LRPCAP_LAUNCH_LAST_C(StoreSplit, true); else LRPCAP_LAUNCH_LAST_C(StoreSplit, false);
   } else {
-    if (Wb) LRPCAP_LAUNCH_LAST(StoreF32, true); else LRPCAP_LAUNCH_LAST(StoreF32, false);
+    if (Wb) LRPCAP_LAUNCH_LAST_C(StoreF32, true); else LRPCAP_LAUNCH_LAST_C(StoreF32, false);
   }
+#undef LRPCAP_LAUNCH_LAST_C
 #undef LRPCAP_LAUNCH_LAST
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;

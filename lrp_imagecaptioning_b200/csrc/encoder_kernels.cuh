@@ -18,6 +18,12 @@ enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
 int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps = 9,
                  int planes = 2);
 
+// Backward weights of the alpha-beta rule with beta != 0, stacked along K (2*cout input channels):
+//   k <  cout : scale_a * sign_a(W)      k >= cout : scale_b * sign_b(W)
+// fmt: WF_SIMT_BWD -> fp32 [tap'][2*cout][cin]; WF_TC_BWD -> split-bf16 [tap'][cin][2*cout].
+int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign_a, float scale_a, int sign_b,
+                      float scale_b, cudaStream_t s);
+
 // 2x2/2 max-pool of `act` [items,H,W,C] (storage-typed). If `pooled` != null writes [items,H/2,W/2,C];
 // if `G` != null zeroes every G entry that is not the first maximum of its window (TF MaxPoolGrad routing,
 // innvestigate relevance_analyzer.py:459-480).
@@ -25,7 +31,8 @@ int pool_mask(const void* act, size_t act_elems, int planes /*0 = fp32, 2, 3*/, 
               int H, int W, int C, cudaStream_t s);
 
 // msg[item] = (relu?)(R[item]) * M[img_index[item]]   ([items, hw, hw, C]); msg storage-typed.
-int seed_message(const float* R, const float* M, const int* img_index, void* msg, size_t msg_elems, bool split,
+// M2 != null: dual message with 2*C channels [R*M | R*M2].
+int seed_message(const float* R, const float* M, const float* M2, const int* img_index, void* msg, size_t msg_elems, bool split,
                  int items, int pix, int C, int relu, cudaStream_t s);
 
 // Last transposed conv (64 -> 3 channels) + input re-weighting:

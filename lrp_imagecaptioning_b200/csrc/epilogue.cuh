@@ -25,6 +25,7 @@ struct EpiDev {
   size_t x_elems;
   const int* img_index;
   const float* Gin;
+  const float* Gin2;
   int up;
   int relu_acc;
 };
@@ -211,10 +212,17 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
       for (int sx = 0; sx < e.up; ++sx) {
         const size_t pix = (size_t)(y * e.up + sy) * WW + (x * e.up + sx);
         float gg[NV], o[NV];
+        const int NO = e.Gin2 ? 2 * Nout : Nout;
         load_f32<NV>(e.Gin + ((size_t)img * HH * WW + pix) * Nout + n, gg);
 #pragma unroll
         for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[i];
-        ST::template store<NV>(e.out, e.out_elems, ((size_t)item * HH * WW + pix) * Nout + n, o);
+        ST::template store<NV>(e.out, e.out_elems, ((size_t)item * HH * WW + pix) * NO + n, o);
+        if (e.Gin2) {
+          load_f32<NV>(e.Gin2 + ((size_t)img * HH * WW + pix) * Nout + n, gg);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[i];
+          ST::template store<NV>(e.out, e.out_elems, ((size_t)item * HH * WW + pix) * NO + Nout + n, o);
+        }
       }
     }
   }
@@ -233,6 +241,7 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->x_elems = p.x_act_elems;
   e->img_index = p.img_index;
   e->Gin = p.Gin;
+  e->Gin2 = p.Gin2;
   e->up = p.up;
   e->relu_acc = p.relu_acc;
   e->out = nullptr;

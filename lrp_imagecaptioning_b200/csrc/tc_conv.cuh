@@ -40,6 +40,8 @@ struct EpiParams {
   // backward
   const int* img_index = nullptr;   // [items] -> image
   const float* Gin = nullptr;       // fp32 [images, H*up, W*up, Nout]
+  const float* Gin2 = nullptr;      // alpha-beta with beta != 0: second multiplier (inhibitor branch); the output then has
+                                    // 2*Nout channels: [acc*Gin | acc*Gin2]
   int up = 1;
   int relu_acc = 0;
   void* out_msg = nullptr;          // split storage [items, H*up, W*up, Nout]

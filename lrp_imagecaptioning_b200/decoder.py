@@ -120,6 +120,12 @@ class DecoderEngine(object):
         _lib.check(_lib.load().lrpcap_decoder_caption_logits(self.handle(), _lib.dptr(out)))
         return out
 
+    def last_logits(self):
+        """Full logits [N, V] of the last step of the most recent forward (float64)."""
+        out = np.zeros((self.N, self.V), dtype=np.float64)
+        _lib.check(_lib.load().lrpcap_decoder_last_logits(self.handle(), _lib.dptr(out), self._stream()))
+        return out
+
     def attention(self):
         """(alpha [N, T+1, L], beta [N, T+1]) with the zero row at index 0, as the reference stores them."""
         al = np.zeros((self.N, self.T + 1, self.L), dtype=np.float32)

@@ -9,7 +9,8 @@ epsilon rule.
 
 Differences a maintainer should know (all switchable or documented in DESIGN.md):
   * `_explain_sentence` runs every word of the sentence in one batched launch sequence instead of a Python loop.
-  * `_beam_search` supports beam_size == 1 (greedy arg-max on the device); wider beams are not built yet.
+  * `_beam_search` ranks hypotheses with the decoder's last-step logits (one batched teacher-forced forward per
+    round for all images x beams) instead of re-running the whole Keras model incl. VGG16 per round.
 """
 import numpy as np
 
@@ -45,19 +46,57 @@ class ExplainImgCaptioningAttentionModel(object):
         self._decoder = DecoderEngine(model.dec, sos=self._preprocessor.SOS_TOKEN_LABEL_ENCODED, device=model.device)
         self._img = None
 
-    # ---- caption generation (explainers.py:51-120)
+    # ---- caption generation (explainers.py:51-120; inference.py:267-315 BatchNLargest / NLargest / Caption)
     def _beam_search(self, X, beam_size):
-        if beam_size != 1:
-            raise NotImplementedError("beam search with beam_size > 1 is not built yet; use beam_size=1 (greedy)")
+        """Beam search over the captioner's logits (the Keras model's: (h + c_hat) W_o + b for both kinds), with the
+        reference's bookkeeping: hypotheses start as [SOS, EOS]; each round extends every hypothesis by its `beam_size`
+        best words, keeps the best `beam_size` per image; a hypothesis extended by EOS records its parent as complete.
+        Returns, per beam rank, the token list without SOS (`[words..., EOS]`) -- the structure `explain_image.py:41-43`
+        indexes as `_beam_search(X, 3)[0]` for a single image."""
+        import heapq
         _, imgs = X
+        imgs = np.asarray(imgs, dtype=np.float32)
+        B = imgs.shape[0]
+        pre = self._preprocessor
+        SOS, EOS = pre.SOS_TOKEN_LABEL_ENCODED, pre.EOS_TOKEN_LABEL_ENCODED
         self._image_model.forward(imgs, self._CNN_explainer._rule())
-        cap = self._decoder.forward(self._image_model.features(), T=self._max_caption_length, greedy=True, eos=-1)
-        eos = self._preprocessor.EOS_TOKEN_LABEL_ENCODED
-        out = []
-        for row in cap:
-            row = [int(t) for t in row]
-            out.append(row[:row.index(eos)] if eos in row else row)
-        return out
+        feats = self._image_model.features().reshape(B, self.L, self.D)
+        if getattr(self, "_decoder_keras", None) is None:
+            self._decoder_keras = DecoderEngine(self._model.dec, sos=SOS, keras_logits=True, device=self._model.device)
+
+        def push(heap, item):
+            if len(heap) < beam_size:
+                heapq.heappush(heap, item)
+            else:
+                heapq.heappushpop(heap, item)
+        partial = [[(0.0, [SOS, EOS])] for _ in range(B)]
+        complete = [[] for _ in range(B)]
+        for _ in range(self._max_caption_length):
+            hyps = [(b, lp, sent) for b in range(B) for (lp, sent) in sorted(partial[b], reverse=True)]
+            tokens = np.asarray([sent[1:-1] + [SOS] for (_, _, sent) in hyps], dtype=np.int32)   # last token is never read
+            self._decoder_keras.forward(feats[[b for (b, _, _) in hyps]], tokens)
+            logits = self._decoder_keras.last_logits()
+            logp = logits - np.max(logits, axis=-1, keepdims=True)
+            logp = logp - np.log(np.sum(np.exp(logp), axis=-1, keepdims=True))
+            partial = [[] for _ in range(B)]
+            for (b, lp_prev, sent), row in zip(hyps, logp):
+                top = np.argpartition(row, -beam_size)[-beam_size:]
+                for w in top:
+                    word = int(w) + 1                       # model index -> tokenizer id
+                    lp = float(row[w] + lp_prev)
+                    push(partial[b], (lp, sent[:-1] + [word, sent[-1]]))
+                    if word == EOS:
+                        push(complete[b], (lp, sent))
+        results = []
+        for rank in range(beam_size):
+            row = []
+            for b in range(B):
+                top_p = sorted(partial[b], reverse=True)
+                top_c = sorted(complete[b], reverse=True)
+                cap = top_c[rank] if rank < len(top_c) else (top_p[rank] if rank < len(top_p) else None)
+                row.append(cap[1][1:] if cap is not None else None)
+            results.append(row[0] if B == 1 else row)
+        return results
 
     # ---- forward with stored state (explainers.py:370-436, 1092-1178)
     def _forward_beam_search(self, X, beam_search_captions):

@@ -49,5 +49,33 @@ def main():
         print(path, os.path.getsize(path), "bytes")
 
 
+def lrp_inference_case(kind):
+    """Shared by the fixture generator and the tests (weights are re-synthesised from the seeds, not stored)."""
+    vgg = synth.vgg16_weights(0)
+    dec = synth.decoder_weights(kind, V=30, H=16, E=16, D=512, seed=1)
+    imgs = synth.images(2, 32, 2)
+    yp = np.random.default_rng(3).standard_normal((2, 4, 30))
+    yp[..., -1] = -100.0     # the reference overflows its (V,) buffer when the arg-max is the last index (quirk B10)
+    yp[1, 2, 1] = 50.0       # EOS (id 2) predicted at position 3 of sample 1
+    word_of = {i: "w%d" % i for i in range(1, 31)}
+    word_of[int(np.argmax(yp[0, 1]) + 1)] = "the"    # a stop word
+    return vgg, dec, imgs, yp, word_of
+
+
+def main_lrp_inference():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    _, M = refstub.load_reference()
+    for kind in ("adaptive", "gridtd"):
+        vgg, dec, imgs, yp, word_of = lrp_inference_case(kind)
+        store = {"stop_words": np.array(sorted(set(M.STOP_WORDS)))}
+        for mode in ("mean", "pos_mean", "quantile"):
+            ref = refstub.make_reference_lrp_inference_layer(kind, dec, vgg, mode=mode, word_of=word_of)
+            store[mode] = ref.call([np.zeros((2, 4), dtype=np.int32), imgs, yp.copy()])
+        path = os.path.join(out_dir, "lrp_inference_%s.npz" % kind)
+        np.savez_compressed(path, **store)
+        print(path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    main_lrp_inference()

@@ -151,3 +151,55 @@ def make_reference_explainer(kind, variant, dec, feat, sos=1, eos=2):
         o._output_weight_bm = dec["output_w"]
         o._output_bias_bm = dec["output_b"]
     return o
+
+
+def make_reference_lrp_inference_layer(kind, dec, vgg, mode="mean", sos=1, eos=2, word_of=None):
+    """Reference LRPInferenceLayer{Adaptive,gridTD} (models/model.py:1379, :1693) without its Keras constructor: the
+    NumPy decoder is the reference's own; `_image_model.predict` and `_CNN_explainer.analyze` (TensorFlow in the
+    reference) are served by oracle/encoder_ref.py."""
+    import numpy as np
+    from oracle import encoder_ref as ER
+    _, M = load_reference()
+    cls = M.LRPInferenceLayerAdaptive if kind == "adaptive" else M.LRPInferenceLayergridTD
+    o = object.__new__(cls)
+    o._hidden_dim, o._embedding_dim = dec["hidden_dim"], dec["embedding_dim"]
+    o.D = dec["D"]
+    o._max_caption_length = 20
+    o._preprocessor = _Pre(sos, eos)
+    o._preprocessor._word_of = word_of if word_of is not None else {}
+    o._EOS_ENCODED, o._SOS_ENCODER = eos, sos
+    o._color_conversion = "BGRtoRGB"
+    o._lrp_inference_mode = mode
+
+    class _Img(object):
+        def predict(self, x):
+            f = ER.features(np.asarray(x, dtype=np.float32), vgg)
+            o.L = f.shape[1] * f.shape[2]
+            return f
+    o._image_model = _Img()
+
+    def _grid(x):   # grid-TD layer reads features through a Keras sub-model that already reshapes to (L, D)
+        f = _Img().predict(x)
+        return f.reshape(f.shape[0], -1, f.shape[-1])
+    o._img_feature_input_model_bm = _Predict(_grid)
+    o._CNN_explainer = type("A", (),{"analyze": staticmethod(lambda XR: ER.analyze("lrp.sequential_preset_a", XR[0], XR[1], vgg))})()
+    emb = dec["embedding"]
+    embed = _Predict(lambda idx: emb[np.asarray(idx)][None])
+    if kind == "adaptive":
+        o._embedding = embed
+        o._image_features_wieght, o._image_features_bias = dec["image_features_w"], dec["image_features_b"]
+        o._global_img_feature_weight, o._global_img_feature_bias = dec["global_w"], dec["global_b"]
+        o._lstm_weight_i, o._lstm_weight_h, o._lstm_bias = dec["lstm_wi"], dec["lstm_wh"], dec["lstm_b"]
+        for k in ("Wv", "Wg", "V", "Wx", "Wh", "Ws"):
+            setattr(o, "_" + k, dec[k])
+        o._output_weight, o._output_bias = dec["output_w"], dec["output_b"]
+    else:
+        o._embedding_bm = embed
+        o._image_features_weight_bm, o._image_features_bias_bm = dec["image_features_w"], dec["image_features_b"]
+        o._global_img_feature_weight_bm, o._global_img_feature_bias_bm = dec["global_w"], dec["global_b"]
+        o._language_lstm_weight_i, o._language_lstm_weight_h, o._language_lstm_bias = dec["lang_wi"], dec["lang_wh"], dec["lang_b"]
+        o._top_down_lstm_weight_i, o._top_down_lstm_weight_h, o._top_down_lstm_weight_bias = dec["td_wi"], dec["td_wh"], dec["td_b"]
+        for k in ("W_va", "W_ha", "W_a", "W_x", "W_s", "W_h"):
+            setattr(o, "_" + k, dec[k])
+        o._output_weight_bm, o._output_bias_bm = dec["output_w"], dec["output_b"]
+    return o

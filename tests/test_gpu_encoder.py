@@ -25,6 +25,8 @@ RULES = {
     "z": ("lrp.z", {}, "lrp.z", {}),
     "presetA": ("lrp.sequential_preset_a", {}, "lrp.sequential_preset_a", dict(epsilon=0.01)),
     "a1b0": ("lrp.alpha_1_beta_0", {}, "lrp.alpha_1_beta_0", {}),
+    "a2b1": ("lrp.alpha_2_beta_1", {}, "lrp.alpha_2_beta_1", {}),
+    "ab_3_2_ib": ("lrp.alpha_beta", dict(alpha=3, beta=2, bias=False), "lrp.alpha_beta", dict(alpha=3, beta=2, bias=False)),
     "zplus": ("lrp.z_plus", {}, "lrp.z_plus", {}),
     "zplus_fast": ("lrp.z_plus_fast", {}, "lrp.z_plus_fast", {}),
     "gradient": ("gradient", {}, "gradient", {}),
@@ -141,7 +143,7 @@ def test_chunking_is_invisible():
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("rule,precision", [("presetA", "bf16x3"), ("eps", "bf16x3"), ("presetA", "fp32"), ("eps", "fp32"),
+@pytest.mark.parametrize("rule,precision", [("presetA", "bf16x3"), ("eps", "bf16x3"), ("presetA", "fp32"), ("eps", "fp32"), ("a2b1", "bf16x3"),
                                             ("guided", "bf16x3"), ("ixg", "bf16x3")])
 def test_relevance_matches_oracle_224(rule, precision):
     """BASELINE.json full image size.  Three images, one word each; ~4e7 discrete decisions per image, so a flipped

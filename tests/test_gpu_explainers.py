@@ -98,11 +98,45 @@ def test_gradient_family_explainers(kind):
         assert linf_rel(heat, ref) <= 8e-2
 
 
-def test_greedy_caption_via_beam_search_entry():
+def test_beam_search_matches_host_reimplementation():
+    """explainers.py:51-120: same search on the oracle's logits (Keras logits = explainer logits for adaptive)."""
+    import heapq
     from lrp_imagecaptioning_b200 import synth, explainers as E
+    from oracle import encoder_ref as ER
+    from oracle.decoder_ref import DecoderRef
     model, vgg, dec = _model("adaptive", seed=5)
-    ex = E.ExplainImgCaptioningAdaptiveAttention(model, None, _Provider(), 8)
+    ex = E.ExplainImgCaptioningAdaptiveAttention(model, None, _Provider(), 6)
+    img = synth.images(1, HW, 9)
+    beam = 3
+    got = ex._beam_search((None, img), beam)
+    assert len(got) == beam and all(c[-1] == 2 or len(c) == 7 for c in got)
+    F = ER.features(img, vgg)[0].reshape(-1, 512)
+
+    def logp_next(prefix):
+        o = DecoderRef(dec).forward(F, prefix + [1])
+        row = o.logits[-1] - o.logits[-1].max()
+        return row - np.log(np.exp(row).sum())
+    partial, complete = [(0.0, [1, 2])], []
+
+    def push(h, it):
+        heapq.heappush(h, it) if len(h) < beam else heapq.heappushpop(h, it)
+    for _ in range(6):
+        prev, partial = sorted(partial, reverse=True), []
+        for lp_prev, sent in prev:
+            row = logp_next(sent[1:-1])
+            for w in np.argsort(row)[-beam:]:
+                lp = float(row[w] + lp_prev)
+                push(partial, (lp, sent[:-1] + [int(w) + 1, sent[-1]]))
+                if int(w) + 1 == 2:
+                    push(complete, (lp, sent))
+    top_p, top_c = sorted(partial, reverse=True), sorted(complete, reverse=True)
+    want = [(top_c[r] if r < len(top_c) else top_p[r])[1][1:] for r in range(beam)]
+    assert got == want
+
+
+def test_greedy_is_beam_one():
+    from lrp_imagecaptioning_b200 import synth, explainers as E
+    model, vgg, dec = _model("gridtd", seed=6)
+    ex = E.ExplainImgCaptioningGridTDModel(model, None, _Provider(), 5)
     caps = ex._beam_search((None, synth.images(2, HW, 9)), 1)
-    assert len(caps) == 2 and all(1 <= len(c) <= 8 for c in caps)
-    with pytest.raises(NotImplementedError):
-        ex._beam_search((None, synth.images(1, HW, 9)), 3)
+    assert len(caps) == 1 and len(caps[0]) == 2 and all(len(c) >= 1 for c in caps[0])

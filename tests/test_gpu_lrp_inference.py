@@ -1,0 +1,78 @@
+"""GPU: LRP-inference weights and the fine-tuning step (BASELINE.json configs[4]) against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class _Pre(object):
+    SOS_TOKEN_LABEL_ENCODED = 1
+    EOS_TOKEN_LABEL_ENCODED = 2
+
+    def __init__(self, word_of):
+        self._word_of = word_of
+
+
+class _Provider(object):
+    def __init__(self, word_of):
+        self.caption_preprocessor = _Pre(word_of)
+
+
+def _case(kind):
+    from oracle.make_golden import lrp_inference_case
+    return lrp_inference_case(kind)
+
+
+@pytest.mark.parametrize("mode", ["mean", "pos_mean", "quantile"])
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_lrp_inference_weights_match_oracle(kind, mode):
+    from lrp_imagecaptioning_b200.model import CaptioningModel
+    from lrp_imagecaptioning_b200 import lrp_inference as LI
+    from oracle.lrp_inference_ref import lrp_inference_weights
+    vgg, dec, imgs, yp, word_of = _case(kind)
+    model = CaptioningModel(kind, vgg, dec, image_hw=32, precision="bf16x3")
+    cls = LI.LRPInferenceLayerAdaptive if kind == "adaptive" else LI.LRPInferenceLayergridTD
+    layer = cls(model, _Provider(word_of), 16, 16, 4, 512, "vgg16", mode, stop_words={"the"})
+    got = layer.call([np.zeros((2, 4), np.int32), imgs, yp])
+    ref = lrp_inference_weights(dec, vgg, imgs, yp, eos=2, word_of=word_of, stop_words={"the"}, mode=mode)
+    assert got.shape == ref.shape == yp.shape
+    assert np.array_equal(got != 1, ref != 1)
+    assert np.abs(got - ref).max() <= 2e-3 * max(1e-3, np.abs(ref - 1).max()) + 1e-5
+    with pytest.raises(NotImplementedError):
+        cls(model, _Provider(word_of), 16, 16, 4, 512, "vgg16", "bogus")
+
+
+def test_differentiable_model_matches_oracle_logits():
+    """The torch training model implements the Keras step math: adaptive logits equal the oracle's forward."""
+    import torch
+    from lrp_imagecaptioning_b200.model import CaptioningModel
+    from lrp_imagecaptioning_b200.lrp_inference import CaptionerTorch
+    from oracle import encoder_ref as ER
+    from oracle.decoder_ref import DecoderRef
+    vgg, dec, imgs, yp, _ = _case("adaptive")
+    model = CaptioningModel("adaptive", vgg, dec, image_hw=32, precision="fp32")
+    net = CaptionerTorch(model)
+    cap = np.array([[5, 9, 3, 7], [4, 4, 11, 6]])
+    tok_in = np.concatenate([np.ones((2, 1), int), cap[:, :-1]], axis=1)
+    with torch.no_grad():
+        lg = net(torch.as_tensor(tok_in).cuda(), torch.as_tensor(imgs).cuda()).cpu().numpy()
+    for b in range(2):
+        F = ER.features(imgs[b:b + 1], vgg)[0].reshape(-1, 512)
+        o = DecoderRef(dec).forward(F, list(cap[b]))
+        assert np.abs(lg[b] - o.logits).max() <= 1e-3 * np.abs(o.logits).max()
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_fine_tune_step_runs_and_learns(kind):
+    from lrp_imagecaptioning_b200.model import CaptioningModel
+    from lrp_imagecaptioning_b200.lrp_inference import LRPInferenceTrainer
+    vgg, dec, imgs, yp, word_of = _case(kind)
+    model = CaptioningModel(kind, vgg, dec, image_hw=32, precision="bf16x3")
+    tr = LRPInferenceTrainer(model, _Provider(word_of), "mean", learning_rate=1e-4)
+    g = np.random.default_rng(0)
+    cap = g.integers(3, 29, size=(2, 4))
+    tok_in = np.concatenate([np.ones((2, 1), int), cap[:, :-1]], axis=1)
+    y = np.eye(30, dtype=np.float32)[cap - 1]
+    losses = [tr.step(tok_in, imgs, y) for _ in range(6)]
+    assert all(np.isfinite(losses)) and min(losses[1:]) < losses[0], losses
+    assert tr.explained_words_total > 0

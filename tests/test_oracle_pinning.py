@@ -123,3 +123,22 @@ def test_encoder_oracle_parameter_checks():
         ER.analyze("lrp.alpha_beta", x, R, W)
     with pytest.raises(ValueError):
         ER.analyze("lrp.alpha_beta", x, R, W, alpha=2, beta=0.5)
+
+
+# ---------------------------------------------------------------- LRP-inference weights (models/model.py:1641-1691, 2013-2062)
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_lrp_inference_oracle_matches_reference_fixture(kind):
+    """Fixture = output of the reference's own LRPInferenceLayer*.call under the Keras stub (encoder served by the
+    torch oracle, since TensorFlow is unavailable)."""
+    from oracle.make_golden import lrp_inference_case
+    from oracle.lrp_inference_ref import lrp_inference_weights
+    z = np.load(os.path.join(GOLD, "lrp_inference_%s.npz" % kind))
+    vgg, dec, imgs, yp, word_of = lrp_inference_case(kind)
+    stop = set(str(s) for s in z["stop_words"])
+    for mode in ("mean", "pos_mean", "quantile"):
+        got = lrp_inference_weights(dec, vgg, imgs, yp, eos=2, word_of=word_of, stop_words=stop, mode=mode)
+        assert got.shape == z[mode].shape
+        assert np.array_equal(got != 1, z[mode] != 1)          # same words weighted: stop word skipped, EOS stops
+        assert np.abs(got - z[mode]).max() <= 1e-6
+    with pytest.raises(NotImplementedError):
+        lrp_inference_weights(dec, vgg, imgs, yp, eos=2, mode="bogus")

@@ -1,0 +1,20 @@
+"""Short encoder-only workload for ncu: forward of 4 images, then the relevance backward for 80 words (20 per image)
+at 224x224, epsilon rule.  `ncu -k regex:tc_conv_kernel -s 12 -c 12` captures the 12 transposed-conv launches."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lrp_imagecaptioning_b200 import synth, _lib
+from lrp_imagecaptioning_b200.encoder import ImageModel, RuleSpec
+
+n_img, per = 4, 20
+m = ImageModel(synth.vgg16_weights(0), image_hw=224, precision="bf16x3")
+m.set_chunk_words(n_img * per)
+x = synth.images(n_img, 224, 1)
+m.forward(x, RuleSpec(_lib.RULE_EPSILON, epsilon=0.01))
+F = m.features()
+idx = np.repeat(np.arange(n_img), per).astype(np.int32)
+R = (F[torch.as_tensor(idx, device=F.device).long()] * torch.randn((len(idx),) + tuple(F.shape[1:]), device=F.device)).contiguous()
+out = m.relevance(idx, R)
+torch.cuda.synchronize()
+print("ok", float(out.abs().max()))

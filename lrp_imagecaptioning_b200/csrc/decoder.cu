@@ -21,7 +21,7 @@ Decoder::~Decoder() {
   DevBuf* bufs[] = {&F_, &Vp_, &P_, &a_, &gp_, &tok_, &logitk_, &logits_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_,
                     &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
                     &Z_, &hp_, &sg_, &sp_, &e_, &hc_, &d_wimg_, &d_wt_, &d_order_, &Rh1_, &Rh2_, &Rh2n_, &Rc1_, &Rc2_,
-                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_};
+                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_, &As_, &C32_};
   for (DevBuf* b : bufs) b->release();
 }
 
@@ -59,6 +59,50 @@ int Decoder::upload_cat(const float* a, int ra, const float* b, int rb, int cols
     }
   }
   return upload(t.data(), t.size(), out);
+}
+
+// rows of a stacked over rows of b, column slice -> split-bf16 [rows][ncols] (hi plane then lo plane)
+int Decoder::upload_split(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, void** out) {
+  LRPCAP_REQUIRE(a && b, kErrInvalidArg, "decoder_create: missing weight tensor");
+  const int R = ra + rb;
+  const size_t n = (size_t)R * ncols;
+  std::vector<__nv_bfloat16> sp(2 * n);
+  for (int r = 0; r < R; ++r) {
+    const float* src = (r < ra) ? a + (size_t)r * cols : b + (size_t)(r - ra) * cols;
+    for (int c = 0; c < ncols; ++c) {
+      const float v = src[col0 + c];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      sp[(size_t)r * ncols + c] = hi;
+      sp[n + (size_t)r * ncols + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+  void* p = nullptr;
+  LRPCAP_CUDA(cudaMalloc(&p, 2 * n * sizeof(__nv_bfloat16)));
+  owned_.push_back(p);
+  LRPCAP_CUDA(cudaMemcpy(p, sp.data(), 2 * n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  *out = p;
+  return kOk;
+}
+
+int Decoder::gemm_tc(const double* A, int M, int K, const void* Bsplit, int N, double* C, cudaStream_t s) {
+  if (M <= 0) return kOk;
+  const int Hrows = (M + 15) / 16;             // rows laid out as a [1, Hrows, 16, K] "image" for the 1x1-conv kernel
+  const size_t nA = (size_t)Hrows * 16 * K, nC = (size_t)Hrows * 16 * N;
+  LRPCAP_TRY(As_.ensure(nA * 4));
+  LRPCAP_TRY(C32_.ensure(nC * 4));
+  __nv_bfloat16* hi = As_.as<__nv_bfloat16>();
+  if ((size_t)M * K < nA) LRPCAP_CUDA(cudaMemsetAsync(As_.p, 0, nA * 4, s));   // zero the padded rows
+  f64_to_split_strided_kernel<<<nblk((size_t)M * K, 256), 256, 0, s>>>(A, hi, hi + nA, (size_t)M * K);
+  TcConvArgs a;
+  a.A = As_.p; a.A_elems = nA; a.n_items = 1; a.H = Hrows; a.W = 16; a.C = K;
+  a.B = Bsplit; a.B_elems = (size_t)N * K; a.taps = 1; a.Nout = N;
+  a.epi.mode = EPI_RAW;
+  a.epi.out_f32 = C32_.as<float>();
+  LRPCAP_TRY(tc_conv_launch(a, s));
+  f32_to_f64_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(C32_.as<float>(), C, (size_t)M * N);
+  launches_ += 3;
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
 }
 
 int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_token, int keras_logits) {
@@ -111,6 +155,14 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
     UP(d->upload_cat(w->W_x, H + 2 * E, w->W_h, H, H, 0, H, false, &d->Wsx_));
     UP(d->upload(w->W_s, (size_t)H * H, &d->Wss_));
     UP(d->upload(w->W_a, H, &d->Va_));
+  }
+  if (H % 64 == 0 && E % 64 == 0 && !getenv("LRPCAP_DECODER_FP64_GEMM")) {
+    if (w->kind == LRPCAP_DECODER_ADAPTIVE) {
+      UP(d->upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, &d->Wgate1TC_));
+    } else {
+      UP(d->upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, &d->Wgate1TC_));
+      UP(d->upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, &d->Wgate2TC_));
+    }
   }
   if (H % 64 == 0 && D % 64 == 0 && !getenv("LRPCAP_DECODER_FP64_GEMM")) {
     // B operand of the [words*L, H] x [H, D] relevance GEMM: B[d][h] = W_if[d][h] -- the Keras (D, H) layout as is
@@ -387,7 +439,8 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
       if (na == 0) continue;
       lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), zg1_.as<double>(), c1_.as<double>(),
                                          Rc1_.as<double>(), Rh1_.as<double>(), nullptr, U_.as<double>(), T, H);
-      LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
+      if (Wgate1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate1TC_, Kin1_, Y_.as<double>(), s));
+      else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
       lrp_scatter_adaptive_kernel<<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh1_.as<double>(),
                                                      Rglob_.as<double>(), rword_.as<double>(), T, H, E);
       launches_ += 2;
@@ -402,7 +455,8 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
       if (na == 0) continue;
       lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia2_.as<double>(), fa2_.as<double>(), zg2_.as<double>(), c2_.as<double>(),
                                          Rc2_.as<double>(), Rh2_.as<double>(), nullptr, U_.as<double>(), T, H);
-      LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, H, nullptr, s));
+      if (Wgate2TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate2TC_, Kin2_, Y_.as<double>(), s));
+      else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, H, nullptr, s));
       // Rctx_ doubles as the "extra" (r_s + R_h1) buffer of the top-down cell
       lrp_scatter_lang_kernel<<<na, 256, 0, s>>>(wr, i, XH2_.as<double>(), Y_.as<double>(), chat_.as<double>(),
                                                  ctx_.as<double>(), s_.as<double>(), beta_.as<double>(),
@@ -411,7 +465,8 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
       // top-down cell: Rc1 += extra (Rh1 is already folded into extra, so pass a zero-free "Rh" = extra, extra = null)
       lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), zg1_.as<double>(), c1_.as<double>(),
                                          Rc1_.as<double>(), Rctx_.as<double>(), nullptr, U_.as<double>(), T, H);
-      LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
+      if (Wgate1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate1TC_, Kin1_, Y_.as<double>(), s));
+      else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
       lrp_scatter_td_kernel<<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh2n_.as<double>(),
                                                Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
                                                rword_.as<double>(), T, H, E);

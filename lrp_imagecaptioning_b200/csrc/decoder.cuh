@@ -48,13 +48,18 @@ class Decoder {
                  double** out);
   int gemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
            const double* bias, cudaStream_t s);
-  int features_gemm(int m, cudaStream_t s);   // YF_[m*L, D] = UV_[m*L, H] * W_if^T (tensor cores when shapes allow)
+  int features_gemm(int m, cudaStream_t s);
+  // C[M,N] (fp64) = A[M,K] (fp64) * B^T with B given as split-bf16 [N][K]: tcgen05 path for the per-step relevance GEMMs
+  int gemm_tc(const double* A, int M, int K, const void* Bsplit, int N, double* C, cudaStream_t s);
+  int upload_split(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, void** out);   // YF_[m*L, D] = UV_[m*L, H] * W_if^T (tensor cores when shapes allow)
   int sort_words(const int* h_word_img, const int* h_word_t, int n_words, cudaStream_t s);
 
   int kind_ = 0, V_ = 0, H_ = 0, E_ = 0, D_ = 0, L_ = 0, N_ = 0, T_ = 0, sos_ = 1, keras_logits_ = 0;
   int Kin1_ = 0, Kin2_ = 0;   // LSTM input widths incl. recurrent part (adaptive: Kin1 = 2E+H)
   long long launches_ = 0;
   bool tc_features_ = false;
+  void *Wgate1TC_ = nullptr, *Wgate2TC_ = nullptr;   // split-bf16 [Kin][H]: g-gate slices as K-major B operands
+  DevBuf As_, C32_;
   void* WifTC_ = nullptr;   // split-bf16 [D][H]: K-major B operand of the image_features relevance GEMM
   DevBuf UVs_, YF32_, gemm_ws_;
   std::vector<void*> owned_;

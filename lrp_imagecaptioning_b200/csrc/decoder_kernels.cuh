@@ -103,6 +103,16 @@ __global__ void f64_to_split_kernel(const double* __restrict__ in, __nv_bfloat16
   hi[i] = h;
   lo[i] = l;
 }
+// as f64_to_split_kernel, the two planes given separately (the destination may be padded beyond n)
+__global__ void f64_to_split_strided_kernel(const double* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                            __nv_bfloat16* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  __nv_bfloat16 h, l;
+  split_bf16((float)in[i], h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
 __global__ void round_f32_kernel(double* x, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = f32r(x[i]);

@@ -30,6 +30,7 @@ METRIC = "explained words/sec (full LRP to pixels)"
 UNIT = "words/s"
 N_IMG, T_WORDS, VOCAB, HW = 64, 20, 10000, 224
 ENC_GFLOP_PER_WORD = 30.69      # one transposed-conv sweep of VGG16
+NCU_DRAM_MB_PER_WORD = 94.5     # measured: profiles/r01_ncu_full_tc_conv_bwd_summary.csv
 
 
 def peaks():
@@ -199,6 +200,21 @@ def run_ours(args, rank, local_rank, world):
     launches = (eng.launches() - l0) // max(args.steps, 1)
     ms_e2e = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
 
+    # phase breakdown of one extra resident step (CUDA events on the launching stream)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    model.image_model.forward(x_dev, eng.rule)
+    feats = model.image_model.features()
+    ev[1].record()
+    eng.decoder.forward(feats, T=T_WORDS, greedy=True, eos=eng.eos)
+    ev[2].record()
+    R_head, _, _ = eng.decoder.relevance(wi, wt, want_words=False, want_attention=False)
+    ev[3].record()
+    model.image_model.relevance(wi, R_head.view(-1, HW // 16, HW // 16, R_head.shape[-1]))
+    ev[4].record()
+    torch.cuda.synchronize()
+    phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(("encoder_forward", "decoder_forward", "decoder_relevance", "encoder_relevance"))}
+
     total_words = n_words * world
     value = total_words / (ms / 1000.0)
     peak_tf, peak_bw, peak_src = peaks()
@@ -206,7 +222,10 @@ def run_ours(args, rank, local_rank, world):
     achieved = (tc_flops / 1e12) / (tc_ms / 1e3) if tc_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "tc_conv_kernel<BN, EPI_BWD> (tcgen05 transposed conv + fused rule epilogue)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": None, "peak_source": "%s bf16 cuBLAS (sustained)" % peak_src,
+                "traffic": NCU_DRAM_MB_PER_WORD * 1e6 * n_words / max(tc_n / max(args.steps, 1), 1.0),
+                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (profiles/r01_ncu_full_tc_conv_bwd_summary.csv, "
+                                "80 words: 7.56 GB = %.1f MB/word; algorithmic message traffic 95.1 MB/word), scaled to this run's words per launch" % NCU_DRAM_MB_PER_WORD,
+                "peak_source": "%s bf16 cuBLAS (sustained)" % peak_src,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC of the transposed convs, %.2f GFLOP/word) / CUDA-event "
                         "kernel time; every algorithmic MAC is 3 bf16 tensor-core MACs (hi*hi + hi*lo + lo*hi), so tensor-pipe "
                         "work is 3x this figure" % ENC_GFLOP_PER_WORD,
@@ -221,7 +240,7 @@ def run_ours(args, rank, local_rank, world):
            "data": "synthetic", "config": config_dict(args, world), "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": total_words / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
                    "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4 + cap_host.nbytes)},
-           "roofline": roofline}
+           "phases_ms": phases, "roofline": roofline}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t_img, t_word = cpu_reference_sample(n_words=2)
         out["cpu_baseline"] = {"value": T_WORDS / (t_img + T_WORDS * t_word), "unit": UNIT, "cores": os.cpu_count() or 1,

@@ -232,7 +232,8 @@ def run_ours(args, rank, local_rank, world):
                 "tensor_pipe_frac": 3.0 * achieved / peak_tf if peak_tf else None,
                 "kernel_ms_per_step": tc_ms / max(args.steps, 1), "kernel_launches_per_step": tc_n / max(args.steps, 1),
                 "share_of_step": (tc_ms / max(args.steps, 1)) / ms if ms > 0 else None,
-                "forward_tc_ms_per_step": prof["tc_fwd"][0] / max(args.steps, 1)}
+                "forward_tc_ms_per_step": prof["tc_fwd"][0] / max(args.steps, 1),
+                "last_dgrad_ms_per_step": prof["last"][0] / max(args.steps, 1)}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate) encoder / f64 decoder" if args.precision == "bf16x3"

@@ -84,10 +84,11 @@ int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words);
 int lrpcap_encoder_set_promote(lrpcap_encoder_t* enc, int every_k_steps);
 long long lrpcap_encoder_launches(lrpcap_encoder_t* enc);
 /* Kernel timing (CUDA events on the launching stream around every convolution launch) for roofline reporting.
- * h_out9: per class {0: tcgen05 transposed conv (relevance), 1: tcgen05 forward conv, 2: fp32 SIMT conv}
- * [total ms, algorithmic FLOPs, launches]; reading synchronises and resets the counters. */
+ * h_out12: per class {0: tcgen05 transposed conv (relevance), 1: tcgen05 forward conv, 2: fp32 SIMT conv,
+ * 3: last transposed conv (64 -> 3 channels) + input re-weighting} [total ms, algorithmic FLOPs, launches];
+ * reading synchronises and resets the counters. */
 int lrpcap_encoder_profile(lrpcap_encoder_t* enc, int enable);
-int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out9);
+int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out12);
 
 /* ----------------------------------------------------------------------------------------------- decoder */
 

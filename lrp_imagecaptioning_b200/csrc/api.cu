@@ -120,9 +120,9 @@ int lrpcap_encoder_profile(lrpcap_encoder_t* enc, int enable) {
   return kOk;
 }
 
-int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out9) {
+int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out12) {
   LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_profile_read: null handle");
-  return enc->impl->profile_read(h_out9);
+  return enc->impl->profile_read(h_out12);
 }
 
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,

@@ -156,7 +156,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
 
 int Encoder::profile_read(double* out) {
   LRPCAP_REQUIRE(out != nullptr, kErrInvalidArg, "profile_read: null output");
-  for (int i = 0; i < 9; ++i) out[i] = 0.0;
+  for (int i = 0; i < 12; ++i) out[i] = 0.0;
   for (ProfRec& r : prof_) {
     LRPCAP_CUDA(cudaEventSynchronize(r.b));
     float ms = 0.f;
@@ -265,6 +265,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
       ep.gmode = gmode;
       ep.eps = rule.epsilon;
       ep.rule_bias = rule.bias;
+      ep.g_up = L.pool_after ? 2 : 1;
       if (gmode != G_NONE) { ep.G = Gl; ep.Mseed = Ml; }
       LRPCAP_TRY(conv(l, false, WS_ALL, X, X_elems, m, ep, s));
 
@@ -277,6 +278,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
         ez.x_act_elems = (size_t)m * oe;
         ez.G = Gl;
         ez.Mseed = Ml;
+        ez.g_up = L.pool_after ? 2 : 1;
         if (l == 0 && ab) {
           LRPCAP_TRY(posneg_.ensure((size_t)m * hw_ * hw_ * 6 * sizeof(float)));
           LRPCAP_TRY(make_posneg(img, posneg_.as<float>(), (size_t)m * hw_ * hw_, s));
@@ -383,12 +385,25 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       ep.out_msg = msg_[cur ^ 1].p;
       ep.Gin2 = inh ? G2_[l - 1].as<float>() : nullptr;
       ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1) * mul;
+      ep.out_planar8 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only, 8 channels at a time
       LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l) * mul, m, ep, s, inh));
       cur ^= 1;
+    }
+    ProfRec rec{};
+    if (profile_) {
+      LRPCAP_CUDA(cudaEventCreate(&rec.a));
+      LRPCAP_CUDA(cudaEventCreate(&rec.b));
+      rec.cls = 3;
+      rec.flops = 2.0 * 9.0 * (double)m * hw_ * hw_ * 64.0 * mul * 3.0;
+      LRPCAP_CUDA(cudaEventRecord(rec.a, s));
     }
     LRPCAP_TRY(last_dgrad(msg_[cur].p, (size_t)m * layer_out_elems(0) * mul, split(), reinterpret_cast<const float*>(Wa),
                           reinterpret_cast<const float*>(Wb), X0_.as<float>(), idx, d_R_pix + (size_t)w0 * pix_elems, m,
                           hw_, hw_, 64 * mul, mult, s));
+    if (profile_) {
+      LRPCAP_CUDA(cudaEventRecord(rec.b, s));
+      prof_.push_back(rec);
+    }
     ++launches_;
   }
   return kOk;

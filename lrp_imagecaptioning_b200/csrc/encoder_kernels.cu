@@ -103,14 +103,15 @@ __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems,
       if (v[p][i] > m[i]) { m[i] = v[p][i]; am[i] = p; }   // strict '>' keeps the first maximum
   }
   if (pooled) ST::template store<4>(pooled, pooled_elems, (((size_t)item * Ho + yo) * Wo + xo) * C + c, m);
-  if (G) {
+  if (G) {   // G is stored channel-tiled with the 2x2 sub-pixel as a plane index (epilogue.cuh: g_offset, up = 2)
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       float g[4];
-      load_f32<4>(G + off[p], g);
+      float* gp = G + g_offset(item, 2 * yo + (p >> 1), 2 * xo + (p & 1), c, H, W, C, 2);
+      load_f32<4>(gp, g);
 #pragma unroll
       for (int i = 0; i < 4; ++i) g[i] = (am[i] == p) ? g[i] : 0.f;
-      store_f32<4>(G + off[p], g);
+      store_f32<4>(gp, g);
     }
   }
 }
@@ -146,20 +147,29 @@ __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict
 }
 
 // ------------------------------------------------------------------ last transposed conv (C -> 3) + re-weighting
-// HBM-bound (12.85 MB in, 0.6 MB out per word at 224x224). Weights sit in constant memory so every FMA takes its
-// weight as a uniform constant operand; a thread owns two horizontally adjacent pixels and re-uses its 3x4 window.
-constexpr int kLTY = 16, kLTX = 32;   // tile (rows x cols), 256 threads x 2 pixels
-constexpr int kLC = 16;               // channel chunk staged in shared memory
-constexpr int kLastMaxC = 128;   // 64 channels, or 2 x 64 for the dual (beta != 0) message
-__constant__ float c_wlast[2][9 * kLastMaxC * 3];
+// fp32-FMA bound (1728 FMA per pixel; 12.85 MB in, 0.6 MB out per word at 224x224). The message arrives channel-planar,
+// [item][C/8][H][W][8] (EpiParams::out_planar8 of the layer above), so that the halo patch of one 8-channel chunk is a
+// run of contiguous 16 B pieces -- with the pixel-major layout every chunk pass touched every 128 B line of the patch
+// again and the kernel was DRAM-bound on re-fetches (ncu: 78 % DRAM, 20 % FMA). A thread owns a 2 x 4 pixel block:
+// per channel it loads its 4 x 6 window (4 LDS.128 + 4 LDS.64) and the channel's 27 weights (7 broadcast LDS.128 from a
+// shared-memory copy) for 216 FMAs, which keeps the LSU well below the FMA pipe.
+constexpr int kLTY = 32, kLTX = 32;   // tile (rows x cols): 128 threads x (2 x 4) pixels
+constexpr int kLThreads = 128;
+constexpr int kLC = 8;                // channel chunk staged in shared memory
+constexpr int kLastMaxC = 128;        // 64 channels, or 2 x 64 for the dual (beta != 0) message
+constexpr int kLPSX = kLTX + 4, kLPSY = kLTY + 2;   // halo patch; row pitch padded to a multiple of 4 floats (LDS.128)
+constexpr int kLHalo = kLPSY * (kLTX + 2), kLIters = (kLHalo + kLThreads - 1) / kLThreads;
+constexpr int kLWPitch = 28;          // 27 weights per channel (tap-major, 3 colours), padded to 7 x float4
 
 template <class ST, bool DUAL, int C>
-__global__ void __launch_bounds__(256)
-last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* __restrict__ images,
-                  const int* __restrict__ img_index, float* __restrict__ out, int H, int W, int tiles_x,
-                  int tiles_y, int mult) {
-  constexpr int PSX = kLTX + 2, PSY = kLTY + 2;
-  __shared__ float S[kLC][PSX * PSY + 1];
+__global__ void __launch_bounds__(kLThreads, 3)
+last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* __restrict__ Wa,
+                  const float* __restrict__ Wb, const float* __restrict__ images, const int* __restrict__ img_index,
+                  float* __restrict__ out, int H, int W, int tiles_x, int tiles_y, int mult) {
+  extern __shared__ __align__(16) float last_smem[];
+  float (*S)[kLPSY * kLPSX] = reinterpret_cast<float (*)[kLPSY * kLPSX]>(last_smem);
+  float* Wsa = last_smem + kLC * kLPSY * kLPSX;      // [C][28]
+  float* Wsb = Wsa + C * kLWPitch;                   // [C][28] (DUAL only)
 
   int bid = blockIdx.x;
   const int tiles = tiles_x * tiles_y;
@@ -167,66 +177,107 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
   bid -= item * tiles;
   const int y0 = (bid / tiles_x) * kLTY, x0 = (bid % tiles_x) * kLTX;
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = (tid & 15) * 2;
+  const int ty = (tid >> 3) * 2, tx = (tid & 7) * 4;
 
-  float ca[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, cb[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  // weights arrive as [tap][C][3]; shared copy is [c][tap * 3 + colour]
+  for (int i = tid; i < 9 * C * 3; i += kLThreads) {
+    const int tap = i / (C * 3), rem = i - tap * C * 3, c = rem / 3, ci = rem - c * 3;
+    Wsa[c * kLWPitch + tap * 3 + ci] = __ldg(Wa + i);
+    if (DUAL) Wsb[c * kLWPitch + tap * 3 + ci] = __ldg(Wb + i);
+  }
+
+  float ca[2][4][3], cb[2][4][3];
 #pragma unroll
-  for (int c0 = 0; c0 < C; c0 += kLC) {   // fully unrolled: every constant-bank offset below is an immediate
-    __syncthreads();
-    for (int pix = tid; pix < PSX * PSY; pix += 256) {     // one halo pixel (16 channels = 4 x 16 B loads) per thread
-      const int py = pix / PSX, px = pix - py * PSX;
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) ca[py][px][ci] = cb[py][px][ci] = 0.f;
+
+#pragma unroll 1
+  for (int c0 = 0; c0 < C; c0 += kLC) {
+    // stage the halo patch of this channel chunk: all global loads are issued before the barrier (they overlap the
+    // other warps' FMAs on the previous chunk), the shared-memory stores after it
+    float v[kLIters][kLC];
+#pragma unroll
+    for (int it = 0; it < kLIters; ++it) {
+      const int pix = tid + it * kLThreads;
+      const int py = pix / (kLTX + 2), px = pix - py * (kLTX + 2);
       const int gy = y0 + py - 1, gx = x0 + px - 1;
-      float v[kLC];
 #pragma unroll
-      for (int i = 0; i < kLC; ++i) v[i] = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-        ST::template load<kLC>(msg, msg_elems, (((size_t)item * H + gy) * W + gx) * C + c0, v);
-#pragma unroll
-      for (int i = 0; i < kLC; ++i) S[i][pix] = v[i];
+      for (int i = 0; i < kLC; ++i) v[it][i] = 0.f;
+      if (pix < kLHalo && gy >= 0 && gy < H && gx >= 0 && gx < W)
+        ST::template load<kLC>(msg, msg_elems, ((((size_t)item * (C / kLC) + c0 / kLC) * H + gy) * W + gx) * kLC, v[it]);
     }
     __syncthreads();
 #pragma unroll
+    for (int it = 0; it < kLIters; ++it) {
+      const int pix = tid + it * kLThreads;
+      const int py = pix / (kLTX + 2), px = pix - py * (kLTX + 2);
+      if (pix < kLHalo) {
+#pragma unroll
+        for (int i = 0; i < kLC; ++i) S[i][py * kLPSX + px] = v[it][i];
+      }
+    }
+    __syncthreads();
+#pragma unroll 2
     for (int k = 0; k < kLC; ++k) {
-      float win[3][4];
+      float win[4][6];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 4; ++r) {
+        const float* row = &S[k][(ty + r) * kLPSX + tx];
+        const float4 a = *reinterpret_cast<const float4*>(row);
+        const float2 b = *reinterpret_cast<const float2*>(row + 4);
+        win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w; win[r][4] = b.x; win[r][5] = b.y;
+      }
+      float wa[kLWPitch], wb[kLWPitch];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) win[r][q] = S[k][(ty + r) * PSX + tx + q];
+      for (int i = 0; i < kLWPitch / 4; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(Wsa + (c0 + k) * kLWPitch + 4 * i);
+        wa[4 * i] = t.x; wa[4 * i + 1] = t.y; wa[4 * i + 2] = t.z; wa[4 * i + 3] = t.w;
+        if (DUAL) {
+          const float4 u = *reinterpret_cast<const float4*>(Wsb + (c0 + k) * kLWPitch + 4 * i);
+          wb[4 * i] = u.x; wb[4 * i + 1] = u.y; wb[4 * i + 2] = u.z; wb[4 * i + 3] = u.w;
+        }
+      }
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        const float* wa = &c_wlast[0][(tap * C + c0 + k) * 3];
-        const float* wb = &c_wlast[1][(tap * C + c0 + k) * 3];
 #pragma unroll
-        for (int px = 0; px < 2; ++px) {
-          const float sv = win[tap / 3][tap % 3 + px];
+        for (int py = 0; py < 2; ++py)
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci) {
-            ca[px][ci] = fmaf(sv, wa[ci], ca[px][ci]);
-            if (DUAL) cb[px][ci] = fmaf(sv, wb[ci], cb[px][ci]);
+          for (int px = 0; px < 4; ++px) {
+            const float sv = win[tap / 3 + py][tap % 3 + px];
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+              ca[py][px][ci] = fmaf(sv, wa[tap * 3 + ci], ca[py][px][ci]);
+              if (DUAL) cb[py][px][ci] = fmaf(sv, wb[tap * 3 + ci], cb[py][px][ci]);
+            }
           }
-        }
       }
     }
   }
-  const int y = y0 + ty;
-  if (y >= H) return;
+  const int img = mult ? __ldg(img_index + item) : 0;
 #pragma unroll
-  for (int px = 0; px < 2; ++px) {
-    const int x = x0 + tx + px;
-    if (x >= W) continue;
-    const size_t pix = (size_t)y * W + x;
-    float* o = out + ((size_t)item * H * W + pix) * 3;
-    if (mult) {
-      const int img = __ldg(img_index + item);
-      const float* xi = images + ((size_t)img * H * W + pix) * 3;
+  for (int py = 0; py < 2; ++py) {
+    const int y = y0 + ty + py;
+    if (y >= H) continue;
 #pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float xv = __ldg(xi + ci);
-        o[ci] = DUAL ? (xv >= 0.f ? xv * ca[px][ci] : xv * cb[px][ci]) : xv * ca[px][ci];
+    for (int px = 0; px < 4; ++px) {
+      const int x = x0 + tx + px;
+      if (x >= W) continue;
+      const size_t pix = (size_t)y * W + x;
+      float* o = out + ((size_t)item * H * W + pix) * 3;
+      if (mult) {
+        const float* xi = images + ((size_t)img * H * W + pix) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float xv = __ldg(xi + ci);
+          o[ci] = DUAL ? (xv >= 0.f ? xv * ca[py][px][ci] : xv * cb[py][px][ci]) : xv * ca[py][px][ci];
+        }
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) o[ci] = ca[py][px][ci];
       }
-    } else {
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) o[ci] = ca[px][ci];
     }
   }
 }
@@ -309,20 +360,31 @@ int seed_message(const float* R, const float* M, const float* M2, const int* img
   return kOk;
 }
 
+template <class ST, bool DUAL, int C>
+int launch_last(const void* msg, size_t msg_elems, const float* Wa, const float* Wb, const float* images,
+                const int* img_index, float* out, int H, int W, int tiles_x, int tiles_y, int mult, unsigned grid,
+                cudaStream_t s) {
+  const int smem = (kLC * kLPSY * kLPSX + (DUAL ? 2 : 1) * C * kLWPitch) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    LRPCAP_CUDA(cudaFuncSetAttribute(last_dgrad_kernel<ST, DUAL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  last_dgrad_kernel<ST, DUAL, C><<<grid, kLThreads, smem, s>>>(msg, msg_elems, Wa, Wb, images, img_index, out, H, W,
+                                                               tiles_x, tiles_y, mult);
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, const float* Wb, const float* images,
                const int* img_index, float* out, int items, int H, int W, int C, int mult, cudaStream_t s) {
-  LRPCAP_REQUIRE(C % kLC == 0 && C <= kLastMaxC, kErrShape, "last_dgrad: C must be a multiple of %d and <= %d", kLC, kLastMaxC);
+  LRPCAP_REQUIRE(C == 64 || C == 128, kErrShape, "last_dgrad: C must be 64 (or 128 for the dual message), got %d", C);
   const int tiles_x = ceil_div(W, kLTX), tiles_y = ceil_div(H, kLTY);
   const long long blocks = (long long)items * tiles_x * tiles_y;
   LRPCAP_REQUIRE(blocks > 0 && blocks < (1ll << 31), kErrShape, "last_dgrad: grid out of range");
   const unsigned g = (unsigned)blocks;
-  const size_t wbytes = (size_t)9 * C * 3 * sizeof(float);
-  // stream-ordered refresh of the constant bank (one encoder stream at a time uses it)
-  LRPCAP_CUDA(cudaMemcpyToSymbolAsync(c_wlast, Wa, wbytes, 0, cudaMemcpyDeviceToDevice, s));
-  if (Wb) LRPCAP_CUDA(cudaMemcpyToSymbolAsync(c_wlast, Wb, wbytes, sizeof(float) * 9 * kLastMaxC * 3, cudaMemcpyDeviceToDevice, s));
-  LRPCAP_REQUIRE(C == 64 || C == 128, kErrShape, "last_dgrad: C must be 64 (or 128 for the dual message)");
 #define LRPCAP_LAUNCH_LAST(ST, DUAL, CC) \
-  last_dgrad_kernel<ST, DUAL, CC><<<g, 256, 0, s>>>(msg, msg_elems, images, img_index, out, H, W, tiles_x, tiles_y, mult)
+  return launch_last<ST, DUAL, CC>(msg, msg_elems, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s)
 #define LRPCAP_LAUNCH_LAST_C(ST, DUAL) \
   do { if (C == 64) LRPCAP_LAUNCH_LAST(ST, DUAL, 64); else LRPCAP_LAUNCH_LAST(ST, DUAL, 128); } while (0)
   if (split) {
@@ -332,7 +394,6 @@ int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, c
   }
 #undef LRPCAP_LAUNCH_LAST_C
 #undef LRPCAP_LAUNCH_LAST
-  LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 

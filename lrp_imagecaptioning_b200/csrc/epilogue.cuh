@@ -28,7 +28,33 @@ struct EpiDev {
   const float* Gin2;
   int up;
   int relu_acc;
+  int g_up;           // layout of G written by the forward epilogues (see g_offset)
+  int out_planar8;    // backward: message written as [items][Nout/8][H][W][8]
 };
+
+// Per-image multipliers G are only ever touched by epilogues (never by TMA), so they are stored in the order the
+// backward epilogue reads them: 16-channel runs of consecutive accumulator pixels are contiguous,
+//   [img][C/16][up*up sub-pixel][H/up][W/up][16],   up = 2 when a 2x2 max-pool follows the layer.
+// A warp of the backward epilogue (one accumulator pixel per lane, 16 channels per access) then reads 64 B per lane
+// from consecutive addresses instead of one 64 B piece per 4*C-byte pixel row: 4x fewer L1 wavefronts.
+__host__ __device__ __forceinline__ size_t g_offset(int img, int y, int x, int n, int H, int W, int C, int up) {
+  const int Hc = H / up, Wc = W / up;
+  const int sub = (y % up) * up + (x % up);
+  return (((((size_t)img * (C >> 4) + (n >> 4)) * (up * up) + sub) * Hc + y / up) * Wc + x / up) * 16 + (n & 15);
+}
+
+// ---- 256-bit global accesses (sm_100: LDG.256 / STG.256). The epilogue's accesses are one pixel per lane, i.e. one
+// L1 wavefront per lane whatever the width, so doubling the width halves the LSU wavefronts per tile.
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&u)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(const void* p, uint32_t (&u)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "l"(p));
+}
 
 // ---- storage policies ----
 struct StoreSplit {
@@ -37,7 +63,16 @@ struct StoreSplit {
     static_assert(NV % 4 == 0, "split storage moves 4 or 8 elements per vector");
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(base);
     __nv_bfloat16* lo = hi + elems;
-    if constexpr (NV % 8 == 0) {
+    if constexpr (NV % 16 == 0) {
+#pragma unroll
+      for (int j = 0; j < NV / 16; ++j) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1], h[i], l[i]);
+        stg256(hi + off + 16 * j, h);
+        stg256(lo + off + 16 * j, l);
+      }
+    } else if constexpr (NV % 8 == 0) {
 #pragma unroll
       for (int j = 0; j < NV / 8; ++j) {
         uint32_t h[4], l[4];
@@ -132,17 +167,37 @@ struct StoreF32 {
   template <int NV>
   static __device__ __forceinline__ void store(void* base, size_t, size_t off, const float (&v)[NV]) {
     static_assert(NV % 4 == 0, "fp32 storage moves 4 elements per 16 B");
-    float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+    if constexpr (NV % 8 == 0) {
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      for (int j = 0; j < NV / 8; ++j) {
+        uint32_t u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(v[8 * j + i]);
+        stg256(reinterpret_cast<float*>(base) + off + 8 * j, u);
+      }
+    } else {
+      float4* q = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
   template <int NV>
   static __device__ __forceinline__ void load(const void* base, size_t, size_t off, float (&v)[NV]) {
-    const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    if constexpr (NV % 8 == 0) {
 #pragma unroll
-    for (int i = 0; i < NV / 4; ++i) {
-      const float4 t = __ldg(q + i);
-      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      for (int j = 0; j < NV / 8; ++j) {
+        uint32_t u[8];
+        ldg256_nc(reinterpret_cast<const float*>(base) + off + 8 * j, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * j + i] = __uint_as_float(u[i]);
+      }
+    } else {
+      const float4* q = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        const float4 t = __ldg(q + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
     }
   }
 };
@@ -151,6 +206,130 @@ template <int NV>
 __device__ __forceinline__ void load_f32(const float* p, float (&v)[NV]) { StoreF32::load<NV>(p, 0, 0, v); }
 template <int NV>
 __device__ __forceinline__ void store_f32(float* p, const float (&v)[NV]) { StoreF32::store<NV>(p, 0, 0, v); }
+
+// Backward epilogue for one run of NV channels: s_prev = acc * G'[img] at the UP x UP pixels the (pooled) pixel routes to.
+// All multiplier loads are issued before the first use so their latencies overlap (8 epilogue warps give little
+// thread-level parallelism to hide them otherwise).
+template <int NV, class ST>
+__device__ __forceinline__ void epi_store_msg(const EpiDev& e, size_t item_pixels, int item, size_t pix, int NO, int n,
+                                              const float (&o)[NV]) {
+  if (!e.out_planar8) {
+    ST::template store<NV>(e.out, e.out_elems, ((size_t)item * item_pixels + pix) * NO + n, o);
+  } else {
+    constexpr int R = NV < 8 ? NV : 8;
+#pragma unroll
+    for (int h = 0; h < NV; h += R) {
+      float t[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) t[i] = o[h + i];
+      const size_t off = (((size_t)item * (NO >> 3) + ((n + h) >> 3)) * item_pixels + pix) * 8 + ((n + h) & 7);
+      ST::template store<R>(e.out, e.out_elems, off, t);
+    }
+  }
+}
+
+template <int UP, int NV, class ST>
+__device__ __forceinline__ void epi_bwd(const EpiDev& e, int H, int W, int Nout, int item, int y, int x, int n,
+                                        const float (&v)[NV]) {
+  const int img = __ldg(e.img_index + item);
+  const int WW = W * UP;
+  const size_t item_pixels = (size_t)H * UP * WW;
+  const int NO = e.Gin2 ? 2 * Nout : Nout;
+  // multiplier run of sub-pixel (sy, sx): see g_offset (H, W here are the accumulator grid = the pooled grid)
+  const size_t gsub = (size_t)H * W * 16;
+  const size_t g0 = ((((size_t)img * (Nout >> 4) + (n >> 4)) * (UP * UP)) * H + y) * W * 16 + (size_t)x * 16 + (n & 15);
+  float gg[UP * UP][NV];
+#pragma unroll
+  for (int sub = 0; sub < UP * UP; ++sub) load_f32<NV>(e.Gin + g0 + sub * gsub, gg[sub]);
+#pragma unroll
+  for (int sy = 0; sy < UP; ++sy)
+#pragma unroll
+    for (int sx = 0; sx < UP; ++sx) {
+      const size_t pix = (size_t)(y * UP + sy) * WW + (x * UP + sx);
+      float o[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[sy * UP + sx][i];
+      epi_store_msg<NV, ST>(e, item_pixels, item, pix, NO, n, o);
+    }
+  if (e.Gin2) {   // alpha-beta with beta != 0: inhibitor branch -> channels [Nout, 2 Nout)
+#pragma unroll
+    for (int sub = 0; sub < UP * UP; ++sub) load_f32<NV>(e.Gin2 + g0 + sub * gsub, gg[sub]);
+#pragma unroll
+    for (int sy = 0; sy < UP; ++sy)
+#pragma unroll
+      for (int sx = 0; sx < UP; ++sx) {
+        const size_t pix = (size_t)(y * UP + sy) * WW + (x * UP + sx);
+        float o[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[sy * UP + sx][i];
+        epi_store_msg<NV, ST>(e, item_pixels, item, pix, NO, Nout + n, o);
+      }
+  }
+}
+
+// Backward epilogue of one accumulator row (pixel) over NCH 16-channel chunks, software-pipelined: the multiplier run of
+// unit u+1 (unit = chunk x sub-pixel) is loaded while unit u is multiplied and stored, and the image index is read once.
+// Written for the tcgen05 kernels, whose 8 epilogue warps have too little thread-level parallelism to hide a
+// load -> use latency per chunk (ncu: the epilogue, not the tensor pipe, paced the 64-channel layers).
+// load_acc(c, v) must fetch chunk c of the accumulator and is called by every lane (tcgen05.ld is warp-collective);
+// `valid` only guards global-memory traffic. Chunk c covers channels [n_first + c * n_step, +16).
+template <int UP, int NCH, class ST, class AccLoader>
+__device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, int Nout, int item, int y, int x,
+                                               int n_first, int n_step, bool valid, AccLoader&& load_acc) {
+  constexpr int SUBS = UP * UP;
+  constexpr int UNITS = NCH * SUBS;
+  const int img = valid ? __ldg(e.img_index + item) : 0;
+  const int WW = W * UP;
+  const size_t item_pixels = (size_t)H * UP * WW;
+  const int NO = e.Gin2 ? 2 * Nout : Nout;
+  const size_t gsub = (size_t)H * W * 16;
+  const size_t gpix = ((size_t)y * W + x) * 16;
+  const size_t gimg = (size_t)img * (Nout >> 4);
+  for (int pass = 0; pass < (e.Gin2 ? 2 : 1); ++pass) {
+    const float* G = pass ? e.Gin2 : e.Gin;
+    float gg[2][16];
+    if (valid) load_f32<16>(G + ((gimg + (n_first >> 4)) * SUBS) * gsub + gpix, gg[0]);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      float v[16];
+      __syncwarp();   // reconverge after the predicated global accesses: the accumulator load is .sync.aligned
+      load_acc(c, v);
+      if (e.relu_acc) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      const int n = n_first + c * n_step;
+#pragma unroll
+      for (int sub = 0; sub < SUBS; ++sub) {
+        const int u = c * SUBS + sub;
+        if (u + 1 < UNITS && valid) {
+          const int cn = (u + 1) / SUBS, sn = (u + 1) % SUBS;
+          load_f32<16>(G + ((gimg + ((n_first + cn * n_step) >> 4)) * SUBS + sn) * gsub + gpix, gg[(u + 1) & 1]);
+        }
+        if (valid) {
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = v[i] * gg[u & 1][i];
+          const size_t pix = (size_t)(y * UP + sub / UP) * WW + (x * UP + sub % UP);
+          epi_store_msg<16, ST>(e, item_pixels, item, pix, NO, pass * Nout + n, o);
+        }
+      }
+    }
+  }
+}
+
+// Pulls the multiplier runs a backward epilogue thread is about to read into L2. Issued before the thread waits for its
+// accumulator, so the DRAM latency of G overlaps the MMAs instead of serialising with every 16-column chunk.
+__device__ __forceinline__ void epi_prefetch_bwd(const EpiDev& e, int H, int W, int Nout, int item, int y, int x, int n) {
+  const int img = __ldg(e.img_index + item);
+  const int subs = e.up * e.up;
+  const size_t gsub = (size_t)H * W * 16;
+  const size_t g0 = ((((size_t)img * (Nout >> 4) + (n >> 4)) * subs) * H + y) * W * 16 + (size_t)x * 16;
+  for (int sub = 0; sub < subs; ++sub) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gin + g0 + sub * gsub));
+    if (e.Gin2) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gin2 + g0 + sub * gsub));
+  }
+}
 
 // v: accumulator values for channels [n, n+NV) of output pixel (item, y, x) of an H x W x Nout map.
 template <int MODE, int NV, class ST>
@@ -186,7 +365,7 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
           gg[i] = mm[i];
         }
       }
-      if (e.G) store_f32<NV>(e.G + off, gg);
+      if (e.G) store_f32<NV>(e.G + g_offset(item, y, x, n, H, W, Nout, e.g_up), gg);
       if (e.Mseed) store_f32<NV>(e.Mseed + off, mm);
     }
   } else if (MODE == EPI_FWD_ZACT) {
@@ -199,32 +378,17 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
       mm[i] = 1.f / d;
       gg[i] = xa[i] / d;
     }
-    if (e.G) store_f32<NV>(e.G + off, gg);
+    if (e.G) store_f32<NV>(e.G + g_offset(item, y, x, n, H, W, Nout, e.g_up), gg);
     if (e.Mseed) store_f32<NV>(e.Mseed + off, mm);
   } else {  // EPI_BWD
-    const int img = __ldg(e.img_index + item);
-    const int HH = H * e.up, WW = W * e.up;
     if (e.relu_acc) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
     }
-    for (int sy = 0; sy < e.up; ++sy) {
-      for (int sx = 0; sx < e.up; ++sx) {
-        const size_t pix = (size_t)(y * e.up + sy) * WW + (x * e.up + sx);
-        float gg[NV], o[NV];
-        const int NO = e.Gin2 ? 2 * Nout : Nout;
-        load_f32<NV>(e.Gin + ((size_t)img * HH * WW + pix) * Nout + n, gg);
-#pragma unroll
-        for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[i];
-        ST::template store<NV>(e.out, e.out_elems, ((size_t)item * HH * WW + pix) * NO + n, o);
-        if (e.Gin2) {
-          load_f32<NV>(e.Gin2 + ((size_t)img * HH * WW + pix) * Nout + n, gg);
-#pragma unroll
-          for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[i];
-          ST::template store<NV>(e.out, e.out_elems, ((size_t)item * HH * WW + pix) * NO + Nout + n, o);
-        }
-      }
-    }
+    if (e.up == 2)
+      epi_bwd<2, NV, ST>(e, H, W, Nout, item, y, x, n, v);
+    else
+      epi_bwd<1, NV, ST>(e, H, W, Nout, item, y, x, n, v);
   }
 }
 
@@ -244,6 +408,8 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->Gin2 = p.Gin2;
   e->up = p.up;
   e->relu_acc = p.relu_acc;
+  e->g_up = p.g_up;
+  e->out_planar8 = p.out_planar8;
   e->out = nullptr;
   e->out_elems = 0;
   switch (p.mode) {

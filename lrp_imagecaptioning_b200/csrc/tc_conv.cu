@@ -13,123 +13,19 @@
 //                   of two TMEM accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem stage.
 //   warps 2..9    : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic -> global.
 #include "epilogue.cuh"
-#include <cuda.h>
+#include "tc_ptx.cuh"
 #include <type_traits>
 
 namespace lrpcap {
 
 namespace {
 
-constexpr int kBlockK = 64;                       // channels per k-step: 64 bf16 = 128 B = one swizzle row
+using namespace tcptx;
 constexpr int kATileBytes = 128 * 128;            // 128 rows x 128 B
-constexpr uint64_t kWaitLimitNs = 4000000000ull;   // 4 s of wall clock on one barrier = protocol bug -> trap
 
 struct Geom {
   int H, W, TW, TH, tiles_x, tiles_y, cblocks, taps, Nout, n_items, n_tiles_n, group;   // group: k-steps per accumulator hand-over
 };
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ uint64_t global_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_ns();
-  while (!mbar_try_wait(bar, parity)) {
-    if (global_ns() - t0 > kWaitLimitNs) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024)
-//   [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
-}
 
 // NS = number of bf16 planes per operand: 2 -> products (0,0)(0,1)(1,0); 3 -> additionally (0,2)(2,0)(1,1).
 template <int BN, int NS>
@@ -153,9 +49,6 @@ struct Maps {
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 struct TileCoord {
   int item, x0, y0, n0;
@@ -335,15 +228,33 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         __syncwarp();
       } else {
         const uint32_t buf = tl & 1u;
+        if (MODE == EPI_BWD && row_ok) {   // multipliers of the NEXT tile (and of the first one) -> L2, a tile period ahead
+          for (int pt = (tl == 0 ? tile : tile + (int)gridDim.x); pt <= tile + (int)gridDim.x && pt < total_tiles;
+               pt += gridDim.x) {
+            const TileCoord nt = tile_coord(g, pt, BN);
+            if (nt.y0 + ty < g.H && nt.x0 + tx < g.W)
+              for (int c = half; c < BN / 16; c += kEpiWarps / 4)
+                epi_prefetch_bwd(e, g.H, g.W, g.Nout, nt.item, nt.y0 + ty, nt.x0 + tx, nt.n0 + c * 16);
+          }
+        }
         mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
         tc_fence_after();
         const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+        if constexpr (MODE == EPI_BWD) {
+          constexpr int kStep = kEpiWarps / 4;
+          auto load_acc = [&](int c, float (&v)[16]) { tmem_ld16(lane_base + (uint32_t)((half + c * kStep) * 16), v); };
+          if (e.up == 2)
+            epi_bwd_chunks<2, kChunks, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+          else
+            epi_bwd_chunks<1, kChunks, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+        } else {
 #pragma unroll 1
-        for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
-          float v[16];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-          tmem_ld16(lane_base + (uint32_t)(c * 16), v);
-          if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+          for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
+            float v[16];
+            __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+            tmem_ld16(lane_base + (uint32_t)(c * 16), v);
+            if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -358,12 +269,14 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
   if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-// ------------------------------------------------------------------ host side
+}  // namespace
+
+// ------------------------------------------------------------------ host side (shared with tc_conv_vh.cu)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn get_encode_fn() {
+static EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -402,6 +315,8 @@ int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
   LRPCAP_REQUIRE(r == CUDA_SUCCESS, kErrCuda, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
   return kOk;
 }
+
+namespace {
 
 template <int BN, int MODE, int NS, bool PROMO>
 int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
@@ -485,6 +400,7 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   LRPCAP_REQUIRE(a.n_items > 0 && a.H > 0 && a.W > 0, kErrShape, "tc_conv: empty problem");
   LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3, kErrInvalidArg, "tc_conv: planes must be 2 or 3");
   const int BN = (a.planes == 2 && a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
+  if (tc_conv_vh_eligible(a, BN)) return tc_conv_vh_launch(a, BN, stream);   // wide shallow layers: tc_conv_vh.cu
   Geom g;
   g.H = a.H;
   g.W = a.W;

@@ -30,7 +30,8 @@ struct EpiParams {
   void* out_act = nullptr;          // split storage [items, H, W, Nout]
   size_t out_act_elems = 0;
   float* out_f32 = nullptr;         // optional fp32 copy [items, H, W, Nout]
-  float* G = nullptr;               // fp32 [items, H, W, Nout]
+  float* G = nullptr;               // fp32 per-image multiplier, channel-tiled layout (epilogue.cuh: g_offset)
+  int g_up = 1;                     // 2 when a 2x2 max-pool follows this layer (its G is read by an up-sampling epilogue)
   float* Mseed = nullptr;           // fp32 [items, H, W, Nout] seed multiplier (last layer only)
   int gmode = G_NONE;
   float eps = 0.f;
@@ -39,12 +40,13 @@ struct EpiParams {
   size_t x_act_elems = 0;
   // backward
   const int* img_index = nullptr;   // [items] -> image
-  const float* Gin = nullptr;       // fp32 [images, H*up, W*up, Nout]
+  const float* Gin = nullptr;       // fp32 multiplier of the layer below, [images][Nout/16][up*up][H][W][16] (g_offset)
   const float* Gin2 = nullptr;      // alpha-beta with beta != 0: second multiplier (inhibitor branch); the output then has
                                     // 2*Nout channels: [acc*Gin | acc*Gin2]
   int up = 1;
   int relu_acc = 0;
   void* out_msg = nullptr;          // split storage [items, H*up, W*up, Nout]
+  int out_planar8 = 0;              // 1: write the message as [items][Nout/8][H*up][W*up][8] (read by last_dgrad only)
   size_t out_msg_elems = 0;
 };
 

@@ -1,0 +1,361 @@
+// tcgen05 implicit-GEMM 3x3 (transposed) convolution, "vertical halo" variant for the wide, shallow layers
+// (224x224 and 112x112 maps, 64 / 128 output channels) where the generic kernel (tc_conv.cu) is bound by
+// L2 -> shared-memory operand traffic: it re-fetches the activation tile for each of the 9 taps and the weight tile
+// for every 128-pixel tile.
+//
+// Same contraction and the same fused epilogues as tc_conv.cu (reference: iNNvestigate GradientWRT on a conv layer,
+// innvestigate/layers.py:138-157 -> utils/keras/backend.py:58-60), different operand staging:
+//   * a CTA tile is 16 x 16 pixels = two 128-row MMA tiles side by side; both use every weight tile once
+//     it is in shared memory (weight traffic per pixel halves);
+//   * an MMA tile is 8 x 16 pixels (8 wide, 16 tall); per (64-channel block, dx, MMA tile) ONE activation patch of
+//     8 x 18 pixels is loaded (TMA box shifted by dx, rows y0-1 .. y0+16, OOB zero-fill = 'same' padding). A patch row
+//     is 8 pixels = one swizzle group of 8 x 128 B, so the operand for tap (dy, dx) is the same patch at byte offset
+//     dy * 1024 -- a plain SWIZZLE_128B K-major descriptor. 3 patches of 18 rows replace 9 tiles of 16 rows: 2.7x less
+//     activation traffic. Patches are 36 KB ring slots (4 of them): with one 72 KB patch per dx and 2 slots the ring
+//     was shallower than the TMA latency and the tensor pipe idled 45 % of the time;
+//   * NCAT (64 output channels): the weight planes [hi ; lo] sit back to back in shared memory and are issued as ONE
+//     N = 128 operand against A_hi (accumulator columns [0,64) = hi*hi, [64,128) = hi*lo) plus one N = 64 MMA
+//     A_lo * B_hi; the epilogue adds the two column blocks. Two MMAs instead of three, and a third less
+//     shared-memory operand bandwidth, which is what bounds N = 64 MMAs.
+// Rings: activation patches (kNA slots) and weight taps (NB slots) are separate mbarrier rings fed by one TMA thread.
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+#include <cstdlib>
+
+namespace lrpcap {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kTW = 16, kTH = 16, kTM = 2;              // CTA tile: 16 x 16 pixels = kTM MMA tiles of 8 (wide) x 16
+constexpr int kMW = kTW / kTM;                          // MMA tile width: 8 pixels = one 1024 B swizzle group per row
+constexpr int kPatchRows = kTH + 2;                     // 18 pixel rows of 8 pixels
+constexpr int kAPlane = kPatchRows * kMW * 128;         // 18,432 B per bf16 plane (multiple of 1024)
+constexpr int kASlot = 2 * kAPlane;
+constexpr int kNA = 4;
+constexpr int kMaxNB = 8;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct VhGeom {
+  int H, W, tiles_x, tiles_y, cblocks, Nout, n_items, n_tiles_n, NB;
+};
+struct VhMaps {
+  CUtensorMap a[2];
+  CUtensorMap b[2];
+};
+
+struct VhTile {
+  int item, x0, y0, n0;
+};
+__device__ __forceinline__ VhTile vh_tile(const VhGeom& g, int tile, int BN) {
+  VhTile t;
+  const int n_tile = tile % g.n_tiles_n;
+  int m = tile / g.n_tiles_n;
+  const int per_item = g.tiles_x * g.tiles_y;
+  t.item = m / per_item;
+  m -= t.item * per_item;
+  t.x0 = (m % g.tiles_x) * kTW;
+  t.y0 = (m / g.tiles_x) * kTH;
+  t.n0 = n_tile * BN;
+  return t;
+}
+
+template <int BN, int MODE, bool NCAT>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDev e, const int total_tiles) {
+  constexpr int kBPlane = BN * 128;
+  constexpr int kBSlot = 2 * kBPlane;
+  constexpr int ACC = NCAT ? 2 * BN : BN;               // accumulator columns per MMA tile
+  constexpr int kTmemCols = 2 * kTM * ACC;              // double-buffered
+  // K-loop order per (channel block, dx): both patches of the dx are held while the three weight taps stream through.
+  constexpr bool JINNER = true;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + kNA * kASlot;
+  uint64_t* afull = reinterpret_cast<uint64_t*>(b_ring + g.NB * kBSlot);
+  uint64_t* aempty = afull + kNA;
+  uint64_t* bfull = aempty + kNA;
+  uint64_t* bempty = bfull + kMaxNB;
+  uint64_t* tfull = bempty + kMaxNB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NB = g.NB;
+
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < 2; ++p) {
+      prefetch_tmap(&tm.a[p]);
+      prefetch_tmap(&tm.b[p]);
+    }
+    for (int s = 0; s < kNA; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull[b], 1);
+      mbar_init(&tempty[b], kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: patches and weight taps in the order the MMA thread consumes them ----------------
+      uint32_t ia = 0, ib = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const VhTile tc = vh_tile(g, tile, BN);
+        for (int cb = 0; cb < g.cblocks; ++cb) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
+            for (int j = 0; j < kTM; ++j, ++ia) {
+              const uint32_t sa = ia % kNA;
+              mbar_wait(&aempty[sa], ((ia / kNA) & 1u) ^ 1u);
+              mbar_expect_tx(&afull[sa], (uint32_t)kASlot);
+              uint8_t* ap = a_ring + sa * kASlot;
+#pragma unroll
+              for (int p = 0; p < 2; ++p)
+                tma_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], cb * kBlockK, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1,
+                            tc.item);
+              if (j == (JINNER ? kTM - 1 : 0)) {   // the three weight taps of this dx, used by both MMA tiles
+                for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
+                  const uint32_t sb = ib % NB;
+                  mbar_wait(&bempty[sb], ((ib / NB) & 1u) ^ 1u);
+                  mbar_expect_tx(&bfull[sb], (uint32_t)kBSlot);
+                  uint8_t* bp = b_ring + sb * kBSlot;
+                  const int tap = dyi * 3 + dxi;
+#pragma unroll
+                  for (int p = 0; p < 2; ++p)
+                    tma_load_2d(&tm.b[p], bp + p * kBPlane, &bfull[sb], cb * kBlockK, tap * g.Nout + tc.n0);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc_n = make_idesc(128, BN);
+      constexpr uint32_t idesc_cat = make_idesc(128, NCAT ? 2 * BN : BN);
+      uint32_t ia = 0, ib = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t buf = tl & 1u;
+        mbar_wait(&tempty[buf], ((tl >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * (kTM * ACC);
+        for (int cb = 0; cb < g.cblocks; ++cb) {
+          for (int dxi = 0; dxi < 3; ++dxi, ib += 3, ia += kTM) {
+            const uint32_t accum = (cb != 0 || dxi != 0) ? 1u : 0u;
+            // All MMAs of one weight tap for both MMA tiles.
+            auto issue_tap = [&](int dyi) {
+              const uint32_t sb = (ib + dyi) % NB;
+              const uint32_t bbase = smem_u32(b_ring + sb * kBSlot);
+              const uint64_t db_hi = make_desc_sw128(bbase);                 // NCAT: the same start, N = 2 BN rows
+              const uint64_t db_lo = make_desc_sw128(bbase + kBPlane);
+              uint64_t da_hi[kTM], da_lo[kTM];
+#pragma unroll
+              for (int j = 0; j < kTM; ++j) {
+                const uint32_t abase = smem_u32(a_ring + ((ia + j) % kNA) * kASlot);
+                da_hi[j] = make_desc_sw128(abase + (uint32_t)dyi * 1024u);
+                da_lo[j] = make_desc_sw128(abase + kAPlane + (uint32_t)dyi * 1024u);
+              }
+              auto mma_slice = [&](int j, int k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                const uint32_t acc_k = (accum != 0u || dyi != 0 || k != 0) ? 1u : 0u;   // the tile's first MMA overwrites
+                const uint32_t d = tmem_d + j * ACC;
+                if (NCAT) {
+                  umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_cat, acc_k);   // [hi*hi | hi*lo]
+                  umma_bf16(d, da_lo[j] + adv, db_hi + adv, idesc_n, 1u);        // += lo*hi into the first block
+                } else {
+                  umma_bf16(d, da_hi[j] + adv, db_lo + adv, idesc_n, acc_k);
+                  umma_bf16(d, da_lo[j] + adv, db_hi + adv, idesc_n, 1u);
+                  umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_n, 1u);
+                }
+              };
+              if (g.cblocks == 1) {   // measured: alternating the two accumulators per K slice helps the K = 576 layer only
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+#pragma unroll
+                  for (int j = 0; j < kTM; ++j) mma_slice(j, k);
+              } else {
+#pragma unroll
+                for (int j = 0; j < kTM; ++j)
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) mma_slice(j, k);
+              }
+            };
+            auto wait_a = [&](int j) {
+              mbar_wait(&afull[(ia + j) % kNA], ((ia + j) / kNA) & 1u);
+              tc_fence_after();
+            };
+            auto wait_b = [&](int dyi) {
+              mbar_wait(&bfull[(ib + dyi) % NB], ((ib + dyi) / NB) & 1u);
+              tc_fence_after();
+            };
+            for (int j = 0; j < kTM; ++j) wait_a(j);
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              wait_b(dyi);
+              issue_tap(dyi);
+              umma_commit(&bempty[(ib + dyi) % NB]);
+            }
+            for (int j = 0; j < kTM; ++j) umma_commit(&aempty[(ia + j) % kNA]);
+          }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ---------------- epilogue: warp w owns TMEM lanes [32 (w % 4), +32) of MMA tile (w - 2) / 4 ----------------
+    const int q = warp & 3;
+    const int j = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int ty = r >> 3, tx = kMW * j + (r & 7);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+      const VhTile tc = vh_tile(g, tile, BN);
+      const int y = tc.y0 + ty, x = tc.x0 + tx;
+      const bool valid = (y < g.H) && (x < g.W);
+      const uint32_t buf = tl & 1u;
+      if (MODE == EPI_BWD) {   // multipliers of the NEXT tile (and of the first one) -> L2, one tile period ahead of use
+        for (int pt = (tl == 0 ? tile : tile + (int)gridDim.x); pt <= tile + (int)gridDim.x && pt < total_tiles;
+             pt += gridDim.x) {
+          const VhTile nt = vh_tile(g, pt, BN);
+          if (nt.y0 + ty < g.H && nt.x0 + tx < g.W)
+            for (int c = 0; c < BN / 16; ++c)
+              epi_prefetch_bwd(e, g.H, g.W, g.Nout, nt.item, nt.y0 + ty, nt.x0 + tx, nt.n0 + c * 16);
+        }
+      }
+      mbar_wait(&tfull[buf], (tl >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t lane_base = tmem_base + buf * (kTM * ACC) + j * ACC + ((uint32_t)(q * 32) << 16);
+      auto load_acc = [&](int c, float (&v)[16]) {
+        if (NCAT) {
+          float w[16];
+          tmem_ld16x2(lane_base + (uint32_t)(c * 16), lane_base + (uint32_t)(BN + c * 16), v, w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += w[i];
+        } else {
+          tmem_ld16(lane_base + (uint32_t)(c * 16), v);
+        }
+      };
+      if constexpr (MODE == EPI_BWD) {
+        if (e.up == 2)
+          epi_bwd_chunks<2, BN / 16, StoreSplit>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0, 16, valid, load_acc);
+        else
+          epi_bwd_chunks<1, BN / 16, StoreSplit>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0, 16, valid, load_acc);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 16; ++c) {
+          float v[16];
+          __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+          load_acc(c, v);
+          if (valid) epi_apply<MODE, 16, StoreSplit>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int BN, int MODE, bool NCAT>
+int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) {
+  constexpr int kBSlot = 2 * BN * 128;
+  int nb = (kSmemLimit - 1024 - 512 - kNA * kASlot) / kBSlot;
+  if (nb > kMaxNB) nb = kMaxNB;
+  LRPCAP_REQUIRE(nb >= 2, kErrUnsupported, "tc_conv_vh: no room for a weight ring (BN=%d)", BN);
+  g.NB = nb;
+  const int smem = kNA * kASlot + nb * kBSlot + 1024 + 512;
+  static int configured = 0;
+  if (configured < smem) {
+    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_vh_kernel<BN, MODE, NCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
+  LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv_vh: %lld tiles out of range", tiles);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LRPCAP_CUDA(cudaGetDevice(&dev));
+    LRPCAP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+  tc_conv_vh_kernel<BN, MODE, NCAT><<<grid, kThreads, smem, stream>>>(tm, g, e, (int)tiles);
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+template <int BN, bool NCAT>
+int launch_vh_mode(int mode, const VhMaps& tm, const VhGeom& g, const EpiDev& e, cudaStream_t stream) {
+  switch (mode) {
+    case EPI_BWD: return launch_vh<BN, EPI_BWD, NCAT>(tm, g, e, stream);
+    case EPI_RAW: return launch_vh<BN, EPI_RAW, NCAT>(tm, g, e, stream);
+  }
+  set_last_error("tc_conv_vh: epilogue mode %d not instantiated", mode);
+  return kErrUnsupported;
+}
+
+bool vh_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = std::getenv("LRPCAP_TC_VH");
+    on = (v && v[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+}  // namespace
+
+bool tc_conv_vh_eligible(const TcConvArgs& a, int BN) {
+  return vh_enabled() && a.taps == 9 && a.planes == 2 && a.promote_every <= 0 && (BN == 64 || BN == 128) &&
+         a.W % kTW == 0 && a.H % kTH == 0 && (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW);
+}
+
+int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream) {
+  LRPCAP_REQUIRE(tc_conv_vh_eligible(a, BN), kErrUnsupported, "tc_conv_vh: shape not eligible");
+  VhGeom g;
+  g.H = a.H;
+  g.W = a.W;
+  g.tiles_x = a.W / kTW;
+  g.tiles_y = a.H / kTH;
+  g.cblocks = a.C / kBlockK;
+  g.Nout = a.Nout;
+  g.n_items = a.n_items;
+  g.n_tiles_n = a.Nout / BN;
+  g.NB = 0;
+  const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
+  const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
+  VhMaps tm;
+  for (int pl = 0; pl < 2; ++pl) {
+    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)pl * a.A_elems, a.n_items, a.H, a.W, a.C, kMW, kPatchRows));
+    LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)pl * a.B_elems, a.taps * a.Nout, a.C, BN));
+  }
+  EpiDev e;
+  LRPCAP_TRY(make_epi_dev(a.epi, &e));
+  if (BN == 64) return launch_vh_mode<64, true>(a.epi.mode, tm, g, e, stream);
+  return launch_vh_mode<128, false>(a.epi.mode, tm, g, e, stream);
+}
+
+}  // namespace lrpcap

@@ -123,10 +123,10 @@ class ImageModel(object):
         _lib.check(_lib.load().lrpcap_encoder_profile(self.handle(), int(bool(enable))))
 
     def profile_read(self):
-        """{class: (ms, algorithmic FLOPs, launches)} for classes tc_bwd / tc_fwd / simt; resets the counters."""
-        out = np.zeros(9, dtype=np.float64)
+        """{class: (ms, algorithmic FLOPs, launches)} for classes tc_bwd / tc_fwd / simt / last; resets the counters."""
+        out = np.zeros(12, dtype=np.float64)
         _lib.check(_lib.load().lrpcap_encoder_profile_read(self.handle(), _lib.dptr(out)))
-        return {k: tuple(out[3 * i:3 * i + 3]) for i, k in enumerate(("tc_bwd", "tc_fwd", "simt"))}
+        return {k: tuple(out[3 * i:3 * i + 3]) for i, k in enumerate(("tc_bwd", "tc_fwd", "simt", "last"))}
 
     def launches(self):
         return int(_lib.load().lrpcap_encoder_launches(self.handle()))

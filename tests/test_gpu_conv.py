@@ -1,0 +1,59 @@
+"""Unit parity of the convolution kernels through the C ABI (lrpcap_debug_conv) against a float64 numpy contraction.
+
+Covers both tcgen05 kernels -- the generic one (csrc/tc_conv.cu) and the vertical-halo variant for wide shallow
+layers (csrc/tc_conv_vh.cu: W % 16 == 0, H % 16 == 0, 64 / 128 output channels) -- plus the fp32 SIMT kernel.
+The contraction is the one iNNvestigate emits for a conv layer and its GradientWRT (innvestigate/layers.py:138-157)."""
+import numpy as np
+import pytest
+
+from lrp_imagecaptioning_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(A, B, taps):
+    A = A.astype(np.float64)
+    B = B.astype(np.float64)
+    items, H, W, C = A.shape
+    if taps == 1:
+        return A @ B[0]
+    out = np.zeros((items, H, W, B.shape[-1]))
+    Ap = np.pad(A, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    for t in range(9):
+        dy, dx = t // 3, t % 3
+        out += Ap[:, dy:dy + H, dx:dx + W, :] @ B[t]
+    return out
+
+
+# (items, H, W, C, Nout, taps)
+GENERIC = [(1, 8, 16, 64, 64, 1), (1, 14, 14, 128, 256, 9), (3, 28, 28, 256, 256, 9), (1, 56, 56, 128, 64, 9),
+           (1, 4, 4, 64, 128, 9), (1, 2, 2, 512, 512, 9), (5, 7, 7, 64, 64, 1), (1, 8, 16, 64, 64, 9)]
+VERTICAL_HALO = [(2, 16, 16, 64, 64, 9), (1, 16, 32, 128, 128, 9), (2, 32, 32, 64, 64, 9), (1, 32, 48, 128, 64, 9),
+                 (3, 48, 32, 256, 128, 9), (150, 16, 16, 64, 64, 9), (1, 112, 112, 128, 64, 9)]
+TOL = {_lib.PREC_FP32_SIMT: 2e-6, _lib.PREC_BF16X3_TC: 3e-5, 2: 2e-6}
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP32_SIMT, _lib.PREC_BF16X3_TC, 2], ids=["simt", "tc", "tc3"])
+@pytest.mark.parametrize("shape", GENERIC + VERTICAL_HALO, ids=lambda s: "x".join(map(str, s)))
+def test_conv_matches_float64(prec, shape):
+    items, H, W, C, Nout, taps = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 31))
+    A = rng.standard_normal((items, H, W, C)).astype(np.float32)
+    B = (rng.standard_normal((taps, C, Nout)) / np.sqrt(taps * C)).astype(np.float32)
+    got = _lib.debug_conv(prec, A, B, taps)
+    ref = ref_conv(A, B, taps)
+    assert np.isfinite(got).all()
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < TOL[prec], (shape, err)
+
+
+def test_tap_geometry_vertical_halo():
+    """One-hot taps with identity weights: the output must be the input shifted by the tap (padding = zeros)."""
+    H, W, C = 32, 32, 64
+    A = (np.arange(H * W)[:, None] + np.arange(C)[None, :] / 128.0).reshape(1, H, W, C).astype(np.float32)
+    for t in range(9):
+        B = np.zeros((9, C, C), dtype=np.float32)
+        B[t] = np.eye(C)
+        got = _lib.debug_conv(_lib.PREC_BF16X3_TC, A, B, 9)
+        ref = ref_conv(A, B, 9)
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5, t

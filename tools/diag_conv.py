@@ -36,6 +36,7 @@ cases = [  # (items, H, W, C, Nout, taps)
     (1, 8, 16, 64, 64, 1), (1, 8, 16, 64, 64, 9), (2, 16, 16, 64, 64, 9), (1, 16, 32, 128, 128, 9),
     (1, 14, 14, 128, 256, 9), (1, 14, 14, 512, 512, 9), (3, 28, 28, 256, 256, 9), (1, 56, 56, 128, 64, 9),
     (1, 4, 4, 64, 128, 9), (1, 2, 2, 512, 512, 9), (2, 32, 32, 64, 64, 9), (5, 7, 7, 64, 64, 1), (1, 224, 224, 64, 64, 9),
+    (1, 32, 48, 128, 64, 9), (3, 48, 32, 256, 128, 9), (150, 16, 16, 64, 64, 9),
 ]
 for prec, pname in ((_lib.PREC_FP32_SIMT, "simt"), (_lib.PREC_BF16X3_TC, "tc"), (2, "tc3")):
     for (items, H, W, C, Nout, taps) in cases:

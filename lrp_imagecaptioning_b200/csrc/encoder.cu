@@ -1,5 +1,6 @@
 // Encoder: per-image forward state and batched per-word relevance backward (see encoder.cuh).
 #include "encoder.cuh"
+#include <cstdlib>
 #include "encoder_kernels.cuh"
 #include "tc_conv.cuh"
 
@@ -57,6 +58,10 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
   Encoder* e = new Encoder();
   e->hw_ = image_hw;
   e->precision_ = precision;
+  if (const char* v = std::getenv("LRPCAP_FWD_PROMOTE")) {   // experiment knob: k-steps per accumulator hand-over, forward
+    const int n = std::atoi(v);
+    if (n >= 1 && n <= 64) e->fwd_promote_ = n;
+  }
   for (int l = 0; l < kLayers; ++l) {
     Layer& L = e->L_[l];
     L.cin = kCin[l];
@@ -136,7 +141,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout * (dual ? 2 : 1); a.taps = 9; a.Nout = Nout;
     a.planes = backward ? 2 : 3;
-    a.promote_every = backward ? bwd_promote_ : 0;
+    a.promote_every = backward ? bwd_promote_ : fwd_promote_;
     a.epi = epi;
     st = tc_conv_launch(a, s);
   } else {

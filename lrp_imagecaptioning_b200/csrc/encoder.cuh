@@ -95,7 +95,7 @@ class Encoder {
   int fwd_planes() const { return split() ? 3 : 0; }
   size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
 
-  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0;
+  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0, fwd_promote_ = 1;
   long long launches_ = 0;
   EncoderRule rule_;
   Layer L_[kLayers];

@@ -1,5 +1,7 @@
 // HBM-bound helper kernels of the encoder relevance path: all coalesced, 16-byte vectorised.
 #include "encoder_kernels.cuh"
+#include "tc_ptx.cuh"
+#include <cstdlib>
 #include "epilogue.cuh"
 
 namespace lrpcap {
@@ -282,6 +284,150 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
   }
 }
 
+// Same computation with the staging done by TMA (split-bf16 messages only): one elected thread pulls the 34 x 34 x 8
+// halo box of the NEXT channel chunk (both planes; OOB zero-fill = padding) into a raw buffer while all threads run the
+// FMAs of the current one, so no thread ever waits on a global load and no registers hold staged data. ncu on the
+// register-staged kernel above: 3.8 long-scoreboard stalls per issue, FMA pipe 31 % busy at 12 warps / SM.
+constexpr int kLHalf = 4;   // channels converted to fp32 at a time
+constexpr int kLRawPlane = ((kLPSY * (kLTX + 2) * 8 * 2 + 127) / 128) * 128;   // bytes of one bf16 plane of the halo box
+
+template <bool DUAL, int C>
+__global__ void __launch_bounds__(kLThreads, 3)
+last_dgrad_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                      const float* __restrict__ Wa, const float* __restrict__ Wb, const float* __restrict__ images,
+                      const int* __restrict__ img_index, float* __restrict__ out, int H, int W, int tiles_x, int tiles_y,
+                      int mult) {
+  using namespace tcptx;
+  extern __shared__ __align__(128) uint8_t last_raw_smem[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(last_raw_smem) + 127) & ~uintptr_t(127));
+  const uint4* raw_hi = reinterpret_cast<const uint4*>(sm);
+  const uint4* raw_lo = reinterpret_cast<const uint4*>(sm + kLRawPlane);
+  float (*S)[kLPSY * kLPSX] = reinterpret_cast<float (*)[kLPSY * kLPSX]>(sm + 2 * kLRawPlane);   // [kLHalf][...]
+  float* Wsa = reinterpret_cast<float*>(sm + 2 * kLRawPlane) + kLHalf * kLPSY * kLPSX;
+  float* Wsb = Wsa + C * kLWPitch;
+  uint64_t* full = reinterpret_cast<uint64_t*>(Wsb + (DUAL ? C * kLWPitch : 0));
+
+  int bid = blockIdx.x;
+  const int tiles = tiles_x * tiles_y;
+  const int item = bid / tiles;
+  bid -= item * tiles;
+  const int y0 = (bid / tiles_x) * kLTY, x0 = (bid % tiles_x) * kLTX;
+  const int tid = threadIdx.x;
+  const int ty = (tid >> 3) * 2, tx = (tid & 7) * 4;
+  constexpr int NCH = C / kLC;
+  constexpr uint32_t kBoxBytes = (uint32_t)kLPSY * (kLTX + 2) * 8 * 2;
+
+  if (tid == 0) {
+    prefetch_tmap(&map_hi);
+    prefetch_tmap(&map_lo);
+    mbar_init(full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(full, 2 * kBoxBytes);
+    tma_load_4d(&map_hi, sm, full, 0, x0 - 1, y0 - 1, item * NCH);
+    tma_load_4d(&map_lo, sm + kLRawPlane, full, 0, x0 - 1, y0 - 1, item * NCH);
+  }
+  for (int i = tid; i < 9 * C * 3; i += kLThreads) {   // weights [tap][C][3] -> shared [c][tap * 3 + colour]
+    const int tap = i / (C * 3), rem = i - tap * C * 3, c = rem / 3, ci = rem - c * 3;
+    Wsa[c * kLWPitch + tap * 3 + ci] = __ldg(Wa + i);
+    if (DUAL) Wsb[c * kLWPitch + tap * 3 + ci] = __ldg(Wb + i);
+  }
+
+  float ca[2][4][3], cb[2][4][3];
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 4; ++px)
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) ca[py][px][ci] = cb[py][px][ci] = 0.f;
+  __syncthreads();   // barrier initialised, weights in place
+
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    mbar_wait(full, (uint32_t)(ch & 1));
+#pragma unroll 1
+    for (int half = 0; half < kLC / kLHalf; ++half) {
+      // raw [pixel][8 ch] (hi, lo) -> fp32 S[ch % 4][pixel] (row pitch padded for LDS.128), four channels at a time so
+      // that three CTAs fit an SM
+      for (int pix = tid; pix < kLHalo; pix += kLThreads) {
+        const int py = pix / (kLTX + 2), px = pix - py * (kLTX + 2);
+        const uint2 a = reinterpret_cast<const uint2*>(raw_hi + pix)[half], b = reinterpret_cast<const uint2*>(raw_lo + pix)[half];
+        S[0][py * kLPSX + px] = bf16lo_to_float(a.x) + bf16lo_to_float(b.x);
+        S[1][py * kLPSX + px] = bf16hi_to_float(a.x) + bf16hi_to_float(b.x);
+        S[2][py * kLPSX + px] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y);
+        S[3][py * kLPSX + px] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y);
+      }
+      if (half == kLC / kLHalf - 1) fence_proxy_async();   // raw-buffer reads ordered before the TMA writes issued below
+      __syncthreads();
+      if (half == kLC / kLHalf - 1 && tid == 0 && ch + 1 < NCH) {
+        mbar_expect_tx(full, 2 * kBoxBytes);
+        tma_load_4d(&map_hi, sm, full, 0, x0 - 1, y0 - 1, item * NCH + ch + 1);
+        tma_load_4d(&map_lo, sm + kLRawPlane, full, 0, x0 - 1, y0 - 1, item * NCH + ch + 1);
+      }
+#pragma unroll 2
+      for (int k = 0; k < kLHalf; ++k) {
+        float win[4][6];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float* row = &S[k][(ty + r) * kLPSX + tx];
+          const float4 a = *reinterpret_cast<const float4*>(row);
+          const float2 b = *reinterpret_cast<const float2*>(row + 4);
+          win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w; win[r][4] = b.x; win[r][5] = b.y;
+        }
+        const int cc = ch * kLC + half * kLHalf + k;
+        float wa[kLWPitch], wb[kLWPitch];
+#pragma unroll
+        for (int i = 0; i < kLWPitch / 4; ++i) {
+          const float4 t = *reinterpret_cast<const float4*>(Wsa + cc * kLWPitch + 4 * i);
+          wa[4 * i] = t.x; wa[4 * i + 1] = t.y; wa[4 * i + 2] = t.z; wa[4 * i + 3] = t.w;
+          if (DUAL) {
+            const float4 u = *reinterpret_cast<const float4*>(Wsb + cc * kLWPitch + 4 * i);
+            wb[4 * i] = u.x; wb[4 * i + 1] = u.y; wb[4 * i + 2] = u.z; wb[4 * i + 3] = u.w;
+          }
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+          for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+              const float sv = win[tap / 3 + py][tap % 3 + px];
+#pragma unroll
+              for (int ci = 0; ci < 3; ++ci) {
+                ca[py][px][ci] = fmaf(sv, wa[tap * 3 + ci], ca[py][px][ci]);
+                if (DUAL) cb[py][px][ci] = fmaf(sv, wb[tap * 3 + ci], cb[py][px][ci]);
+              }
+            }
+        }
+      }
+      __syncthreads();   // S is rewritten by the next conversion
+    }
+  }
+  const int img = mult ? __ldg(img_index + item) : 0;
+#pragma unroll
+  for (int py = 0; py < 2; ++py) {
+    const int y = y0 + ty + py;
+    if (y >= H) continue;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const int x = x0 + tx + px;
+      if (x >= W) continue;
+      const size_t pix = (size_t)y * W + x;
+      float* o = out + ((size_t)item * H * W + pix) * 3;
+      if (mult) {
+        const float* xi = images + ((size_t)img * H * W + pix) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float xv = __ldg(xi + ci);
+          o[ci] = DUAL ? (xv >= 0.f ? xv * ca[py][px][ci] : xv * cb[py][px][ci]) : xv * ca[py][px][ci];
+        }
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) o[ci] = ca[py][px][ci];
+      }
+    }
+  }
+}
+
 __global__ void posneg_kernel(const float* __restrict__ x, float* __restrict__ out, size_t pixels) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= pixels) return;
@@ -376,6 +522,22 @@ int launch_last(const void* msg, size_t msg_elems, const float* Wa, const float*
   return kOk;
 }
 
+template <bool DUAL, int C>
+int launch_last_tma(const CUtensorMap& mh, const CUtensorMap& ml, const float* Wa, const float* Wb, const float* images,
+                    const int* img_index, float* out, int H, int W, int tiles_x, int tiles_y, int mult, unsigned grid,
+                    cudaStream_t s) {
+  const int smem = 2 * kLRawPlane + (kLHalf * kLPSY * kLPSX + (DUAL ? 2 : 1) * C * kLWPitch) * (int)sizeof(float) + 16 + 128;
+  static bool configured = false;
+  if (!configured) {
+    LRPCAP_CUDA(cudaFuncSetAttribute(last_dgrad_tma_kernel<DUAL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  last_dgrad_tma_kernel<DUAL, C><<<grid, kLThreads, smem, s>>>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x,
+                                                               tiles_y, mult);
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, const float* Wb, const float* images,
                const int* img_index, float* out, int items, int H, int W, int C, int mult, cudaStream_t s) {
   LRPCAP_REQUIRE(C == 64 || C == 128, kErrShape, "last_dgrad: C must be 64 (or 128 for the dual message), got %d", C);
@@ -383,6 +545,19 @@ int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, c
   const long long blocks = (long long)items * tiles_x * tiles_y;
   LRPCAP_REQUIRE(blocks > 0 && blocks < (1ll << 31), kErrShape, "last_dgrad: grid out of range");
   const unsigned g = (unsigned)blocks;
+  static const bool use_tma = [] { const char* v = std::getenv("LRPCAP_LAST_TMA"); return !(v && v[0] == '0'); }();
+  if (split && use_tma) {   // split-bf16 message: TMA-staged kernel
+    CUtensorMap mh, ml;
+    const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(msg);
+    LRPCAP_TRY(make_map_planar8(&mh, hi, items * (C / 8), H, W, kLTX + 2, kLPSY));
+    LRPCAP_TRY(make_map_planar8(&ml, hi + msg_elems, items * (C / 8), H, W, kLTX + 2, kLPSY));
+    if (Wb) {
+      if (C == 64) return launch_last_tma<true, 64>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+      return launch_last_tma<true, 128>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+    }
+    if (C == 64) return launch_last_tma<false, 64>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+    return launch_last_tma<false, 128>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+  }
 #define LRPCAP_LAUNCH_LAST(ST, DUAL, CC) \
   return launch_last<ST, DUAL, CC>(msg, msg_elems, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s)
 #define LRPCAP_LAUNCH_LAST_C(ST, DUAL) \

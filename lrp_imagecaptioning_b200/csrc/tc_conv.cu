@@ -302,6 +302,20 @@ int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, in
   return kOk;
 }
 
+int make_map_planar8(CUtensorMap* m, const void* base, int n_groups, int H, int W, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_groups};
+  cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  cuuint32_t box[4] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LRPCAP_REQUIRE(r == CUDA_SUCCESS, kErrCuda, "cuTensorMapEncodeTiled(planar message) failed: %d", (int)r);
+  return kOk;
+}
+
 int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
   EncodeTiledFn fn = get_encode_fn();
   LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
@@ -412,7 +426,7 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
-  g.group = a.planes == 3 ? 1 : (a.promote_every > 0 ? a.promote_every : 0);
+  g.group = a.planes == 3 ? (a.promote_every > 0 ? a.promote_every : 1) : (a.promote_every > 0 ? a.promote_every : 0);
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);

@@ -63,6 +63,8 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, 
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// Orders this thread's earlier generic-proxy shared-memory accesses before later async-proxy (TMA) ones.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -150,6 +152,8 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, fl
 // 128B-swizzled, OOB zero-filled.  Weights: bf16 [rows, C] read as boxes {64 ch, box_rows}.
 int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int box_w, int box_h);
 int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int box_rows);
+// Channel-planar message [n_groups][H][W][8] bf16 (EpiParams::out_planar8) read as boxes {8 ch, box_w, box_h, 1}, unswizzled.
+int make_map_planar8(CUtensorMap* m, const void* base, int n_groups, int H, int W, int box_w, int box_h);
 
 // Vertical-halo variant of the transposed-conv kernel (tc_conv_vh.cu); returns kErrUnsupported when the shape does
 // not qualify so that the caller can fall back to the generic kernel.

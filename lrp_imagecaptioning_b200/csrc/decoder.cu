@@ -290,7 +290,7 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
     LRPCAP_TRY(gemm(s_new, (T + 1) * H, Wss_, H, sp_.as<double>(), H, N, H, H, nullptr, s));
     scores_kernel<<<dim3(L + 1, N), 128, 0, s>>>(P, hp_.as<double>(), sp_.as<double>(), Va_, e_.as<double>(), L, H);
     softmax_kernel<<<N, 256, 0, s>>>(e_.as<double>(), alpha_.as<double>(), beta_.as<double>(), i, T, L);
-    context_kernel<<<N, 256, 0, s>>>(Vf, alpha_.as<double>(), beta_.as<double>(), s_.as<double>(), ctx_.as<double>(),
+    context_kernel<<<dim3(N, (H + 127) / 128), 128, 0, s>>>(Vf, alpha_.as<double>(), beta_.as<double>(), s_.as<double>(), ctx_.as<double>(),
                                      chat_.as<double>(), h1_.as<double>(), td ? nullptr : hc_.as<double>(), i, T, L, H);
     launches_ += 6;
     if (td) {
@@ -488,8 +488,14 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
       uv_adaptive_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), ctx_.as<double>(),
                                                     Rctx_.as<double>(), UV_.as<double>(), T, L, H);
     else
-      uv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
+      if (T <= kUvMaxT) {
+        constexpr int kLG = 14;
+        uv_gridtd_rows_kernel<<<dim3((L + kLG - 1) / kLG, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
+                                                  UV_.as<double>(), T, L, H, kLG);
+      } else {
+        uv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
                                                   UV_.as<double>(), T, L, H);
+      }
     LRPCAP_TRY(features_gemm(m, s));
     final_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F_.as<double>(), ra_.as<double>(),
                                             YF_.as<double>(), d_R_head, L, D);

@@ -32,19 +32,31 @@ dgemm_kernel(const double* __restrict__ A, int lda, const double* __restrict__ B
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = kb; k0 < K; k0 += GK) {
-    __syncthreads();
+  // register prefetch: the global loads of tile k0 + GK are in flight while tile k0 is multiplied
+  double ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int idx = tid + r * 256;          // 64 x 16
       const int mm = idx >> 4, kk = idx & 15;
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[(size_t)gm * lda + gk] : 0.0;
+      ra[r] = (gm < M && gk < K) ? __ldg(A + (size_t)gm * lda + gk) : 0.0;
       const int kr = idx >> 6, nn = idx & 63;  // 16 x 64
       const int gn = n0 + nn, gkb = k0 + kr;
-      Bs[kr][nn] = (gn < N && gkb < K) ? B[(size_t)gkb * ldb + gn] : 0.0;
+      rb[r] = (gn < N && gkb < K) ? __ldg(B + (size_t)gkb * ldb + gn) : 0.0;
+    }
+  };
+  fetch(kb);
+  for (int k0 = kb; k0 < K; k0 += GK) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      As[idx & 15][idx >> 4] = ra[r];
+      Bs[idx >> 6][idx & 63] = rb[r];
     }
     __syncthreads();
+    if (k0 + GK < K) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
       double a[4], b[4];
@@ -241,8 +253,9 @@ __global__ void context_kernel(const double* __restrict__ Vf, const double* __re
   const size_t s1 = ((size_t)n * (T + 1) + i + 1) * H;
   const double* an = alpha + ((size_t)n * (T + 1) + i + 1) * L;
   const double b = beta[(size_t)n * (T + 1) + i + 1];
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+  for (int j = blockIdx.y * blockDim.x + threadIdx.x; j < H; j += gridDim.y * blockDim.x) {
     double acc = 0.0;
+#pragma unroll 14   // independent loads in flight; the additions keep their order
     for (int l = 0; l < L; ++l) acc += an[l] * Vf[((size_t)n * L + l) * H + j];
     ctx[s1 + j] = acc;
     const double ch = b * s[s1 + j] + (1.0 - b) * acc;
@@ -489,6 +502,39 @@ __global__ void uv_gridtd_kernel(WordRef w, int p0, const double* __restrict__ V
       acc = (float)((double)acc + vf * al * Q[((size_t)p * T + i) * H + j]);
     }
     o[j] = (double)acc / stabd(vp[j]);
+  }
+}
+// Same arithmetic, one block per (word, group of LG locations): the word's Q rows (T x H, shared by all L locations) are
+// held in registers instead of being re-read from L2 for every location.
+constexpr int kUvMaxT = 24;   // the switch below enumerates steps 23 .. 0
+__global__ void __launch_bounds__(256, 3)
+uv_gridtd_rows_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
+                      const double* __restrict__ Q, double* __restrict__ UV, int T, int L, int H, int LG) {
+  const int p = p0 + blockIdx.y;
+  const int n = w.img[p], t = w.t[p];
+  const int l0 = blockIdx.x * LG, l1 = (l0 + LG < L) ? l0 + LG : L;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    double q[kUvMaxT];
+#pragma unroll
+    for (int i = 0; i < kUvMaxT; ++i) q[i] = (i < t) ? Q[((size_t)p * T + i) * H + j] : 0.0;
+    for (int l = l0; l < l1; ++l) {
+      const double v = Vp[((size_t)n * L + l) * H + j];
+      const double vf = fmax(v, 0.0);
+      const double* al = alpha + ((size_t)n * (T + 1) + 1) * L + l;
+      float acc = 0.f;
+      // steps t-1 .. 0 in the reference's order; the fall-through switch enters the unrolled sequence at step t-1 so that
+      // q[] keeps static register indices and no skipped step is issued
+#define LRPCAP_UV_STEP(I) case (I) + 1: acc = (float)((double)acc + vf * al[(size_t)(I) * L] * q[I]);
+      switch (t) {
+        LRPCAP_UV_STEP(23) LRPCAP_UV_STEP(22) LRPCAP_UV_STEP(21) LRPCAP_UV_STEP(20) LRPCAP_UV_STEP(19) LRPCAP_UV_STEP(18)
+        LRPCAP_UV_STEP(17) LRPCAP_UV_STEP(16) LRPCAP_UV_STEP(15) LRPCAP_UV_STEP(14) LRPCAP_UV_STEP(13) LRPCAP_UV_STEP(12)
+        LRPCAP_UV_STEP(11) LRPCAP_UV_STEP(10) LRPCAP_UV_STEP(9) LRPCAP_UV_STEP(8) LRPCAP_UV_STEP(7) LRPCAP_UV_STEP(6)
+        LRPCAP_UV_STEP(5) LRPCAP_UV_STEP(4) LRPCAP_UV_STEP(3) LRPCAP_UV_STEP(2) LRPCAP_UV_STEP(1) LRPCAP_UV_STEP(0)
+        default: break;
+      }
+#undef LRPCAP_UV_STEP
+      UV[((size_t)blockIdx.y * L + l) * H + j] = (double)acc / stabd(v);
+    }
   }
 }
 // R_F[word, l, d] = float32( float32(F/L * ra) + F * YF )      (explainers.py:641-659)

@@ -30,7 +30,7 @@ METRIC = "explained words/sec (full LRP to pixels)"
 UNIT = "words/s"
 N_IMG, T_WORDS, VOCAB, HW = 64, 20, 10000, 224
 ENC_GFLOP_PER_WORD = 30.69      # one transposed-conv sweep of VGG16
-NCU_DRAM_MB_PER_WORD = 94.5     # measured: profiles/r01_ncu_full_tc_conv_bwd_summary.csv
+NCU_DRAM_MB_PER_WORD = 103.1    # measured: profiles/r01b_ncu_full_bwd_summary.csv (33.0 GB over 320 words)
 
 
 def peaks():
@@ -220,11 +220,12 @@ def run_ours(args, rank, local_rank, world):
     peak_tf, peak_bw, peak_src = peaks()
     tc_ms, tc_flops, tc_n = prof["tc_bwd"]
     achieved = (tc_flops / 1e12) / (tc_ms / 1e3) if tc_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "tc_conv_kernel<BN, EPI_BWD> (tcgen05 transposed conv + fused rule epilogue)",
+    roofline = {"bound": "tensor", "kernel": "tc_conv_kernel / tc_conv_vh_kernel <BN, EPI_BWD> (tcgen05 transposed conv + fused rule epilogue)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": NCU_DRAM_MB_PER_WORD * 1e6 * n_words / max(tc_n / max(args.steps, 1), 1.0),
-                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (profiles/r01_ncu_full_tc_conv_bwd_summary.csv, "
-                                "80 words: 7.56 GB = %.1f MB/word; algorithmic message traffic 95.1 MB/word), scaled to this run's words per launch" % NCU_DRAM_MB_PER_WORD,
+                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (profiles/r01b_ncu_full_bwd_summary.csv, "
+                                "320 words: 33.0 GB = %.1f MB/word; algorithmic: 95.1 MB/word of messages + the per-image multipliers), "
+                                "scaled to this run's words per launch" % NCU_DRAM_MB_PER_WORD,
                 "peak_source": "%s bf16 cuBLAS (sustained)" % peak_src,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC of the transposed convs, %.2f GFLOP/word) / CUDA-event "
                         "kernel time; every algorithmic MAC is 3 bf16 tensor-core MACs (hi*hi + hi*lo + lo*hi), so tensor-pipe "
@@ -262,7 +263,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"])
-    ap.add_argument("--chunk-words", type=int, default=640)
+    ap.add_argument("--chunk-words", type=int, default=320)
     ap.add_argument("--promote", type=int, default=None, help="backward accumulator promotion interval (k-steps; 0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

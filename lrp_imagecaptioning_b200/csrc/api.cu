@@ -83,11 +83,7 @@ int lrpcap_encoder_relevance_host(lrpcap_encoder_t* enc, const int* h_img_index,
     set_last_error("encoder_relevance_host: H2D copy failed");
     st = kErrCuda;
   }
-  if (st == kOk) st = e->relevance(h_img_index, dR.as<float>(), n_words, dP.as<float>(), s);
-  if (st == kOk && cudaMemcpyAsync(h_R_pix, dP.p, pix * sizeof(float), cudaMemcpyDeviceToHost, s) != cudaSuccess) {
-    set_last_error("encoder_relevance_host: D2H copy failed");
-    st = kErrCuda;
-  }
+  if (st == kOk) st = e->relevance(h_img_index, dR.as<float>(), n_words, dP.as<float>(), s, h_R_pix);
   if (st == kOk) {
     cudaError_t err = cudaStreamSynchronize(s);
     if (err != cudaSuccess) {

@@ -89,8 +89,7 @@ int lrpcap_explain_batch_host(lrpcap_encoder_t* enc, lrpcap_decoder_t* dec, cons
     }
   if (method == 0) LRPCAP_TRY(D->relevance(wimg.data(), wt.data(), W, d_head.as<float>(), nullptr, nullptr, s));
   else LRPCAP_TRY(D->backward(wimg.data(), wt.data(), W, d_head.as<float>(), nullptr, s));
-  LRPCAP_TRY(E->relevance(wimg.data(), d_head.as<float>(), W, d_pix.as<float>(), s));
-  LRPCAP_CUDA(cudaMemcpyAsync(h_R_pix, d_pix.p, (size_t)W * hw * hw * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  LRPCAP_TRY(E->relevance(wimg.data(), d_head.as<float>(), W, d_pix.as<float>(), s, h_R_pix));   // chunk-wise D2H overlap
   LRPCAP_CUDA(cudaStreamSynchronize(s));
   return kOk;
 }

@@ -35,6 +35,9 @@ Encoder::~Encoder() {
       for (auto& p : f)
         if (p) cudaFree(p);
   }
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
+  if (ev_chunk_) cudaEventDestroy(ev_chunk_);
+  if (ev_copied_) cudaEventDestroy(ev_copied_);
   if (w0_pm_) cudaFree(w0_pm_);
   if (w0_mp_) cudaFree(w0_mp_);
   if (w0_last_a_) cudaFree(w0_last_a_);
@@ -335,7 +338,8 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
   return kOk;
 }
 
-int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s) {
+int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s,
+                       float* h_R_pix) {
   LRPCAP_REQUIRE(n_images_ > 0, kErrState, "encoder_relevance: call encoder_forward first");
   LRPCAP_REQUIRE(h_img_index && d_R_head && d_R_pix && n_words > 0, kErrInvalidArg, "encoder_relevance: bad argument");
   for (int w = 0; w < n_words; ++w)
@@ -410,6 +414,21 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       prof_.push_back(rec);
     }
     ++launches_;
+    if (h_R_pix) {   // stream this chunk's maps to the host while the next chunk computes
+      if (!copy_stream_) {
+        LRPCAP_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+        LRPCAP_CUDA(cudaEventCreateWithFlags(&ev_chunk_, cudaEventDisableTiming));
+        LRPCAP_CUDA(cudaEventCreateWithFlags(&ev_copied_, cudaEventDisableTiming));
+      }
+      LRPCAP_CUDA(cudaEventRecord(ev_chunk_, s));
+      LRPCAP_CUDA(cudaStreamWaitEvent(copy_stream_, ev_chunk_, 0));
+      LRPCAP_CUDA(cudaMemcpyAsync(h_R_pix + (size_t)w0 * pix_elems, d_R_pix + (size_t)w0 * pix_elems,
+                                  (size_t)m * pix_elems * sizeof(float), cudaMemcpyDeviceToHost, copy_stream_));
+    }
+  }
+  if (h_R_pix && copy_stream_) {
+    LRPCAP_CUDA(cudaEventRecord(ev_copied_, copy_stream_));
+    LRPCAP_CUDA(cudaStreamWaitEvent(s, ev_copied_, 0));
   }
   return kOk;
 }

@@ -56,7 +56,11 @@ class Encoder {
   int n_images() const { return n_images_; }
   int image_hw() const { return hw_; }
   // h_img_index[w] -> image of word w; d_R_head fp32 [n_words, fh, fh, 512]; d_R_pix fp32 [n_words, hw, hw, 3].
-  int relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s);
+  // h_R_pix (optional, ideally pinned): every chunk of words is copied to the host on a second stream as soon as its
+  // last kernel has finished, overlapping the device->host transfer with the next chunk; `s` is made to wait for the
+  // last copy, so synchronising `s` covers the host buffer.
+  int relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s,
+                float* h_R_pix = nullptr);
   void set_chunk_words(int n) { chunk_words_ = n > 0 ? n : 1; }
   // k-steps between fp32 promotions of the tensor-core accumulator in the backward GEMMs (0 = never)
   void set_promote(int every) { bwd_promote_ = every > 0 ? every : 0; }
@@ -74,6 +78,8 @@ class Encoder {
     int cls;
     double flops;
   };
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t ev_chunk_ = nullptr, ev_copied_ = nullptr;
   bool profile_ = false;
   std::vector<ProfRec> prof_;
   struct Layer {

@@ -1,5 +1,5 @@
-"""Short encoder-only workload for ncu: forward of 4 images, then the relevance backward for 80 words (20 per image)
-at 224x224, epsilon rule.  `ncu -k regex:tc_conv_kernel -s 12 -c 12` captures the 12 transposed-conv launches."""
+"""Short encoder-only workload for ncu: forward of 4 images, then the relevance backward for 4 x WORDS_PER_IMAGE words
+(default 20 each) at 224x224, epsilon rule.  `ncu -k regex:tc_conv_kernel -s 12 -c 12` captures the 12 transposed-conv launches."""
 import os, sys
 import numpy as np
 import torch
@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lrp_imagecaptioning_b200 import synth, _lib
 from lrp_imagecaptioning_b200.encoder import ImageModel, RuleSpec
 
-n_img, per = 4, 20
+n_img, per = 4, int(os.environ.get("WORDS_PER_IMAGE", "20"))
 m = ImageModel(synth.vgg16_weights(0), image_hw=224, precision="bf16x3")
 m.set_chunk_words(n_img * per)
 x = synth.images(n_img, 224, 1)

@@ -169,6 +169,25 @@ int lrpcap_scale_maps(float* d_maps, const float* d_cam, int n_words, int hw, vo
  * d_maps [n_words, hw, hw, 3]; h_scores [n_words].  Synchronous. */
 int lrpcap_lrp_inference_scores(const float* d_maps, int n_words, int hw, int mode, float* h_scores, void* stream);
 
+/* ----------------------------------------------------------------------------------------------- evaluation reductions
+ * Heat maps the reference derives from a pixel relevance map before it evaluates or plots it.
+ *   mode 0: hp = mean_c(postprocess(R))                    exaimin_word.py:96-103, :127-128
+ *   mode 1: hp = mean_c(relu(-postprocess(R)))             evaluate_bbox.py:79-83 (negative scores, the committed variant)
+ *   mode 2: hp = mean_c(relu(postprocess(R)))              evaluate_bbox.py:80 commented out
+ * then `project`: hp / max|hp| (all zeros if the maximum is 0), and, when shift_negative != 0 and some value is
+ * negative, (hp + 1) / 2 (evaluate_bbox.py:60-69).  window > 1 first pools window x window tiles of the channel value,
+ * pool_type 0 = max, 1 = average (exaimin_word.py:64-77, :143-148; the reference uses 16 on 224 x 224 maps).
+ * d_maps [n_words, hw, hw, 3]; d_out [n_words, hw/window, hw/window]; h_means (optional) [n_words] = mean of each
+ * projected map (exaimin_word.py:446-447).  Synchronous when h_means is given. */
+int lrpcap_heatmaps(const float* d_maps, int n_words, int hw, int mode, int shift_negative, int window, int pool_type,
+                    float* d_out, float* h_means, void* stream);
+/* Bounding-box "correctness" `_calculate_overlaped_pixels` (evaluate_bbox.py:191-208) for many boxes and thresholds:
+ * values <= threshold are dropped; ratio = mass inside the box / total mass, 0 when the total is 0, capped at 1.
+ * d_heatmaps [n_maps, hw, hw]; h_boxes [n_boxes, 5] = (map index, x0, y0, x1, y1), rows y0..y1-1, columns x0..x1-1;
+ * h_ratio [n_boxes, n_thresholds] (n_thresholds <= 16).  Synchronous. */
+int lrpcap_bbox_correctness(const float* d_heatmaps, int n_maps, int hw, const int* h_boxes, int n_boxes,
+                            const float* h_thresholds, int n_thresholds, float* h_ratio, void* stream);
+
 /* ----------------------------------------------------------------------------------------------- debug / tests
  * Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
  * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */

@@ -63,6 +63,8 @@ PROTOTYPES = {
     "lrpcap_gradcam": (ctypes.c_int, [c_void_p, c_int_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, c_void_p, c_void_p]),
     "lrpcap_scale_maps": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_void_p]),
     "lrpcap_lrp_inference_scores": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_void_p]),
+    "lrpcap_heatmaps": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_float_p, c_void_p]),
+    "lrpcap_bbox_correctness": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_debug_conv": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p]),
 }
 

@@ -76,6 +76,61 @@ def main_lrp_inference():
         print(path, os.path.getsize(path), "bytes")
 
 
+def evaluation_case():
+    """Seeded pixel maps, boxes and thresholds shared by the generator and the tests."""
+    rng = np.random.default_rng(5)
+    maps = (rng.standard_normal((3, 224, 224, 3)) * (rng.random((3, 224, 224, 1)) > 0.6)).astype(np.float32)
+    boxes = [(0, 10, 20, 120, 200), (1, 100, 3, 224, 77), (2, 0, 0, 224, 224), (0, 50, 50, 51, 51)]
+    thresholds = [0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
+    return maps, boxes, thresholds
+
+
+def reference_evaluation_objects():
+    """The reference's evaluation classes (evaluate_bbox.py:39, exaimin_word.py:27) under the Keras stub, with the
+    explainer replaced by a stand-in that returns a prepared pixel map; skimage's pyramid_expand (absent) is only used
+    for the attention map, which this path does not check."""
+    import importlib
+    refstub.load_reference()
+    eb = importlib.import_module("evaluate_bbox")
+    ew = importlib.import_module("exaimin_word")
+    eb.skimage.transform.pyramid_expand = lambda a, **k: np.zeros((224, 224))
+    eb.K.image_data_format = lambda: "channels_last"
+
+    class FakeExplainer(object):
+        def __init__(self):
+            self.map = None
+
+        def _explain_lstm_single_word_sequence(self, t):
+            return None, np.zeros(196)
+
+        def _explain_CNN(self, img, rel):
+            return self.map[None].copy()
+    bb = object.__new__(eb.EvaluationBboxCOCO)
+    bb._img_encoder, bb._color_conversion, bb._explainer = "vgg16", "BGRtoRGB", FakeExplainer()
+    ex = object.__new__(ew.Explainer)
+    return bb, ex
+
+
+def main_evaluation():
+    maps, boxes, thresholds = evaluation_case()
+    bb, ex = reference_evaluation_objects()
+    store = {"heat_negative": [], "ratios": [], "pool_max": [], "pool_ave": []}
+    for i in range(maps.shape[0]):
+        bb._explainer.map = maps[i]
+        hm, _ = bb._get_explanation((None, None), 1)
+        store["heat_negative"].append(hm)
+        hp = np.mean(maps[i][..., ::-1], axis=-1)
+        store["pool_max"].append(ex._max_pooling(hp))
+        store["pool_ave"].append(ex._ave_pooling(hp))
+    for (mi, x0, y0, x1, y1) in boxes:
+        rel = store["heat_negative"][mi].copy()
+        store["ratios"].append([bb._calculate_overlaped_pixels([x0, y0, x1, y1], rel, th) for th in thresholds])
+    path = os.path.join(ROOT, "tests", "golden", "evaluation.npz")
+    np.savez_compressed(path, **{k: np.asarray(v, dtype=np.float32 if k != "ratios" else np.float64) for k, v in store.items()})
+    print(path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
     main_lrp_inference()
+    main_evaluation()

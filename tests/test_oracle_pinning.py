@@ -142,3 +142,36 @@ def test_lrp_inference_oracle_matches_reference_fixture(kind):
         assert np.abs(got - z[mode]).max() <= 1e-6
     with pytest.raises(NotImplementedError):
         lrp_inference_weights(dec, vgg, imgs, yp, eos=2, mode="bogus")
+
+
+# ---------------------------------------------------------------- evaluation helpers (evaluate_bbox.py, exaimin_word.py)
+def test_evaluation_oracle_matches_reference_fixture():
+    """Fixture = outputs of the reference's own EvaluationBboxCOCO._get_explanation / _calculate_overlaped_pixels and
+    Explainer._max_pooling / _ave_pooling (oracle/make_golden.py: main_evaluation)."""
+    from oracle.make_golden import evaluation_case
+    from oracle import evaluation_ref as EV
+    z = np.load(os.path.join(GOLD, "evaluation.npz"))
+    maps, boxes, thresholds = evaluation_case()
+    for i in range(maps.shape[0]):
+        assert np.abs(EV.heatmap(maps[i], "negative", True) - z["heat_negative"][i]).max() <= 1e-7
+        hp = np.mean(EV.postprocess(maps[i]), axis=-1)
+        assert np.abs(EV.pool(hp, 16, "max") - z["pool_max"][i]).max() <= 1e-7
+        assert np.abs(EV.pool(hp, 16, "ave") - z["pool_ave"][i]).max() <= 1e-7
+    for bi, (mi, x0, y0, x1, y1) in enumerate(boxes):
+        for ti, th in enumerate(thresholds):
+            ref = EV.overlapped_pixels([x0, y0, x1, y1], z["heat_negative"][mi], th)
+            assert abs(ref - z["ratios"][bi, ti]) <= 1e-9
+
+
+def test_evaluation_oracle_matches_reference_code_when_present():
+    from oracle import refstub
+    if not refstub.reference_available():
+        pytest.skip("reference tree not present")
+    from oracle.make_golden import evaluation_case, reference_evaluation_objects
+    from oracle import evaluation_ref as EV
+    maps, boxes, thresholds = evaluation_case()
+    bb, ex = reference_evaluation_objects()
+    bb._explainer.map = maps[1]
+    hm, _ = bb._get_explanation((None, None), 1)
+    assert np.abs(EV.heatmap(maps[1], "negative", True) - hm).max() == 0
+    assert bb._calculate_overlaped_pixels([100, 3, 224, 77], hm.copy(), 0.2) == EV.overlapped_pixels([100, 3, 224, 77], hm, 0.2)

@@ -74,7 +74,8 @@ def config_dict(args, world):
     return {"workload": "configs[1]: grid-TD, %d images/GPU x %d greedy words, LRP-eps decoder + VGG16 LRPEpsilon(0.01) encoder, 224x224"
                         % (N_IMG, T_WORDS),
             "images_per_gpu": N_IMG, "words_per_image": T_WORDS, "vocab": VOCAB, "parallelism": "images sharded over %d GPU(s), no data-path collective" % world,
-            "precision": args.precision, "l2": "inputs larger than L2 (relevance messages are GBs per layer)"}
+            "precision": args.precision, "l2": "inputs larger than L2 (relevance messages are GBs per layer)",
+            "lanes": getattr(args, "lanes", 1), "chunk_words": getattr(args, "chunk_words", None)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -130,7 +131,7 @@ def run_ours(args, rank, local_rank, world):
     import torch
     from lrp_imagecaptioning_b200 import _lib, synth
     from lrp_imagecaptioning_b200.encoder import RuleSpec
-    from lrp_imagecaptioning_b200.engine import ExplainEngine, word_list
+    from lrp_imagecaptioning_b200.engine import ExplainEngine, StreamedEngine, word_list
     from lrp_imagecaptioning_b200.model import CaptioningModel
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU path; use --impl reference for the CPU arm)")
@@ -150,7 +151,13 @@ def run_ours(args, rank, local_rank, world):
     wi, wt = word_list(N_IMG, T_WORDS)
     n_words = len(wi)
 
+    lanes = max(1, args.lanes)
+    seng = StreamedEngine(model, rule=eng.rule, lanes=lanes, chunk_words=args.chunk_words) if lanes > 1 else None
+    engines = [l["engine"] for l in seng.lanes] if seng else [eng]
+
     def step_resident():
+        if seng:
+            return seng.explain_batch(x_dev, T_WORDS, greedy=True)[0]
         eng.forward(x_dev, T=T_WORDS, greedy=True)
         return eng.explain_words(wi, wt)
 
@@ -160,7 +167,7 @@ def run_ours(args, rank, local_rank, world):
     x_np = x_host.numpy()
 
     def step_e2e():
-        eng.explain_batch_host(x_np, cap_host, greedy=True, out=out_np)
+        (seng or eng).explain_batch_host(x_np, cap_host, greedy=True, out=out_np)
         return float(out_np[0, 0, 0, 0])
 
     def barrier():
@@ -189,15 +196,19 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
-    l0 = eng.launches()
-    model.image_model.profile(True)
-    model.image_model.profile_read()
+    l0 = sum(e.launches() for e in engines)
+    for e in engines:
+        e.image_model.profile(True)
+        e.image_model.profile_read()
     sampler.start()
     ms = timed(step_resident, args.steps, 0)
     clocks = sampler.stop()
-    prof = model.image_model.profile_read()
-    model.image_model.profile(False)
-    launches = (eng.launches() - l0) // max(args.steps, 1)
+    prof = None
+    for e in engines:   # kernel times add up over the lanes (their launches queue behind one another on the SMs)
+        p = e.image_model.profile_read()
+        e.image_model.profile(False)
+        prof = p if prof is None else {k: tuple(a + b for a, b in zip(prof[k], p[k])) for k in p}
+    launches = (sum(e.launches() for e in engines) - l0) // max(args.steps, 1)
     ms_e2e = timed(step_e2e, args.steps, max(1, min(args.warmup, 2)))
 
     # phase breakdown of one extra resident step (CUDA events on the launching stream)
@@ -264,6 +275,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "fp32"])
     ap.add_argument("--chunk-words", type=int, default=320)
+    ap.add_argument("--lanes", type=int, default=1, help="independent stream/thread lanes over blocks of images")
     ap.add_argument("--promote", type=int, default=None, help="backward accumulator promotion interval (k-steps; 0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -72,7 +72,7 @@ int lrpcap_explain_batch_host(lrpcap_encoder_t* enc, lrpcap_decoder_t* dec, cons
   const int hw = E->image_hw(), fh = E->feature_hw(), L = fh * fh;
   const size_t img_elems = (size_t)n_images * hw * hw * 3;
   const int W = n_images * T;
-  static thread_local DevBuf d_img, d_head, d_pix;   // reused across calls of the same thread
+  DevBuf &d_img = enc->stage_img, &d_head = enc->stage_head, &d_pix = enc->stage_pix;   // reused across calls
   LRPCAP_TRY(d_img.ensure(img_elems * sizeof(float)));
   LRPCAP_TRY(d_head.ensure((size_t)W * L * 512 * sizeof(float)));
   LRPCAP_TRY(d_pix.ensure((size_t)W * hw * hw * 3 * sizeof(float)));

@@ -84,3 +84,104 @@ class ExplainEngine(object):
 
     def launches(self):
         return self.image_model.launches() + self.decoder.launches()
+
+
+class StreamedEngine(object):
+    """Runs `lanes` independent ExplainEngine instances, one CUDA stream and one host thread each, on contiguous blocks
+    of the batch's images.
+
+    Explanation jobs of different images are independent, and the decoder phases are chains of
+    small latency-bound kernels that leave most SMs idle: with several lanes in flight those phases overlap each other
+    and the tensor-core phases of the other lanes, while the tcgen05 kernels (persistent, one CTA per SM) simply queue
+    behind one another. Each lane owns its handles (per-image state, message buffers); the weights are shared on the
+    host and uploaded once per lane."""
+
+    def __init__(self, model, rule=None, lanes=2, sos=1, eos=2, keras_logits=False, chunk_words=None):
+        import threading
+        from .model import CaptioningModel
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.device = torch.device(model.device)
+        self.lanes = []
+        for i in range(lanes):
+            m = model if i == 0 else CaptioningModel(model.kind, model.vgg, model.dec, image_hw=model.image_hw,
+                                                     precision=model.precision, device=model.device)
+            eng = ExplainEngine(m, rule=rule, sos=sos, eos=eos, keras_logits=keras_logits)
+            if chunk_words:
+                m.image_model.set_chunk_words(chunk_words)
+            self.lanes.append({"engine": eng, "stream": torch.cuda.Stream(device=self.device)})
+        self.rule = self.lanes[0]["engine"].rule
+        self.eos = eos
+        self._threading = threading
+
+    def _split(self, n):
+        k = len(self.lanes)
+        base, rem = divmod(n, k)
+        bounds, s = [], 0
+        for i in range(k):
+            e = s + base + (1 if i < rem else 0)
+            bounds.append((s, e))
+            s = e
+        return bounds
+
+    def _run(self, fn):
+        """fn(lane_index, lane) on one host thread per lane; the lane streams start after the caller's stream and the
+        caller's stream continues after all of them (so CUDA events on the caller's stream bracket the work)."""
+        cur = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(cur)
+        results, errors = [None] * len(self.lanes), []
+
+        def work(i, lane):
+            try:
+                torch.cuda.set_device(self.device)
+                lane["stream"].wait_event(start)
+                with torch.cuda.stream(lane["stream"]):
+                    results[i] = fn(i, lane)
+            except BaseException as e:   # re-raised on the calling thread
+                errors.append(e)
+        threads = [self._threading.Thread(target=work, args=(i, lane)) for i, lane in enumerate(self.lanes)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for lane in self.lanes:
+            done = torch.cuda.Event()
+            done.record(lane["stream"])
+            cur.wait_event(done)
+        if errors:
+            raise errors[0]
+        return results
+
+    def explain_batch(self, images, T, greedy=True, method=METHOD_LRP, captions=None):
+        """images: torch cuda [N, hw, hw, 3]. Returns (list of per-lane maps [n_i*T, hw, hw, 3] in image order, captions)."""
+        bounds = self._split(images.shape[0])
+
+        def fn(i, lane):
+            a, b = bounds[i]
+            if b <= a:
+                return None, np.zeros((0, T), dtype=np.int32)
+            cap = None if captions is None else np.ascontiguousarray(captions[a:b])
+            return lane["engine"].explain_batch(images[a:b], captions=cap, T=T, greedy=greedy, method=method)
+        res = self._run(fn)
+        maps = [r[0] for r in res if r[0] is not None]
+        for m in maps:
+            m.record_stream(torch.cuda.current_stream(self.device))
+        return maps, np.concatenate([r[1] for r in res], axis=0)
+
+    def explain_batch_host(self, images, captions, greedy=True, method=METHOD_LRP, out=None):
+        """Host buffers in and out, one lrpcap_explain_batch_host call per lane on its block of images."""
+        N, hw, T = images.shape[0], images.shape[1], captions.shape[1]
+        if out is None:
+            out = np.empty((N * T, hw, hw, 3), dtype=np.float32)
+        bounds = self._split(N)
+
+        def fn(i, lane):
+            a, b = bounds[i]
+            if b > a:
+                lane["engine"].explain_batch_host(images[a:b], captions[a:b], greedy=greedy, method=method, out=out[a * T:b * T])
+        self._run(fn)
+        return out
+
+    def launches(self):
+        return sum(l["engine"].launches() for l in self.lanes)

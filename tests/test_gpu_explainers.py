@@ -140,3 +140,27 @@ def test_greedy_is_beam_one():
     ex = E.ExplainImgCaptioningGridTDModel(model, None, _Provider(), 5)
     caps = ex._beam_search((None, synth.images(2, HW, 9)), 1)
     assert len(caps) == 1 and len(caps[0]) == 2 and all(len(c) >= 1 for c in caps[0])
+
+
+def test_streamed_engine_lanes_give_identical_maps():
+    """Independent lanes (own handles, stream and host thread per block of images) must reproduce the single-engine
+    result bit for bit, resident and through the host-buffer C-ABI call."""
+    import torch
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.engine import ExplainEngine, StreamedEngine
+    model, _, _ = _model("gridtd", seed=3)
+    x = synth.images(5, HW, 21)
+    T = 4
+    one = ExplainEngine(model)
+    ref_maps, ref_cap = one.explain_batch(torch.from_numpy(x).cuda(), T=T, greedy=True)
+    ref_maps = ref_maps.cpu().numpy()
+    se = StreamedEngine(model, lanes=3, chunk_words=7)
+    maps, cap = se.explain_batch(torch.from_numpy(x).cuda(), T, greedy=True)
+    torch.cuda.synchronize()
+    got = torch.cat(maps, 0).cpu().numpy()
+    assert np.array_equal(cap, ref_cap)
+    assert np.array_equal(got, ref_maps)
+    cap_h = np.zeros((5, T), dtype=np.int32)
+    host = se.explain_batch_host(x, cap_h, greedy=True)
+    assert np.array_equal(cap_h, ref_cap)
+    assert np.array_equal(host, ref_maps)

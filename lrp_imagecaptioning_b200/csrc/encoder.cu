@@ -61,6 +61,9 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
   Encoder* e = new Encoder();
   e->hw_ = image_hw;
   e->precision_ = precision;
+  if (const char* v = std::getenv("LRPCAP_FWD_PLANES")) {    // experiment knob: bf16 planes of the forward operands
+    if (std::atoi(v) == 2) e->fwd_planes_ = 2;
+  }
   if (const char* v = std::getenv("LRPCAP_FWD_PROMOTE")) {   // experiment knob: k-steps per accumulator hand-over, forward
     const int n = std::atoi(v);
     if (n >= 1 && n <= 64) e->fwd_promote_ = n;
@@ -129,7 +132,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
   const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
   if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
   if (dual) LRPCAP_TRY(get_dual_weights(l, tc, &B, s));
-  else LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : WF_TC_FWD3) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  else LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : (fwd_planes_ == 3 ? WF_TC_FWD3 : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
   ProfRec rec{};
   if (profile_) {
     LRPCAP_CUDA(cudaEventCreate(&rec.a));
@@ -143,7 +146,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     TcConvArgs a;
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout * (dual ? 2 : 1); a.taps = 9; a.Nout = Nout;
-    a.planes = backward ? 2 : 3;
+    a.planes = backward ? 2 : fwd_planes_;
     a.promote_every = backward ? bwd_promote_ : fwd_promote_;
     a.epi = epi;
     st = tc_conv_launch(a, s);
@@ -151,7 +154,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     SimtConvArgs a;
     a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout;
-    a.out_planes = split() ? (backward ? 2 : 3) : 0;
+    a.out_planes = split() ? (backward ? 2 : fwd_planes_) : 0;
     a.epi = epi;
     st = simt_conv_launch(a, s);
   }

@@ -98,10 +98,10 @@ class Encoder {
   // storage planes of forward activations: 3 bf16 planes (fp32-exact operands) in tensor-core mode, fp32 otherwise.
   // The per-image forward decides ReLU signs / pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level
   // errors downstream, while the per-word backward is insensitive to them.
-  int fwd_planes() const { return split() ? 3 : 0; }
+  int fwd_planes() const { return split() ? fwd_planes_ : 0; }
   size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
 
-  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0, fwd_promote_ = 1;
+  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0, fwd_promote_ = 1, fwd_planes_ = 3;
   long long launches_ = 0;
   EncoderRule rule_;
   Layer L_[kLayers];

@@ -21,7 +21,7 @@ Decoder::~Decoder() {
   DevBuf* bufs[] = {&F_, &Vp_, &P_, &a_, &gp_, &tok_, &logitk_, &logits_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_,
                     &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
                     &Z_, &hp_, &sg_, &sp_, &e_, &hc_, &d_wimg_, &d_wt_, &d_order_, &Rh1_, &Rh2_, &Rh2n_, &Rc1_, &Rc2_,
-                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_, &As_, &C32_};
+                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_, &As_, &C32_, &As3_};
   for (DevBuf* b : bufs) b->release();
 }
 
@@ -105,6 +105,40 @@ int Decoder::gemm_tc(const double* A, int M, int K, const void* Bsplit, int N, d
   return kOk;
 }
 
+int Decoder::split3_weights(const double* d_Wt, int N, int K, int* Npad, void** out) {
+  const int np = (N + 63) / 64 * 64;
+  void* p = nullptr;
+  LRPCAP_CUDA(cudaMalloc(&p, (size_t)3 * np * K * sizeof(__nv_bfloat16)));
+  owned_.push_back(p);
+  f64_rows_to_split3_kernel<<<nblk((size_t)np * K, 256), 256>>>(d_Wt, K, N, K, np, reinterpret_cast<__nv_bfloat16*>(p));
+  LRPCAP_CUDA(cudaGetLastError());
+  LRPCAP_CUDA(cudaDeviceSynchronize());
+  *Npad = np;
+  *out = p;
+  return kOk;
+}
+
+int Decoder::gemm_tc3(const double* A, int lda, int M, int K, const void* B3, int Npad, int N, const double* bias,
+                      double* C, int ldc, cudaStream_t s) {
+  if (M <= 0) return kOk;
+  const int Mpad = (M + 15) / 16 * 16;            // rows laid out as a [1, Mpad/16, 16, K] "image" for the 1x1-conv kernel
+  const size_t nA = (size_t)Mpad * K;
+  LRPCAP_TRY(As3_.ensure(nA * 3 * sizeof(__nv_bfloat16)));
+  LRPCAP_TRY(C32_.ensure((size_t)Mpad * Npad * sizeof(float)));
+  f64_rows_to_split3_kernel<<<nblk(nA, 256), 256, 0, s>>>(A, lda, M, K, Mpad, As3_.as<__nv_bfloat16>());
+  TcConvArgs a;
+  a.A = As3_.p; a.A_elems = nA; a.n_items = 1; a.H = Mpad / 16; a.W = 16; a.C = K;
+  a.B = B3; a.B_elems = (size_t)Npad * K; a.taps = 1; a.Nout = Npad;
+  a.planes = 3;
+  a.epi.mode = EPI_RAW;
+  a.epi.out_f32 = C32_.as<float>();
+  LRPCAP_TRY(tc_conv_launch(a, s));
+  f32_to_f64_bias_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(C32_.as<float>(), Npad, C, ldc, M, N, bias);
+  launches_ += 3;
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
 int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_token, int keras_logits) {
   LRPCAP_REQUIRE(out && w, kErrInvalidArg, "decoder_create: null argument");
   LRPCAP_REQUIRE(w->kind == LRPCAP_DECODER_ADAPTIVE || w->kind == LRPCAP_DECODER_GRIDTD, kErrInvalidArg,
@@ -183,6 +217,16 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
     d->owned_.push_back(p);
     d->WifTC_ = p;
     d->tc_features_ = true;
+  }
+  {
+    const char* v = getenv("LRPCAP_DECODER_TC_FWD");
+    const bool want = v ? (v[0] != '0') : true;   // LRPCAP_DECODER_TC_FWD=0: all forward GEMMs in fp64
+    if (want && H % 64 == 0 && d->Kin1_ % 64 == 0 && (w->kind == LRPCAP_DECODER_ADAPTIVE || d->Kin2_ % 64 == 0)) {
+      UP(d->split3_weights(d->Wcat1T_, 4 * H, d->Kin1_, &d->G4pad_, &d->Wcat1TC3_));
+      if (w->kind == LRPCAP_DECODER_GRIDTD) UP(d->split3_weights(d->Wcat2T_, 4 * H, d->Kin2_, &d->G4pad_, &d->Wcat2TC3_));
+      UP(d->split3_weights(d->WoT_, V, H, &d->Vpad_, &d->WoTC3_));
+      d->tc_forward_ = true;
+    }
   }
 #undef UP
   *out = d;
@@ -279,7 +323,8 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
     build_xh_kernel<<<N, 256, 0, s>>>(XH1_.as<double>(), Emb_, gp_.as<double>(), h1_.as<double>(),
                                       td ? h2_.as<double>() : nullptr, tok, i, T, H, E, sos_, td ? 1 : 0);
     const double* xh = XH1_.as<double>() + (size_t)i * Kin1_;
-    LRPCAP_TRY(gemm(xh, T * Kin1_, Wcat1_, 4 * H, Z_.as<double>(), 4 * H, N, 4 * H, Kin1_, b1_, s));
+    if (tc_forward_) LRPCAP_TRY(gemm_tc3(xh, T * Kin1_, N, Kin1_, Wcat1TC3_, G4pad_, 4 * H, b1_, Z_.as<double>(), 4 * H, s));
+    else LRPCAP_TRY(gemm(xh, T * Kin1_, Wcat1_, 4 * H, Z_.as<double>(), 4 * H, N, 4 * H, Kin1_, b1_, s));
     lstm_point_kernel<<<N, 256, 0, s>>>(Z_.as<double>(), h1_.as<double>(), c1_.as<double>(), zg1_.as<double>(),
                                         ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(), i, T, H);
     const double* h_new = h1_.as<double>() + (size_t)(i + 1) * H;
@@ -295,15 +340,20 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
     launches_ += 6;
     if (td) {
       build_xh2_kernel<<<N, 256, 0, s>>>(XH2_.as<double>(), chat_.as<double>(), h1_.as<double>(), h2_.as<double>(), i, T, H);
-      LRPCAP_TRY(gemm(XH2_.as<double>() + (size_t)i * Kin2_, T * Kin2_, Wcat2_, 4 * H, Z_.as<double>(), 4 * H, N, 4 * H,
-                      Kin2_, b2_, s));
+      if (tc_forward_)
+        LRPCAP_TRY(gemm_tc3(XH2_.as<double>() + (size_t)i * Kin2_, T * Kin2_, N, Kin2_, Wcat2TC3_, G4pad_, 4 * H, b2_,
+                            Z_.as<double>(), 4 * H, s));
+      else
+        LRPCAP_TRY(gemm(XH2_.as<double>() + (size_t)i * Kin2_, T * Kin2_, Wcat2_, 4 * H, Z_.as<double>(), 4 * H, N, 4 * H,
+                        Kin2_, b2_, s));
       lstm_point_kernel<<<N, 256, 0, s>>>(Z_.as<double>(), h2_.as<double>(), c2_.as<double>(), zg2_.as<double>(),
                                           ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(), i, T, H);
       gridtd_hc_kernel<<<N, 256, 0, s>>>(h2_.as<double>(), chat_.as<double>(), hc_.as<double>(), i, T, H, keras_logits_);
       launches_ += 3;
     }
     if (greedy) {
-      LRPCAP_TRY(gemm(hc_.as<double>(), H, Wo_, V, logits_.as<double>(), V, N, V, H, bo_, s));
+      if (tc_forward_) LRPCAP_TRY(gemm_tc3(hc_.as<double>(), H, N, H, WoTC3_, Vpad_, V, bo_, logits_.as<double>(), V, s));
+      else LRPCAP_TRY(gemm(hc_.as<double>(), H, Wo_, V, logits_.as<double>(), V, N, V, H, bo_, s));
       argmax_kernel<<<N, 256, 0, s>>>(logits_.as<double>(), V, eos_token >= 1 ? eos_token - 1 : -1, tok,
                                       logitk_.as<double>(), i, T);
     } else {

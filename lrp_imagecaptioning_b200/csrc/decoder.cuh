@@ -51,6 +51,11 @@ class Decoder {
   int features_gemm(int m, cudaStream_t s);
   // C[M,N] (fp64) = A[M,K] (fp64) * B^T with B given as split-bf16 [N][K]: tcgen05 path for the per-step relevance GEMMs
   int gemm_tc(const double* A, int M, int K, const void* Bsplit, int N, double* C, cudaStream_t s);
+  // forward GEMMs on tensor cores with fp32-exact operands (three bf16 planes, accumulator promoted every k-step):
+  // C[M, N] = A[M, K] (row stride lda) * B^T (+ bias), B3 = planes of B^T [Npad, K] from split3_weights()
+  int gemm_tc3(const double* A, int lda, int M, int K, const void* B3, int Npad, int N, const double* bias, double* C,
+               int ldc, cudaStream_t s);
+  int split3_weights(const double* d_Wt, int N, int K, int* Npad, void** out);
   int upload_split(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, void** out);   // YF_[m*L, D] = UV_[m*L, H] * W_if^T (tensor cores when shapes allow)
   int sort_words(const int* h_word_img, const int* h_word_t, int n_words, cudaStream_t s);
 
@@ -58,6 +63,10 @@ class Decoder {
   int Kin1_ = 0, Kin2_ = 0;   // LSTM input widths incl. recurrent part (adaptive: Kin1 = 2E+H)
   long long launches_ = 0;
   bool tc_features_ = false;
+  bool tc_forward_ = false;                       // gate / logit GEMMs of the forward on tensor cores (gemm_tc3)
+  void *Wcat1TC3_ = nullptr, *Wcat2TC3_ = nullptr, *WoTC3_ = nullptr;
+  int Vpad_ = 0, G4pad_ = 0;
+  DevBuf As3_;
   void *Wgate1TC_ = nullptr, *Wgate2TC_ = nullptr;   // split-bf16 [Kin][H]: g-gate slices as K-major B operands
   DevBuf As_, C32_;
   void* WifTC_ = nullptr;   // split-bf16 [D][H]: K-major B operand of the image_features relevance GEMM

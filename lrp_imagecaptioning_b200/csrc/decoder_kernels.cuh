@@ -125,6 +125,29 @@ __global__ void f64_to_split_strided_kernel(const double* __restrict__ in, __nv_
   hi[i] = h;
   lo[i] = l;
 }
+// rows of a strided fp64 matrix -> three bf16 planes [Mpad, K] (rows >= M zero): fp32-exact GEMM operand
+__global__ void f64_rows_to_split3_kernel(const double* __restrict__ A, int lda, int M, int K, int Mpad,
+                                          __nv_bfloat16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)Mpad * K;
+  if (i >= n) return;
+  const int m = (int)(i / K), k = (int)(i - (size_t)m * K);
+  float v = m < M ? (float)A[(size_t)m * lda + k] : 0.f;
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[(size_t)p * n + i] = h;
+    v -= __bfloat162float(h);
+  }
+}
+// C[m, n] = (double)C32[m, n] (+ bias[n]) for the un-padded part of a tensor-core result
+__global__ void f32_to_f64_bias_kernel(const float* __restrict__ C32, int ld32, double* __restrict__ C, int ldc, int M,
+                                       int N, const double* __restrict__ bias) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * N) return;
+  const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+  C[(size_t)m * ldc + n] = (double)C32[(size_t)m * ld32 + n] + (bias ? bias[n] : 0.0);
+}
 __global__ void round_f32_kernel(double* x, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = f32r(x[i]);

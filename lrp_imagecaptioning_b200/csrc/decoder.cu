@@ -193,7 +193,10 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
   if (H % 64 == 0 && E % 64 == 0 && !getenv("LRPCAP_DECODER_FP64_GEMM")) {
     if (w->kind == LRPCAP_DECODER_ADAPTIVE) {
       UP(d->upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, &d->Wgate1TC_));
+      UP(d->upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, &d->WcatB1TC_));
     } else {
+      UP(d->upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, &d->WcatB1TC_));
+      UP(d->upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, &d->WcatB2TC_));
       UP(d->upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, &d->Wgate1TC_));
       UP(d->upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, &d->Wgate2TC_));
     }
@@ -617,20 +620,23 @@ int Decoder::backward(const int* h_word_img, const int* h_word_t, int W, float* 
     if (!td) {
       grad_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(),
                                           c1_.as<double>(), Rh1_.as<double>(), nullptr, Rc1_.as<double>(), U_.as<double>(), T, H);
-      LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, 4 * H, nullptr, s));
+      if (WcatB1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, 4 * H, WcatB1TC_, Kin1_, Y_.as<double>(), s));
+      else LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, 4 * H, nullptr, s));
       grad_scatter_adaptive_kernel<<<na, 256, 0, s>>>(i, Y_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
                                                       rword_.as<double>(), T, H, E);
       launches_ += 2;
     } else {
       grad_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(),
                                           c2_.as<double>(), Rh2_.as<double>(), nullptr, Rc2_.as<double>(), U_.as<double>(), T, H);
-      LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, 4 * H, nullptr, s));
+      if (WcatB2TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, 4 * H, WcatB2TC_, Kin2_, Y_.as<double>(), s));
+      else LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, 4 * H, nullptr, s));
       grad_scatter_lang_kernel<<<na, 256, 0, s>>>(wr, i, Y_.as<double>(), beta_.as<double>(), Rchat_.as<double>(),
                                                   Rctx_.as<double>(), Rh2_.as<double>(), Q_.as<double>(), T, H);
       grad_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(),
                                           c1_.as<double>(), Rh1_.as<double>(), Rctx_.as<double>(), Rc1_.as<double>(),
                                           U_.as<double>(), T, H);
-      LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, 4 * H, nullptr, s));
+      if (WcatB1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, 4 * H, WcatB1TC_, Kin1_, Y_.as<double>(), s));
+      else LRPCAP_TRY(gemm(U_.as<double>(), 4 * H, Wcat1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, 4 * H, nullptr, s));
       grad_scatter_td_kernel<<<na, 256, 0, s>>>(i, Y_.as<double>(), Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
                                                 rword_.as<double>(), T, H, E);
       launches_ += 4;

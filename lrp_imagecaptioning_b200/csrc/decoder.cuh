@@ -64,6 +64,7 @@ class Decoder {
   long long launches_ = 0;
   bool tc_features_ = false;
   bool tc_forward_ = false;                       // gate / logit GEMMs of the forward on tensor cores (gemm_tc3)
+  void *WcatB1TC_ = nullptr, *WcatB2TC_ = nullptr;   // [Kin, 4H] split-bf16: B operand of the gradient decoder's GEMMs
   void *Wcat1TC3_ = nullptr, *Wcat2TC3_ = nullptr, *WoTC3_ = nullptr;
   int Vpad_ = 0, G4pad_ = 0;
   DevBuf As3_;

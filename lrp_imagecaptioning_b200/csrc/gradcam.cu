@@ -2,7 +2,7 @@
 //   weights = mean_{xy} grads ; cam = sum_k weights_k F_k ; pyramid_expand(cam, upscale, sigma) ; relu ; / (max|cam| + 1e-6)
 // skimage.transform.pyramid_expand (un-vendored, version unpinned -> parity unpinned) is restated as
 // order-1 resize with skimage 'reflect' boundary (= scipy.ndimage 'mirror') followed by scipy.ndimage.gaussian_filter
-// (mode 'reflect', truncate 4).  All HBM-bound: one block per word (and row), shared-memory staging, separable blur.
+// (mode 'reflect', truncate 4).  Both steps are linear and separable, so they are folded into one [hw, fh] matrix.
 #include "../../include/lrpcap.h"
 #include "common.cuh"
 #include <cmath>
@@ -34,78 +34,82 @@ cam_kernel(const float* __restrict__ F, const int* __restrict__ img_index, const
   }
 }
 
-__device__ __forceinline__ int mirror(int i, int n) {   // d c b | a b c d | c b a
+// pyramid_expand is linear and separable: out = A cam A^T with A [hw, fh] = (Gaussian, 'reflect') o (order-1 resize,
+// 'mirror'), built once per call on the host in double precision (build_expand_matrix below).  One block per word:
+// T = A cam (hw x fh, shared memory), out = relu(T A^T), block-wide max, scale by 1 / (max + 1e-6).
+__global__ void __launch_bounds__(256)
+expand_kernel(const float* __restrict__ cam, const float* __restrict__ A, float* __restrict__ out, int fh, int hw) {
+  extern __shared__ float sm[];
+  float* As = sm;                    // [hw][fh]
+  float* Ts = sm + hw * fh;          // [hw][fh]
+  float* cs = Ts + hw * fh;          // [fh][fh]
+  __shared__ float red[256];
+  const int w = blockIdx.x;
+  for (int i = threadIdx.x; i < hw * fh; i += 256) As[i] = A[i];
+  for (int i = threadIdx.x; i < fh * fh; i += 256) cs[i] = cam[(size_t)w * fh * fh + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < hw * fh; i += 256) {
+    const int y = i / fh, j = i - y * fh;
+    float s = 0.f;
+    for (int k = 0; k < fh; ++k) s = fmaf(As[y * fh + k], cs[k * fh + j], s);
+    Ts[i] = s;
+  }
+  __syncthreads();
+  float* o = out + (size_t)w * hw * hw;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < hw * hw; i += 256) {
+    const int y = i / hw, x = i - y * hw;
+    float s = 0.f;
+    for (int j = 0; j < fh; ++j) s = fmaf(Ts[y * fh + j], As[x * fh + j], s);
+    s = fmaxf(s, 0.f);
+    o[i] = s;
+    m = fmaxf(m, s);
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + st]);
+    __syncthreads();
+  }
+  const float inv = 1.f / (red[0] + 1e-6f);
+  for (int i = threadIdx.x; i < hw * hw; i += 256) o[i] *= inv;   // each thread rescales what it wrote
+}
+
+inline int mirror_h(int i, int n) {   // d c b | a b c d | c b a   (skimage 'reflect' = ndimage 'mirror')
   if (n == 1) return 0;
   const int p = 2 * (n - 1);
   i = ((i % p) + p) % p;
   return i < n ? i : p - i;
 }
-__device__ __forceinline__ int reflect(int i, int n) {  // d c b a | a b c d | d c b a
+inline int reflect_h(int i, int n) {  // d c b a | a b c d | d c b a   (ndimage 'reflect')
   const int p = 2 * n;
   i = ((i % p) + p) % p;
   return i < n ? i : p - 1 - i;
 }
 
-// one block per (word, output row): bilinear resize of that row, then horizontal Gaussian
-__global__ void __launch_bounds__(256)
-resize_blurx_kernel(const float* __restrict__ cam, float* __restrict__ tmp, const float* __restrict__ gw, int fh, int hw,
-                    int up, int radius) {
-  extern __shared__ float row[];
-  const int w = blockIdx.y, y = blockIdx.x;
-  const float* c = cam + (size_t)w * fh * fh;
-  const float iy = (y + 0.5f) / up - 0.5f;
-  const int y0 = (int)floorf(iy);
-  const float ty = iy - y0;
-  const int ya = mirror(y0, fh), yb = mirror(y0 + 1, fh);
-  for (int x = threadIdx.x; x < hw; x += 256) {
-    const float ix = (x + 0.5f) / up - 0.5f;
-    const int x0 = (int)floorf(ix);
-    const float tx = ix - x0;
-    const int xa = mirror(x0, fh), xb = mirror(x0 + 1, fh);
-    const float top = c[ya * fh + xa] * (1.f - tx) + c[ya * fh + xb] * tx;
-    const float bot = c[yb * fh + xa] * (1.f - tx) + c[yb * fh + xb] * tx;
-    row[x] = top * (1.f - ty) + bot * ty;
+// A[x, j]: weight of source sample j in output sample x of  gaussian_filter1d(resize1d(.))
+std::vector<float> build_expand_matrix(int fh, int up, float sigma) {
+  const int hw = fh * up, radius = (int)(4.0f * sigma + 0.5f);
+  std::vector<double> gw(2 * radius + 1);
+  double sum = 0.0;
+  for (int k = -radius; k <= radius; ++k) sum += (gw[k + radius] = std::exp(-0.5 * k * k / ((double)sigma * sigma)));
+  for (double& v : gw) v /= sum;
+  std::vector<double> R((size_t)hw * fh, 0.0);
+  for (int x = 0; x < hw; ++x) {
+    const double ix = (x + 0.5) / up - 0.5;
+    const int x0 = (int)std::floor(ix);
+    const double t = ix - x0;
+    R[(size_t)x * fh + mirror_h(x0, fh)] += 1.0 - t;
+    R[(size_t)x * fh + mirror_h(x0 + 1, fh)] += t;
   }
-  __syncthreads();
-  for (int x = threadIdx.x; x < hw; x += 256) {
-    float s = 0.f;
-    for (int k = -radius; k <= radius; ++k) s = fmaf(gw[k + radius], row[reflect(x + k, hw)], s);
-    tmp[((size_t)w * hw + y) * hw + x] = s;
-  }
-}
-
-// one block per (word, 32-column strip): vertical Gaussian + relu
-__global__ void __launch_bounds__(256)
-blury_kernel(const float* __restrict__ tmp, float* __restrict__ out, const float* __restrict__ gw, int hw, int radius) {
-  extern __shared__ float col[];   // [hw][32]
-  const int w = blockIdx.y, x0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < hw * 32; i += 256) {
-    const int y = i / 32, x = x0 + (i & 31);
-    col[i] = x < hw ? tmp[((size_t)w * hw + y) * hw + x] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < hw * 32; i += 256) {
-    const int y = i / 32, xl = i & 31;
-    if (x0 + xl >= hw) continue;
-    float s = 0.f;
-    for (int k = -radius; k <= radius; ++k) s = fmaf(gw[k + radius], col[reflect(y + k, hw) * 32 + xl], s);
-    out[((size_t)w * hw + y) * hw + x0 + xl] = fmaxf(s, 0.f);
-  }
-}
-
-__global__ void __launch_bounds__(256) normalize_kernel(float* __restrict__ out, int n) {
-  float* o = out + (size_t)blockIdx.x * n;
-  __shared__ float red[256];
-  float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += 256) m = fmaxf(m, fabsf(o[i]));
-  red[threadIdx.x] = m;
-  __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s]);
-    __syncthreads();
-  }
-  const float inv = 1.f / (red[0] + 1e-6f);
-  for (int i = threadIdx.x; i < n; i += 256) o[i] *= inv;
+  std::vector<float> A((size_t)hw * fh);
+  for (int x = 0; x < hw; ++x)
+    for (int j = 0; j < fh; ++j) {
+      double s = 0.0;
+      for (int k = -radius; k <= radius; ++k) s += gw[k + radius] * R[(size_t)reflect_h(x + k, hw) * fh + j];
+      A[(size_t)x * fh + j] = (float)s;
+    }
+  return A;
 }
 
 __global__ void scale_maps_kernel(float* __restrict__ maps, const float* __restrict__ cam, size_t pixels) {
@@ -128,33 +132,28 @@ extern "C" int lrpcap_gradcam(const float* d_features, const int* h_img_index, c
   LRPCAP_REQUIRE(n_words > 0 && fh > 0 && D > 0 && upscale > 0 && sigma > 0.f, kErrShape, "gradcam: bad shape");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int L = fh * fh, hw = fh * upscale;
-  const int radius = (int)(4.0f * sigma + 0.5f);
-  LRPCAP_REQUIRE((size_t)hw * 32 * sizeof(float) <= 48 * 1024 && (size_t)D * sizeof(float) <= 48 * 1024, kErrShape,
+  const size_t smem = ((size_t)2 * hw * fh + (size_t)fh * fh) * sizeof(float);
+  LRPCAP_REQUIRE(smem <= 200 * 1024 && (size_t)D * sizeof(float) <= 48 * 1024, kErrShape,
                  "gradcam: map too large for the staging buffers");
-  std::vector<float> gw(2 * radius + 1);
-  double sum = 0.0;
-  for (int k = -radius; k <= radius; ++k) sum += (gw[k + radius] = (float)std::exp(-0.5 * k * k / ((double)sigma * sigma)));
-  for (float& v : gw) v = (float)(v / sum);
+  const std::vector<float> A = build_expand_matrix(fh, upscale, sigma);
   int* d_idx = nullptr;
-  float *d_gw = nullptr, *d_small = nullptr, *d_tmp = nullptr;
+  float *d_A = nullptr, *d_small = nullptr;
   int st = kOk;
   auto run = [&]() -> int {
     LRPCAP_CUDA(cudaMalloc(&d_idx, (size_t)n_words * sizeof(int)));
-    LRPCAP_CUDA(cudaMalloc(&d_gw, gw.size() * sizeof(float)));
+    LRPCAP_CUDA(cudaMalloc(&d_A, A.size() * sizeof(float)));
     LRPCAP_CUDA(cudaMalloc(&d_small, (size_t)n_words * L * sizeof(float)));
-    LRPCAP_CUDA(cudaMalloc(&d_tmp, (size_t)n_words * hw * hw * sizeof(float)));
     LRPCAP_CUDA(cudaMemcpyAsync(d_idx, h_img_index, (size_t)n_words * sizeof(int), cudaMemcpyHostToDevice, s));
-    LRPCAP_CUDA(cudaMemcpyAsync(d_gw, gw.data(), gw.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    LRPCAP_CUDA(cudaMemcpyAsync(d_A, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     cam_kernel<<<n_words, 256, D * sizeof(float), s>>>(d_features, d_idx, d_grads, d_small, L, D);
-    resize_blurx_kernel<<<dim3(hw, n_words), 256, hw * sizeof(float), s>>>(d_small, d_tmp, d_gw, fh, hw, upscale, radius);
-    blury_kernel<<<dim3((hw + 31) / 32, n_words), 256, (size_t)hw * 32 * sizeof(float), s>>>(d_tmp, d_cam, d_gw, hw, radius);
-    normalize_kernel<<<n_words, 256, 0, s>>>(d_cam, hw * hw);
+    LRPCAP_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    expand_kernel<<<n_words, 256, smem, s>>>(d_small, d_A, d_cam, fh, hw);
     LRPCAP_CUDA(cudaGetLastError());
     LRPCAP_CUDA(cudaStreamSynchronize(s));
     return kOk;
   };
   st = run();
-  cudaFree(d_idx); cudaFree(d_gw); cudaFree(d_small); cudaFree(d_tmp);
+  cudaFree(d_idx); cudaFree(d_A); cudaFree(d_small);
   return st;
 }
 

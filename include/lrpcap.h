@@ -57,6 +57,10 @@ int lrpcap_version(void);
  * block1_conv1 .. block5_conv3.  image_hw: 224 (any multiple of 16 is accepted). */
 int lrpcap_encoder_create(lrpcap_encoder_t** out, const float* const* h_kernels_hwio, const float* const* h_biases,
                           int image_hw, int precision);
+/* Replaces the weights of an existing handle in place (same layouts as lrpcap_encoder_create) and invalidates the
+ * per-image state: what `LRPInferenceLayer*` needs between fine-tuning steps (train.py:569-577), where the reference
+ * explains the model that is being trained; the large state and message buffers are kept. Synchronises the device. */
+int lrpcap_encoder_set_weights(lrpcap_encoder_t* enc, const float* const* h_kernels_hwio, const float* const* h_biases);
 int lrpcap_encoder_destroy(lrpcap_encoder_t* enc);
 
 /* Replaces `_image_model.predict(img)` (explainers.py:375, 1097) and the forward half of

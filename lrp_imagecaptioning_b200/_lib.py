@@ -40,6 +40,7 @@ PROTOTYPES = {
     "lrpcap_last_error": (ctypes.c_char_p, []),
     "lrpcap_version": (ctypes.c_int, []),
     "lrpcap_encoder_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), ctypes.c_int, ctypes.c_int]),
+    "lrpcap_encoder_set_weights": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p)]),
     "lrpcap_encoder_destroy": (ctypes.c_int, [c_void_p]),
     "lrpcap_encoder_forward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_void_p]),
     "lrpcap_encoder_features": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),

@@ -33,6 +33,11 @@ int lrpcap_encoder_create(lrpcap_encoder_t** out, const float* const* h_kernels_
   return kOk;
 }
 
+int lrpcap_encoder_set_weights(lrpcap_encoder_t* enc, const float* const* h_kernels_hwio, const float* const* h_biases) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_set_weights: null handle");
+  return enc->impl->set_weights(h_kernels_hwio, h_biases);
+}
+
 int lrpcap_encoder_destroy(lrpcap_encoder_t* enc) {
   if (!enc) return kOk;
   delete enc->impl;

@@ -95,6 +95,29 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
   return kOk;
 }
 
+int Encoder::set_weights(const float* const* kernels_hwio, const float* const* biases) {
+  LRPCAP_REQUIRE(kernels_hwio && biases, kErrInvalidArg, "encoder_set_weights: null argument");
+  for (int l = 0; l < kLayers; ++l)
+    LRPCAP_REQUIRE(kernels_hwio[l] && biases[l], kErrInvalidArg, "encoder_set_weights: layer %d weights missing", l);
+  LRPCAP_CUDA(cudaDeviceSynchronize());   // nothing may still read the old layouts
+  for (int l = 0; l < kLayers; ++l) {
+    Layer& L = L_[l];
+    LRPCAP_CUDA(cudaMemcpy(L.w_hwio, kernels_hwio[l], (size_t)9 * L.cin * L.cout * sizeof(float), cudaMemcpyHostToDevice));
+    LRPCAP_CUDA(cudaMemcpy(L.bias, biases[l], L.cout * sizeof(float), cudaMemcpyHostToDevice));
+    for (auto& f : L.prepared)
+      for (auto& p : f)
+        if (p) { cudaFree(p); p = nullptr; }
+    for (auto& p : L.dual)
+      if (p) { cudaFree(p); p = nullptr; }
+  }
+  float** small[] = {&w0_pm_, &w0_mp_, &w0_last_a_, &w0_last_b_};
+  for (float** p : small)
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  w0_host_.assign(kernels_hwio[0], kernels_hwio[0] + 9 * 3 * 64);
+  n_images_ = 0;
+  return kOk;
+}
+
 int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
   Layer& L = L_[l];
   if (!L.prepared[fmt][sign]) {

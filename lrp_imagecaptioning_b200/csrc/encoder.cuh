@@ -49,6 +49,9 @@ class Encoder {
   ~Encoder();
   static int create(Encoder** out, const float* const* kernels_hwio, const float* const* biases, int image_hw,
                     int precision);
+  // Replaces the 13 kernels / biases in place (fine-tuning: the explained model changes every step); keeps every large
+  // state / message buffer, drops the prepared weight layouts and the per-image state.
+  int set_weights(const float* const* kernels_hwio, const float* const* biases);
   // images: device fp32 [n, hw, hw, 3] (already preprocessed). Builds features + per-image rule state.
   int forward(const float* d_images, int n_images, const EncoderRule& rule, cudaStream_t s);
   const float* features() const { return F_.as<float>(); }   // device fp32 [n, hw/16, hw/16, 512]

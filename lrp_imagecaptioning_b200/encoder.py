@@ -61,6 +61,18 @@ class ImageModel(object):
             self._h = h
         return self._h
 
+    def set_weights(self, weights):
+        """Replace the 13 (kernel, bias) pairs in place (keeps the handle's large buffers; the forward state is dropped)."""
+        weights = [(np.ascontiguousarray(k, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)) for k, b in weights]
+        if len(weights) != 13 or any(k.shape != k0.shape or b.shape != b0.shape for (k, b), (k0, b0) in zip(weights, self.weights)):
+            raise ValueError("set_weights needs 13 (kernel, bias) pairs with the shapes the model was built with")
+        self.weights = weights
+        self._state = None
+        if self._h is not None:
+            ks = (_lib.c_float_p * 13)(*[_lib.fptr(k) for k, _ in self.weights])
+            bs = (_lib.c_float_p * 13)(*[_lib.fptr(b) for _, b in self.weights])
+            _lib.check(_lib.load().lrpcap_encoder_set_weights(self._h, ks, bs))
+
     def close(self):
         if self._h is not None:
             _lib.load().lrpcap_encoder_destroy(self._h)

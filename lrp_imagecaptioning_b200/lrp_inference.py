@@ -138,6 +138,16 @@ class CaptionerTorch(torch.nn.Module):
             dec[k] = p.detach().cpu().numpy()
         return CaptioningModel(model.kind, vgg, dec, image_hw=model.image_hw, precision=model.precision, device=model.device)
 
+    def export_into(self, model):
+        """Writes the current parameters into `model` in place: the encoder handle keeps its buffers
+        (lrpcap_encoder_set_weights); decoder engines built from `model.dec` afterwards see the new weights."""
+        vgg = [(w.detach().permute(2, 3, 1, 0).contiguous().cpu().numpy(), b.detach().cpu().numpy()) for w, b in zip(self.conv_w, self.conv_b)]
+        for k, p in self.dec.items():
+            model.dec[k] = p.detach().cpu().numpy()
+        model.vgg = vgg
+        model.image_model.set_weights(vgg)
+        return model
+
     def features(self, images_nhwc):
         x = images_nhwc.permute(0, 3, 1, 2)
         for l, (w, b) in enumerate(zip(self.conv_w, self.conv_b)):
@@ -248,6 +258,5 @@ class LRPInferenceTrainer(object):
                 off += p.numel()
         torch.nn.utils.clip_grad_value_(self.net.parameters(), self.clipvalue)
         self.opt.step()
-        self.model.image_model.close()
-        self.model = self.net.export(self.model)    # the next step explains with the updated weights
+        self.net.export_into(self.model)            # the next step explains with the updated weights
         return float(loss.item())

@@ -1,0 +1,60 @@
+"""Timing of the LRP-inference fine-tune step (BASELINE.json configs[4]; reference train.py:569-577): predict, explain
+every predicted non-stop word down to pixels, weight the logits, one Adam step.  One rank per GPU (torchrun) with the
+gradient all-reduce over NCCL, or a single process.  Writes gpurun_out/bench_finetune.json on rank 0.
+Usage: python tools/bench_finetune.py [--batch 64] [--steps 3] [--kind adaptive]"""
+import argparse, json, os, sys, time
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lrp_imagecaptioning_b200 import synth
+from lrp_imagecaptioning_b200.model import CaptioningModel
+from lrp_imagecaptioning_b200.lrp_inference import LRPInferenceTrainer
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--kind", default="adaptive")
+ap.add_argument("--vocab", type=int, default=10000)
+args = ap.parse_args()
+world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(lr)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+T, HW = 20, 224
+
+
+class _Pre(object):
+    SOS_TOKEN_LABEL_ENCODED, EOS_TOKEN_LABEL_ENCODED = 1, 2
+    _word_of = {}
+
+
+class _Provider(object):
+    caption_preprocessor = _Pre()
+
+
+model = CaptioningModel.synthetic(args.kind, vocab_size=args.vocab, image_hw=HW, seed=0, device="cuda:%d" % lr)
+tr = LRPInferenceTrainer(model, _Provider(), "mean", learning_rate=1e-5, stop_words=set())
+g = np.random.default_rng(rank)
+imgs = synth.images(args.batch, HW, 50 + rank)
+cap = g.integers(3, args.vocab - 1, size=(args.batch, T))
+tok_in = np.concatenate([np.ones((args.batch, 1), int), cap[:, :-1]], axis=1)
+y = np.zeros((args.batch, T, args.vocab), dtype=np.float32)
+np.put_along_axis(y, (cap - 1)[..., None], 1.0, axis=-1)
+tr.step(tok_in, imgs, y)              # warm-up
+torch.cuda.synchronize()
+t0 = time.time(); words = 0
+for _ in range(args.steps):
+    loss = tr.step(tok_in, imgs, y)
+    words += tr.explained_words
+torch.cuda.synchronize()
+dt = (time.time() - t0) / args.steps
+if rank == 0:
+    out = {"kind": args.kind, "batch_per_gpu": args.batch, "gpus": world, "vocab": args.vocab, "s_per_step": dt,
+           "steps_per_s": 1.0 / dt, "explained_words_per_step_per_gpu": words / args.steps,
+           "explained_words_per_s_all_gpus": world * words / args.steps / dt, "loss": loss}
+    print(json.dumps(out))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/bench_finetune.json", "w"), indent=1)
+if world > 1:
+    dist.destroy_process_group()

@@ -209,3 +209,31 @@ def test_bf16x3_tracks_fp32_mode_224():
     for w in range(n):
         record("bf16x3 vs fp32 presetA 224 image %d" % w, b[w], a[w])
     assert np.median(l2) <= 1e-3 and max(li) <= FLIP_TOL, (li, l2)
+
+
+def test_set_weights_in_place_equals_fresh_handle():
+    """lrpcap_encoder_set_weights: the handle explains the new model exactly like a handle created with it."""
+    import torch
+    from lrp_imagecaptioning_b200 import synth, _lib
+    from lrp_imagecaptioning_b200.encoder import ImageModel, RuleSpec
+    hw = 32
+    wa, wb = synth.vgg16_weights(0), synth.vgg16_weights(7)
+    x = synth.images(2, hw, 3)
+    rule = RuleSpec(_lib.RULE_ALPHA_BETA, alpha=1, beta=0, bias=True)
+    idx = np.array([0, 1, 1], dtype=np.int32)
+    m = ImageModel(wa, image_hw=hw, precision="bf16x3")
+    m.forward(x, rule)
+    R = torch.randn(3, hw // 16, hw // 16, 512, device="cuda")
+    before = m.relevance(idx, R).cpu().numpy()
+    m.set_weights(wb)
+    with pytest.raises(_lib.LrpcapError):
+        m.relevance(idx, R)                 # the per-image state was dropped with the old weights
+    m.forward(x, rule)
+    got = m.relevance(idx, R).cpu().numpy()
+    fresh = ImageModel(wb, image_hw=hw, precision="bf16x3")
+    fresh.forward(x, rule)
+    ref = fresh.relevance(idx, R).cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert not np.array_equal(got, before)
+    with pytest.raises(ValueError):
+        m.set_weights(wb[:5])

@@ -237,3 +237,28 @@ def test_set_weights_in_place_equals_fresh_handle():
     assert not np.array_equal(got, before)
     with pytest.raises(ValueError):
         m.set_weights(wb[:5])
+
+
+@pytest.mark.parametrize("rule", ["eps", "presetA", "a2b1", "gradient"])
+def test_linearity_in_head_relevance_224_property(rule):
+    """Size-independent property at the full size: for a fixed image every rule is linear in the head relevance (the
+    per-image multipliers and arg-max routes do not depend on it), so maps(a R1 + b R2) = a maps(R1) + b maps(R2) up to
+    the 2^-16 operand rounding of the split-bf16 messages."""
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.encoder import ImageModel
+    from lrp_imagecaptioning_b200.analyzers import create_analyzer
+    _, _, name, kw = RULES[rule]
+    x = synth.images(1, 224, 8)
+    m = ImageModel(_weights(), image_hw=224, precision="bf16x3")
+    an = create_analyzer(name, m, neuron_selection_mode="replace", **kw)
+    g = np.random.default_rng(2)
+    F = m.predict(x)
+    R1 = (F[0] * g.standard_normal(F.shape[1:])).astype(np.float32)
+    R2 = (F[0] * g.standard_normal(F.shape[1:])).astype(np.float32)
+    a, b = 0.75, -1.5
+    R = np.stack([R1, R2, (a * R1 + b * R2).astype(np.float32)])
+    out = an.analyze_batch(x, np.zeros(3, dtype=np.int32), R).cpu().numpy().astype(np.float64)
+    comb = a * out[0] + b * out[1]
+    err = l2_rel(out[2], comb)
+    record("linearity %s 224" % rule, out[2], comb)
+    assert err <= 2e-4, err

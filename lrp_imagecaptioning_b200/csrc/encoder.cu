@@ -49,6 +49,9 @@ Encoder::~Encoder() {
       if (p) cudaFree(p);
   X0_.release(); F_.release(); Mseed_.release(); posneg_.release(); idx_.release();
   for (auto& g : G_) g.release();
+  for (auto& g : Gc_) g.release();
+  for (auto& g : Gc2_) g.release();
+  for (auto& g : Gi_) g.release();
   for (auto& a : act_) a.release();
   for (auto& m : msg_) m.release();
 }
@@ -226,7 +229,13 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
   const size_t img_elems = (size_t)hw_ * hw_ * 3;
   LRPCAP_TRY(X0_.ensure((size_t)n * img_elems * sizeof(float)));
   LRPCAP_CUDA(cudaMemcpyAsync(X0_.p, d_images, (size_t)n * img_elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  for (int l = 0; l < kLayers - 1; ++l) LRPCAP_TRY(G_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
+  for (int l = 0; l < kLayers - 1; ++l) {
+    LRPCAP_TRY(G_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
+    if (L_[l].pool_after) {
+      LRPCAP_TRY(Gc_[l].ensure((size_t)n * layer_out_elems(l) / 4 * sizeof(float)));
+      LRPCAP_TRY(Gi_[l].ensure((size_t)n * layer_out_elems(l) / 64 * sizeof(unsigned)));
+    }
+  }
   LRPCAP_TRY(Mseed_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
   LRPCAP_TRY(F_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
   const int FC = n < kForwardChunk ? n : kForwardChunk;
@@ -236,7 +245,10 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
   const bool ab = rule.kind == RULE_ALPHA_BETA, zpf = rule.kind == RULE_ZPLUS_FAST;
   const bool inh = ab && rule.beta != 0.f;   // inhibitor branch f(W-, W+, x+, x-) (relevance_rule.py:314-320)
   if (inh) {
-    for (int l = 0; l < kLayers - 1; ++l) LRPCAP_TRY(G2_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
+    for (int l = 0; l < kLayers - 1; ++l) {
+      LRPCAP_TRY(G2_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
+      if (L_[l].pool_after) LRPCAP_TRY(Gc2_[l].ensure((size_t)n * layer_out_elems(l) / 4 * sizeof(float)));
+    }
     LRPCAP_TRY(Mseed2_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
     if (dual_alpha_ != rule.alpha || dual_beta_ != rule.beta) {   // cached stacked weights depend on (alpha, beta)
       for (auto& L : L_)
@@ -344,10 +356,13 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
       if (L.pool_after) {
         int bp = 0;
         while (bp == bx || bp == by) ++bp;
-        LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), act_[bp].p, (size_t)m * oe / 4, Gl, m, L.hw, L.hw, L.cout, s));
+        LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), act_[bp].p, (size_t)m * oe / 4, Gl,
+                             Gc_[l].as<float>() + (size_t)i0 * oe / 4, Gi_[l].as<unsigned>() + (size_t)i0 * oe / 64, m, L.hw,
+                             L.hw, L.cout, s));
         ++launches_;
         if (inh) {
-          LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), nullptr, 0, G2_[l].as<float>() + (size_t)i0 * oe, m, L.hw, L.hw, L.cout, s));
+          LRPCAP_TRY(pool_mask(Y, (size_t)m * oe, fwd_planes(), nullptr, 0, G2_[l].as<float>() + (size_t)i0 * oe,
+                               Gc2_[l].as<float>() + (size_t)i0 * oe / 4, nullptr, m, L.hw, L.hw, L.cout, s));
           ++launches_;
         }
         X = act_[bp].p;
@@ -414,11 +429,12 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       EpiParams ep;
       ep.mode = EPI_BWD;
       ep.img_index = idx;
-      ep.Gin = G_[l - 1].as<float>();
       ep.up = L_[l - 1].pool_after ? 2 : 1;
+      ep.Gin = ep.up == 2 ? Gc_[l - 1].as<float>() : G_[l - 1].as<float>();
+      ep.Gidx = ep.up == 2 ? Gi_[l - 1].as<unsigned>() : nullptr;
       ep.relu_acc = guided ? 1 : 0;
       ep.out_msg = msg_[cur ^ 1].p;
-      ep.Gin2 = inh ? G2_[l - 1].as<float>() : nullptr;
+      ep.Gin2 = inh ? (ep.up == 2 ? Gc2_[l - 1].as<float>() : G2_[l - 1].as<float>()) : nullptr;
       ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1) * mul;
       ep.out_planar8 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only, 8 channels at a time
       LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l) * mul, m, ep, s, inh));

@@ -115,6 +115,9 @@ class Encoder {
   float dual_alpha_ = 0.f, dual_beta_ = 0.f;            // (alpha, beta) the cached dual weights were built for
   DevBuf X0_, F_, Mseed_, G_[kLayers - 1];
   DevBuf Mseed2_, G2_[kLayers - 1];   // inhibitor-branch multipliers (beta != 0)
+  // layers followed by a max-pool: compact multipliers (value at the window's arg-max + 2-bit position per channel)
+  // read by the up-sampling epilogue; G_[l] / G2_[l] of those layers are scratch between the conv and pool_mask
+  DevBuf Gc_[kLayers - 1], Gc2_[kLayers - 1], Gi_[kLayers - 1];
   DevBuf act_[3], posneg_, msg_[2], idx_;
 };
 

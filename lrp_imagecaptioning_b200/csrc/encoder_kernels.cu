@@ -77,7 +77,8 @@ __global__ void prep_weights_dual_kernel(const float* __restrict__ w, float* __r
 // ------------------------------------------------------------------ max-pool + arg-max masking
 template <class ST>
 __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems, void* pooled, size_t pooled_elems,
-                                 float* G, int items, int H, int W, int C) {
+                                 const float* __restrict__ G, float* __restrict__ Gc, unsigned char* __restrict__ Gi,
+                                 int items, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
   const size_t total = (size_t)items * Ho * Wo * C4;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,12 +89,9 @@ __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems,
   const int yo = r % Ho;
   const int item = r / Ho;
   float v[4][4];
-  size_t off[4];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    off[p] = (((size_t)item * H + (2 * yo + (p >> 1))) * W + (2 * xo + (p & 1))) * C + c;
-    ST::template load<4>(act, act_elems, off[p], v[p]);
-  }
+  for (int p = 0; p < 4; ++p)
+    ST::template load<4>(act, act_elems, (((size_t)item * H + (2 * yo + (p >> 1))) * W + (2 * xo + (p & 1))) * C + c, v[p]);
   float m[4];
   int am[4];
 #pragma unroll
@@ -105,16 +103,17 @@ __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems,
       if (v[p][i] > m[i]) { m[i] = v[p][i]; am[i] = p; }   // strict '>' keeps the first maximum
   }
   if (pooled) ST::template store<4>(pooled, pooled_elems, (((size_t)item * Ho + yo) * Wo + xo) * C + c, m);
-  if (G) {   // G is stored channel-tiled with the 2x2 sub-pixel as a plane index (epilogue.cuh: g_offset, up = 2)
+  if (G) {
+    // compact multiplier of the pooled layer: the value at the arg-max position (every other entry of the window routes
+    // nothing) + its 2-bit position; layout [item][C/16][Ho][Wo][16] / one byte per 4 channels (epilogue.cuh: g_select)
+    float g[4][4], sel[4];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      float g[4];
-      float* gp = G + g_offset(item, 2 * yo + (p >> 1), 2 * xo + (p & 1), c, H, W, C, 2);
-      load_f32<4>(gp, g);
+    for (int p = 0; p < 4; ++p) load_f32<4>(G + g_offset(item, 2 * yo + (p >> 1), 2 * xo + (p & 1), c, H, W, C, 2), g[p]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) g[i] = (am[i] == p) ? g[i] : 0.f;
-      store_f32<4>(gp, g);
-    }
+    for (int i = 0; i < 4; ++i) sel[i] = am[i] == 0 ? g[0][i] : am[i] == 1 ? g[1][i] : am[i] == 2 ? g[2][i] : g[3][i];
+    const size_t run = (((size_t)item * (C >> 4) + (c >> 4)) * Ho + yo) * Wo + xo;
+    store_f32<4>(Gc + run * 16 + (c & 15), sel);
+    if (Gi) Gi[run * 4 + ((c & 15) >> 2)] = (unsigned char)(am[0] | (am[1] << 2) | (am[2] << 4) | (am[3] << 6));
   }
 }
 
@@ -479,16 +478,18 @@ int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int
   return kOk;
 }
 
-int pool_mask(const void* act, size_t act_elems, int planes, void* pooled, size_t pooled_elems, float* G, int items,
-              int H, int W, int C, cudaStream_t s) {
-  LRPCAP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, kErrShape, "pool_mask: H, W must be even and C %% 4 == 0");
+int pool_mask(const void* act, size_t act_elems, int planes, void* pooled, size_t pooled_elems, const float* G, float* Gc,
+              unsigned* Gidx, int items, int H, int W, int C, cudaStream_t s) {
+  LRPCAP_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 16 == 0, kErrShape, "pool_mask: H, W must be even and C %% 16 == 0");
+  LRPCAP_REQUIRE(!G || Gc, kErrInvalidArg, "pool_mask: a multiplier needs its compact destination");
   const size_t total = (size_t)items * (H / 2) * (W / 2) * (C / 4);
+  unsigned char* gi = reinterpret_cast<unsigned char*>(Gidx);
   if (planes == 3)
-    pool_mask_kernel<StoreSplit3><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, items, H, W, C);
+    pool_mask_kernel<StoreSplit3><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
   else if (planes == 2)
-    pool_mask_kernel<StoreSplit><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, items, H, W, C);
+    pool_mask_kernel<StoreSplit><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
   else
-    pool_mask_kernel<StoreF32><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, items, H, W, C);
+    pool_mask_kernel<StoreF32><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }

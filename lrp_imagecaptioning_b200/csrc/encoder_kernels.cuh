@@ -25,10 +25,12 @@ int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt
                       float scale_b, cudaStream_t s);
 
 // 2x2/2 max-pool of `act` [items,H,W,C] (storage-typed). If `pooled` != null writes [items,H/2,W/2,C];
-// if `G` != null zeroes every G entry that is not the first maximum of its window (TF MaxPoolGrad routing,
-// innvestigate relevance_analyzer.py:459-480).
-int pool_mask(const void* act, size_t act_elems, int planes /*0 = fp32, 2, 3*/, void* pooled, size_t pooled_elems, float* G, int items,
-              int H, int W, int C, cudaStream_t s);
+// if `G` != null (the layer's multiplier in the g_offset layout with up = 2) also writes its compact form: `Gc`
+// [items][C/16][H/2][W/2][16] = the value at the first maximum of each 2x2 window (TF MaxPoolGrad routing,
+// innvestigate relevance_analyzer.py:459-480 -- every other entry routes nothing) and, if given, `Gidx`
+// [items][C/16][H/2][W/2] words with 2 bits per channel = window position (sy * 2 + sx) of that maximum.
+int pool_mask(const void* act, size_t act_elems, int planes /*0 = fp32, 2, 3*/, void* pooled, size_t pooled_elems, const float* G,
+              float* Gc, unsigned* Gidx, int items, int H, int W, int C, cudaStream_t s);
 
 // msg[item] = (relu?)(R[item]) * M[img_index[item]]   ([items, hw, hw, C]); msg storage-typed.
 // M2 != null: dual message with 2*C channels [R*M | R*M2].

@@ -26,6 +26,7 @@ struct EpiDev {
   const int* img_index;
   const float* Gin;
   const float* Gin2;
+  const unsigned* Gidx;
   int up;
   int relu_acc;
   int g_up;           // layout of G written by the forward epilogues (see g_offset)
@@ -228,6 +229,13 @@ __device__ __forceinline__ void epi_store_msg(const EpiDev& e, size_t item_pixel
   }
 }
 
+// Multiplier of sub-pixel `sub` from the compact form: the window's only non-zero sits at the arg-max position.
+template <int UP>
+__device__ __forceinline__ float g_select(float g, unsigned idx, int k, int sub) {
+  if (UP == 1) return g;
+  return ((idx >> (2 * k)) & 3u) == (unsigned)sub ? g : 0.f;
+}
+
 template <int UP, int NV, class ST>
 __device__ __forceinline__ void epi_bwd(const EpiDev& e, int H, int W, int Nout, int item, int y, int x, int n,
                                         const float (&v)[NV]) {
@@ -235,60 +243,48 @@ __device__ __forceinline__ void epi_bwd(const EpiDev& e, int H, int W, int Nout,
   const int WW = W * UP;
   const size_t item_pixels = (size_t)H * UP * WW;
   const int NO = e.Gin2 ? 2 * Nout : Nout;
-  // multiplier run of sub-pixel (sy, sx): see g_offset (H, W here are the accumulator grid = the pooled grid)
-  const size_t gsub = (size_t)H * W * 16;
-  const size_t g0 = ((((size_t)img * (Nout >> 4) + (n >> 4)) * (UP * UP)) * H + y) * W * 16 + (size_t)x * 16 + (n & 15);
-  float gg[UP * UP][NV];
+  // (H, W) is the accumulator grid (= the pooled grid when UP == 2): one 16-channel run per accumulator pixel
+  const size_t goff = (((size_t)img * (Nout >> 4) + (n >> 4)) * H + y) * W + x;
+  const unsigned idx = UP == 2 ? __ldg(e.Gidx + goff) : 0u;
+  for (int pass = 0; pass < (e.Gin2 ? 2 : 1); ++pass) {   // pass 1: inhibitor branch (beta != 0) -> channels [Nout, 2 Nout)
+    float gg[NV];
+    load_f32<NV>((pass ? e.Gin2 : e.Gin) + goff * 16 + (n & 15), gg);
 #pragma unroll
-  for (int sub = 0; sub < UP * UP; ++sub) load_f32<NV>(e.Gin + g0 + sub * gsub, gg[sub]);
-#pragma unroll
-  for (int sy = 0; sy < UP; ++sy)
-#pragma unroll
-    for (int sx = 0; sx < UP; ++sx) {
-      const size_t pix = (size_t)(y * UP + sy) * WW + (x * UP + sx);
+    for (int sub = 0; sub < UP * UP; ++sub) {
+      const size_t pix = (size_t)(y * UP + sub / UP) * WW + (x * UP + sub % UP);
       float o[NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[sy * UP + sx][i];
-      epi_store_msg<NV, ST>(e, item_pixels, item, pix, NO, n, o);
+      for (int i = 0; i < NV; ++i) o[i] = v[i] * g_select<UP>(gg[i], idx, (n & 15) + i, sub);
+      epi_store_msg<NV, ST>(e, item_pixels, item, pix, NO, pass * Nout + n, o);
     }
-  if (e.Gin2) {   // alpha-beta with beta != 0: inhibitor branch -> channels [Nout, 2 Nout)
-#pragma unroll
-    for (int sub = 0; sub < UP * UP; ++sub) load_f32<NV>(e.Gin2 + g0 + sub * gsub, gg[sub]);
-#pragma unroll
-    for (int sy = 0; sy < UP; ++sy)
-#pragma unroll
-      for (int sx = 0; sx < UP; ++sx) {
-        const size_t pix = (size_t)(y * UP + sy) * WW + (x * UP + sx);
-        float o[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) o[i] = v[i] * gg[sy * UP + sx][i];
-        epi_store_msg<NV, ST>(e, item_pixels, item, pix, NO, Nout + n, o);
-      }
   }
 }
 
-// Backward epilogue of one accumulator row (pixel) over NCH 16-channel chunks, software-pipelined: the multiplier run of
-// unit u+1 (unit = chunk x sub-pixel) is loaded while unit u is multiplied and stored, and the image index is read once.
-// Written for the tcgen05 kernels, whose 8 epilogue warps have too little thread-level parallelism to hide a
-// load -> use latency per chunk (ncu: the epilogue, not the tensor pipe, paced the 64-channel layers).
+// Backward epilogue of one accumulator row (pixel) over NCH 16-channel chunks, software-pipelined: the multiplier run
+// (and, for up-sampling layers, the arg-max word) of chunk c+1 is loaded while chunk c is multiplied and stored, and the
+// image index is read once.  Written for the tcgen05 kernels, whose 8 epilogue warps have too little thread-level
+// parallelism to hide a load -> use latency per chunk (ncu: the epilogue, not the tensor pipe, paced the 64-channel layers).
 // load_acc(c, v) must fetch chunk c of the accumulator and is called by every lane (tcgen05.ld is warp-collective);
 // `valid` only guards global-memory traffic. Chunk c covers channels [n_first + c * n_step, +16).
 template <int UP, int NCH, class ST, class AccLoader>
 __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, int Nout, int item, int y, int x,
                                                int n_first, int n_step, bool valid, AccLoader&& load_acc) {
   constexpr int SUBS = UP * UP;
-  constexpr int UNITS = NCH * SUBS;
   const int img = valid ? __ldg(e.img_index + item) : 0;
   const int WW = W * UP;
   const size_t item_pixels = (size_t)H * UP * WW;
   const int NO = e.Gin2 ? 2 * Nout : Nout;
-  const size_t gsub = (size_t)H * W * 16;
-  const size_t gpix = ((size_t)y * W + x) * 16;
-  const size_t gimg = (size_t)img * (Nout >> 4);
+  const size_t gplane = (size_t)H * W;                                   // accumulator pixels per 16-channel run plane
+  const size_t gpix = ((size_t)img * (Nout >> 4)) * gplane + (size_t)y * W + x;
   for (int pass = 0; pass < (e.Gin2 ? 2 : 1); ++pass) {
     const float* G = pass ? e.Gin2 : e.Gin;
     float gg[2][16];
-    if (valid) load_f32<16>(G + ((gimg + (n_first >> 4)) * SUBS) * gsub + gpix, gg[0]);
+    unsigned gi[2] = {0u, 0u};
+    if (valid) {
+      const size_t o0 = gpix + (size_t)(n_first >> 4) * gplane;
+      load_f32<16>(G + o0 * 16, gg[0]);
+      if (UP == 2) gi[0] = __ldg(e.Gidx + o0);
+    }
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       float v[16];
@@ -299,17 +295,17 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       const int n = n_first + c * n_step;
+      if (c + 1 < NCH && valid) {
+        const size_t o1 = gpix + (size_t)((n + n_step) >> 4) * gplane;
+        load_f32<16>(G + o1 * 16, gg[(c + 1) & 1]);
+        if (UP == 2) gi[(c + 1) & 1] = __ldg(e.Gidx + o1);
+      }
+      if (valid) {
 #pragma unroll
-      for (int sub = 0; sub < SUBS; ++sub) {
-        const int u = c * SUBS + sub;
-        if (u + 1 < UNITS && valid) {
-          const int cn = (u + 1) / SUBS, sn = (u + 1) % SUBS;
-          load_f32<16>(G + ((gimg + ((n_first + cn * n_step) >> 4)) * SUBS + sn) * gsub + gpix, gg[(u + 1) & 1]);
-        }
-        if (valid) {
+        for (int sub = 0; sub < SUBS; ++sub) {
           float o[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = v[i] * gg[u & 1][i];
+          for (int i = 0; i < 16; ++i) o[i] = v[i] * g_select<UP>(gg[c & 1][i], gi[c & 1], i, sub);
           const size_t pix = (size_t)(y * UP + sub / UP) * WW + (x * UP + sub % UP);
           epi_store_msg<16, ST>(e, item_pixels, item, pix, NO, pass * Nout + n, o);
         }
@@ -322,13 +318,10 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
 // accumulator, so the DRAM latency of G overlaps the MMAs instead of serialising with every 16-column chunk.
 __device__ __forceinline__ void epi_prefetch_bwd(const EpiDev& e, int H, int W, int Nout, int item, int y, int x, int n) {
   const int img = __ldg(e.img_index + item);
-  const int subs = e.up * e.up;
-  const size_t gsub = (size_t)H * W * 16;
-  const size_t g0 = ((((size_t)img * (Nout >> 4) + (n >> 4)) * subs) * H + y) * W * 16 + (size_t)x * 16;
-  for (int sub = 0; sub < subs; ++sub) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gin + g0 + sub * gsub));
-    if (e.Gin2) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gin2 + g0 + sub * gsub));
-  }
+  const size_t goff = (((size_t)img * (Nout >> 4) + (n >> 4)) * H + y) * W + x;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gin + goff * 16));
+  if (e.Gin2) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gin2 + goff * 16));
+  if (e.Gidx) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.Gidx + goff));
 }
 
 // v: accumulator values for channels [n, n+NV) of output pixel (item, y, x) of an H x W x Nout map.
@@ -406,6 +399,7 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->img_index = p.img_index;
   e->Gin = p.Gin;
   e->Gin2 = p.Gin2;
+  e->Gidx = p.Gidx;
   e->up = p.up;
   e->relu_acc = p.relu_acc;
   e->g_up = p.g_up;
@@ -414,7 +408,7 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->out_elems = 0;
   switch (p.mode) {
     case EPI_BWD:
-      LRPCAP_REQUIRE(p.out_msg && p.Gin && p.img_index && (p.up == 1 || p.up == 2), kErrInvalidArg,
+      LRPCAP_REQUIRE(p.out_msg && p.Gin && p.img_index && (p.up == 1 || (p.up == 2 && p.Gidx)), kErrInvalidArg,
                      "conv: incomplete backward epilogue");
       e->out = p.out_msg;
       e->out_elems = p.out_msg_elems;

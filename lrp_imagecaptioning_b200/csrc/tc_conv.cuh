@@ -40,7 +40,10 @@ struct EpiParams {
   size_t x_act_elems = 0;
   // backward
   const int* img_index = nullptr;   // [items] -> image
-  const float* Gin = nullptr;       // fp32 multiplier of the layer below, [images][Nout/16][up*up][H][W][16] (g_offset)
+  const float* Gin = nullptr;       // fp32 multiplier of the layer below, [images][Nout/16][H][W][16] on the accumulator
+                                    // grid; for up == 2 this is the compact form: the one non-zero of each 2x2 window
+  const unsigned* Gidx = nullptr;   // up == 2: [images][Nout/16][H][W] words, bits [2k, 2k+1] = window position
+                                    // (sy * 2 + sx) of the arg-max of channel 16 j + k
   const float* Gin2 = nullptr;      // alpha-beta with beta != 0: second multiplier (inhibitor branch); the output then has
                                     // 2*Nout channels: [acc*Gin | acc*Gin2]
   int up = 1;

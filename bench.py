@@ -30,7 +30,7 @@ METRIC = "explained words/sec (full LRP to pixels)"
 UNIT = "words/s"
 N_IMG, T_WORDS, VOCAB, HW = 64, 20, 10000, 224
 ENC_GFLOP_PER_WORD = 30.69      # one transposed-conv sweep of VGG16
-NCU_DRAM_MB_PER_WORD = 103.1    # measured: profiles/r01b_ncu_full_bwd_summary.csv (33.0 GB over 320 words)
+NCU_DRAM_MB_PER_WORD = 98.2     # measured: profiles/r01c_ncu_full_bwd_summary.csv (31.4 GB over 320 words)
 
 
 def peaks():
@@ -234,8 +234,8 @@ def run_ours(args, rank, local_rank, world):
     roofline = {"bound": "tensor", "kernel": "tc_conv_kernel / tc_conv_vh_kernel <BN, EPI_BWD> (tcgen05 transposed conv + fused rule epilogue)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": NCU_DRAM_MB_PER_WORD * 1e6 * n_words / max(tc_n / max(args.steps, 1), 1.0),
-                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (profiles/r01b_ncu_full_bwd_summary.csv, "
-                                "320 words: 33.0 GB = %.1f MB/word; algorithmic: 95.1 MB/word of messages + the per-image multipliers), "
+                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (profiles/r01c_ncu_full_bwd_summary.csv, "
+                                "320 words: 31.4 GB = %.1f MB/word; algorithmic: 95.1 MB/word of messages + the per-image multipliers), "
                                 "scaled to this run's words per launch" % NCU_DRAM_MB_PER_WORD,
                 "peak_source": "%s bf16 cuBLAS (sustained)" % peak_src,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC of the transposed convs, %.2f GFLOP/word) / CUDA-event "

@@ -144,10 +144,11 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
     EpiParams ep;
     ep.mode = EPI_RAW;
     ep.out_f32 = dO.as<float>();
-    if (precision == PREC_BF16X3_TC || precision == 2) {   // 2: three bf16 planes (the forward pass's arithmetic)
-      const int planes = precision == 2 ? 3 : 2;
-      LRPCAP_TRY(sA.ensure(nA * 2 * planes));
-      LRPCAP_TRY(sB.ensure(nB * 2 * planes));
+    if (precision == PREC_BF16X3_TC || precision == 2 || precision == 3) {
+      // 2: three bf16 planes (the forward pass's arithmetic); 3: two IEEE half planes, promoted (optional forward mode)
+      const int planes = precision == 2 ? 3 : precision == 3 ? kPlanesF16x2 : 2;
+      LRPCAP_TRY(sA.ensure(nA * 2 * 3));
+      LRPCAP_TRY(sB.ensure(nB * 2 * 3));
       LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0, planes));
       LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps, planes));
       TcConvArgs a;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -77,6 +78,18 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t
   hi2 = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
   lo2 = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
 }
+
+// ---- split-fp16 storage (forward activations / weights, optional): v ~= float(hi) + float(lo) with two IEEE half planes,
+//      22 mantissa bits inside the half range (|v| < 65504; lo underflows gradually below |v| ~ 0.1).  Plane code 4. ----
+constexpr int kPlanesF16x2 = 4;
+__device__ __forceinline__ void split2h(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+  const __half al = __float2half_rn(a - __half2float(ah)), bl = __float2half_rn(b - __half2float(bh));
+  hi2 = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+  lo2 = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+}
+__device__ __forceinline__ float f16lo_to_float(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float f16hi_to_float(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 __device__ __forceinline__ float bf16lo_to_float(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_to_float(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }

@@ -35,6 +35,7 @@ Encoder::~Encoder() {
       for (auto& p : f)
         if (p) cudaFree(p);
   }
+  if (d_overflow_) cudaFree(d_overflow_);
   if (copy_stream_) cudaStreamDestroy(copy_stream_);
   if (ev_chunk_) cudaEventDestroy(ev_chunk_);
   if (ev_copied_) cudaEventDestroy(ev_copied_);
@@ -64,8 +65,9 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
   Encoder* e = new Encoder();
   e->hw_ = image_hw;
   e->precision_ = precision;
-  if (const char* v = std::getenv("LRPCAP_FWD_PLANES")) {    // experiment knob: bf16 planes of the forward operands
-    if (std::atoi(v) == 2) e->fwd_planes_ = 2;
+  if (const char* v = std::getenv("LRPCAP_FWD_PLANES")) {    // knob: forward operand storage: 3 bf16 planes (default), 2 bf16
+    const int n = std::atoi(v);                               // planes, or 4 = two IEEE half planes (kPlanesF16x2)
+    if (n == 2 || n == 3 || n == kPlanesF16x2) e->fwd_planes_ = n;
   }
   if (const char* v = std::getenv("LRPCAP_FWD_PROMOTE")) {   // experiment knob: k-steps per accumulator hand-over, forward
     const int n = std::atoi(v);
@@ -93,9 +95,21 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
       return kErrCuda;
     }
   }
+  for (int l = 0; l < kLayers; ++l) e->set_wpow(l, kernels_hwio[l]);
   e->w0_host_.assign(kernels_hwio[0], kernels_hwio[0] + 9 * 3 * 64);
   *out = e;
   return kOk;
+}
+
+// 2^wpow * max|w| in [2^12, 2^13): the high half plane stays far from overflow, the low one (2^-11 of it) normal
+void Encoder::set_wpow(int l, const float* h_w) {
+  Layer& L = L_[l];
+  float m = 0.f;
+  const size_t n = (size_t)9 * L.cin * L.cout;
+  for (size_t i = 0; i < n; ++i) m = std::fmax(m, std::fabs(h_w[i]));
+  int ex = 0;
+  if (m > 0.f && std::isfinite(m)) std::frexp(m, &ex);   // m = f * 2^ex, f in [0.5, 1)
+  L.wpow = 13 - ex;
 }
 
 int Encoder::set_weights(const float* const* kernels_hwio, const float* const* biases) {
@@ -116,6 +130,7 @@ int Encoder::set_weights(const float* const* kernels_hwio, const float* const* b
   float** small[] = {&w0_pm_, &w0_mp_, &w0_last_a_, &w0_last_b_};
   for (float** p : small)
     if (*p) { cudaFree(*p); *p = nullptr; }
+  for (int l = 0; l < kLayers; ++l) set_wpow(l, kernels_hwio[l]);
   w0_host_.assign(kernels_hwio[0], kernels_hwio[0] + 9 * 3 * 64);
   n_images_ = 0;
   return kOk;
@@ -128,6 +143,8 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
     LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * (fmt == WF_TC_FWD3 ? 6 : 4)));
     L.prepared[fmt][sign] = p;
     if (fmt == WF_TC_FWD3) LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, 3));
+    else if (fmt == WF_TC_FWDH)
+      LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, kPlanesF16x2, std::ldexp(1.f, L.wpow)));
     else LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, fmt, sign, s));
     ++launches_;
   }
@@ -158,7 +175,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
   const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
   if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
   if (dual) LRPCAP_TRY(get_dual_weights(l, tc, &B, s));
-  else LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : (fwd_planes_ == 3 ? WF_TC_FWD3 : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  else LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : (fwd_planes_ == 3 ? WF_TC_FWD3 : fwd_planes_ == kPlanesF16x2 ? WF_TC_FWDH : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
   ProfRec rec{};
   if (profile_) {
     LRPCAP_CUDA(cudaEventCreate(&rec.a));
@@ -175,6 +192,10 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     a.planes = backward ? 2 : fwd_planes_;
     a.promote_every = backward ? bwd_promote_ : fwd_promote_;
     a.epi = epi;
+    if (!backward && fwd_planes_ == kPlanesF16x2) {
+      a.epi.acc_scale = std::ldexp(1.f, -L.wpow);
+      a.epi.overflow = d_overflow_;
+    }
     st = tc_conv_launch(a, s);
   } else {
     SimtConvArgs a;
@@ -182,6 +203,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout;
     a.out_planes = split() ? (backward ? 2 : fwd_planes_) : 0;
     a.epi = epi;
+    if (!backward && split() && fwd_planes_ == kPlanesF16x2) a.epi.overflow = d_overflow_;
     st = simt_conv_launch(a, s);
   }
   if (profile_) {
@@ -226,9 +248,14 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
   }
   n_images_ = 0;
   rule_ = rule;
+  if (split() && fwd_planes_ == kPlanesF16x2) {
+    if (!d_overflow_) LRPCAP_CUDA(cudaMalloc(&d_overflow_, sizeof(int)));
+    LRPCAP_CUDA(cudaMemsetAsync(d_overflow_, 0, sizeof(int), s));
+  }
   const size_t img_elems = (size_t)hw_ * hw_ * 3;
   LRPCAP_TRY(X0_.ensure((size_t)n * img_elems * sizeof(float)));
-  LRPCAP_CUDA(cudaMemcpyAsync(X0_.p, d_images, (size_t)n * img_elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (d_images != X0_.p)   // (the half-range fallback below re-enters with the kept copy)
+    LRPCAP_CUDA(cudaMemcpyAsync(X0_.p, d_images, (size_t)n * img_elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
   for (int l = 0; l < kLayers - 1; ++l) {
     LRPCAP_TRY(G_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
     if (L_[l].pool_after) {
@@ -373,6 +400,16 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
         X_elems = (size_t)m * oe;
         bx = by;
       }
+    }
+  }
+  if (split() && fwd_planes_ == kPlanesF16x2) {
+    // an activation outside the half range would turn into inf: fall back to the bf16 planes for this handle, for good
+    int flag = 0;
+    LRPCAP_CUDA(cudaMemcpyAsync(&flag, d_overflow_, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LRPCAP_CUDA(cudaStreamSynchronize(s));
+    if (flag) {
+      fwd_planes_ = 3;
+      return forward(X0_.as<float>(), n, rule, s);
     }
   }
   n_images_ = n;

@@ -90,7 +90,8 @@ class Encoder {
     bool pool_after;
     float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
     float* bias = nullptr;    // device fp32 [cout]
-    void* prepared[5][3] = {};  // [WeightFormat][WeightSign]
+    void* prepared[6][3] = {};  // [WeightFormat][WeightSign]
+    int wpow = 0;             // half-plane forward: weights are stored as 2^wpow * w (keeps the low plane out of the subnormals)
     void* dual[2] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC} backward layouts
   };
   int get_weights(int l, int fmt, int sign, void** out, cudaStream_t s);
@@ -98,13 +99,16 @@ class Encoder {
            cudaStream_t s, bool dual = false);
   int get_dual_weights(int l, bool tc, void** out, cudaStream_t s);
   bool split() const { return precision_ == PREC_BF16X3_TC; }
-  // storage planes of forward activations: 3 bf16 planes (fp32-exact operands) in tensor-core mode, fp32 otherwise.
-  // The per-image forward decides ReLU signs / pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level
-  // errors downstream, while the per-word backward is insensitive to them.
+  // storage planes of forward activations in tensor-core mode (fp32 otherwise). The per-image forward decides ReLU signs
+  // and pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level map errors, so its
+  // operands carry >= 22 bits: two IEEE half planes (default, 3 MMA products; falls back for good when an activation
+  // leaves the half range) or three bf16 planes (6 products, LRPCAP_FWD_PLANES=3).
   int fwd_planes() const { return split() ? fwd_planes_ : 0; }
   size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
 
-  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0, fwd_promote_ = 1, fwd_planes_ = 3;
+  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0, fwd_promote_ = 1, fwd_planes_ = kPlanesF16x2;
+  int* d_overflow_ = nullptr;   // half-plane forward: set by the epilogue when an activation leaves the half range
+  void set_wpow(int l, const float* h_w);
   long long launches_ = 0;
   EncoderRule rule_;
   Layer L_[kLayers];

@@ -16,7 +16,7 @@ inline unsigned grid_for(size_t n, int block) {
 // ------------------------------------------------------------------ weight preparation
 __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out_f32,
                                     __nv_bfloat16* __restrict__ out_hi, int planes, int cin,
-                                    int cout, int fmt, int sign, int taps) {
+                                    int cout, int fmt, int sign, int taps, float scale) {
   const size_t total = (size_t)taps * cin * cout;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -35,6 +35,12 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
   if (sign == WS_MINUS) v = v < 0.f ? v : 0.f;
   if (fmt == WF_SIMT_FWD || fmt == WF_SIMT_BWD) {
     out_f32[idx] = v;
+  } else if (planes == kPlanesF16x2) {   // two half planes of scale * w (scale = 2^k keeps the low plane normal)
+    __half* oh = reinterpret_cast<__half*>(out_hi);
+    v *= scale;
+    const __half h = __float2half_rn(v);
+    oh[idx] = h;
+    oh[total + idx] = __float2half_rn(v - __half2float(h));
   } else {
     for (int p = 0; p < planes; ++p) {
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -442,6 +448,13 @@ __global__ void f32_to_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float v = in[idx];
+  if (planes == kPlanesF16x2) {
+    __half* oh = reinterpret_cast<__half*>(hi);
+    const __half h = __float2half_rn(v);
+    oh[idx] = h;
+    oh[n + idx] = __float2half_rn(v - __half2float(h));
+    return;
+  }
   for (int p = 0; p < planes; ++p) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     hi[(size_t)p * n + idx] = h;
@@ -469,11 +482,11 @@ int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt
 }
 
 int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps,
-                 int planes) {
+                 int planes, float scale) {
   const size_t total = (size_t)taps * cin * cout;
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(out);
   prep_weights_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, reinterpret_cast<float*>(out), hi, planes, cin, cout,
-                                                           fmt, sign, taps);
+                                                           fmt, sign, taps, scale);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -488,6 +501,8 @@ int pool_mask(const void* act, size_t act_elems, int planes, void* pooled, size_
     pool_mask_kernel<StoreSplit3><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
   else if (planes == 2)
     pool_mask_kernel<StoreSplit><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
+  else if (planes == kPlanesF16x2)
+    pool_mask_kernel<StoreSplitH><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
   else
     pool_mask_kernel<StoreF32><<<grid_for(total, 256), 256, 0, s>>>(act, act_elems, pooled, pooled_elems, G, Gc, gi, items, H, W, C);
   LRPCAP_CUDA(cudaGetLastError());

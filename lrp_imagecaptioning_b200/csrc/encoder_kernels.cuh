@@ -9,14 +9,16 @@ enum WeightFormat : int {
   WF_SIMT_BWD = 1,  // fp32 [tap'][cout][cin], tap' = flipped (transposed conv)
   WF_TC_FWD = 2,    // split-bf16 [tap][cout][cin]           (K-major B operand of the forward GEMM)
   WF_TC_BWD = 3,    // split-bf16 [tap'][cin][cout]          (K-major B operand of the dgrad GEMM)
-  WF_TC_FWD3 = 4,   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
+  WF_TC_FWD3 = 4,
+  WF_TC_FWDH = 5,   // as WF_TC_FWD with two IEEE half planes of 2^k * w (Layer::wpow)   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
 };
 enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
 
 // w_hwio: device fp32 [3,3,cin,cout]. out: 9*cin*cout elements in `fmt`.
-// planes: bf16 planes written for the tensor-core formats (2 or 3; ignored for the fp32 formats).
+// planes: bf16 planes written for the tensor-core formats (2 or 3; ignored for the fp32 formats), or kPlanesF16x2:
+// two IEEE half planes of `scale` * w.
 int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign, cudaStream_t s, int taps = 9,
-                 int planes = 2);
+                 int planes = 2, float scale = 1.f);
 
 // Backward weights of the alpha-beta rule with beta != 0, stacked along K (2*cout input channels):
 //   k <  cout : scale_a * sign_a(W)      k >= cout : scale_b * sign_b(W)

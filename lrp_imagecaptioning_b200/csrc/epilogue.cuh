@@ -29,6 +29,8 @@ struct EpiDev {
   const unsigned* Gidx;
   int up;
   int relu_acc;
+  float acc_scale;    // forward: z = acc * acc_scale (+ bias); 2^-k when the weights were pre-scaled by 2^k (half planes)
+  int* overflow;      // forward, half planes: set to 1 when an activation leaves the half range
   int g_up;           // layout of G written by the forward epilogues (see g_offset)
   int out_planar8;    // backward: message written as [items][Nout/8][H][W][8]
 };
@@ -120,6 +122,50 @@ struct StoreSplit {
         v[4 * j + 2] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y);
         v[4 * j + 3] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y);
       }
+    }
+  }
+};
+
+// two IEEE half planes (common.cuh: split2h); same interface and access widths as StoreSplit
+struct StoreSplitH {
+  template <int NV>
+  static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "split storage moves 4, 8 or 16 elements per vector");
+    __half* hi = reinterpret_cast<__half*>(base);
+    __half* lo = hi + elems;
+    if constexpr (NV % 16 == 0) {
+#pragma unroll
+      for (int j = 0; j < NV / 16; ++j) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split2h(v[16 * j + 2 * i], v[16 * j + 2 * i + 1], h[i], l[i]);
+        stg256(hi + off + 16 * j, h);
+        stg256(lo + off + 16 * j, l);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV / 4; ++j) {
+        uint32_t h[2], l[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) split2h(v[4 * j + 2 * i], v[4 * j + 2 * i + 1], h[i], l[i]);
+        reinterpret_cast<uint2*>(hi + off)[j] = make_uint2(h[0], h[1]);
+        reinterpret_cast<uint2*>(lo + off)[j] = make_uint2(l[0], l[1]);
+      }
+    }
+  }
+  template <int NV>
+  static __device__ __forceinline__ void load(const void* base, size_t elems, size_t off, float (&v)[NV]) {
+    static_assert(NV % 4 == 0, "split storage moves 4 elements per vector");
+    const __half* hi = reinterpret_cast<const __half*>(base);
+    const __half* lo = hi + elems;
+#pragma unroll
+    for (int j = 0; j < NV / 4; ++j) {
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(hi + off) + j);
+      const uint2 b = __ldg(reinterpret_cast<const uint2*>(lo + off) + j);
+      v[4 * j + 0] = f16lo_to_float(a.x) + f16lo_to_float(b.x);
+      v[4 * j + 1] = f16hi_to_float(a.x) + f16hi_to_float(b.x);
+      v[4 * j + 2] = f16lo_to_float(a.y) + f16lo_to_float(b.y);
+      v[4 * j + 3] = f16hi_to_float(a.y) + f16hi_to_float(b.y);
     }
   }
 };
@@ -335,8 +381,15 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
     float z[NV], xo[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
+      v[i] *= e.acc_scale;
       z[i] = v[i] + (e.bias ? __ldg(e.bias + n + i) : 0.f);
       xo[i] = fmaxf(z[i], 0.f);
+    }
+    if (e.overflow) {
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) mx = fmaxf(mx, xo[i]);
+      if (!(mx < 32768.f)) atomicOr(e.overflow, 1);
     }
     ST::template store<NV>(e.out, e.out_elems, off, xo);
     if (e.out_f32) store_f32<NV>(e.out_f32 + off, xo);
@@ -367,7 +420,7 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
     ST::template load<NV>(e.x_act, e.x_elems, off, xa);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float d = safe_den(v[i] + ((e.bias && e.rule_bias) ? __ldg(e.bias + n + i) : 0.f));
+      const float d = safe_den(v[i] * e.acc_scale + ((e.bias && e.rule_bias) ? __ldg(e.bias + n + i) : 0.f));
       mm[i] = 1.f / d;
       gg[i] = xa[i] / d;
     }
@@ -403,6 +456,8 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->up = p.up;
   e->relu_acc = p.relu_acc;
   e->g_up = p.g_up;
+  e->acc_scale = p.acc_scale;
+  e->overflow = p.overflow;
   e->out_planar8 = p.out_planar8;
   e->out = nullptr;
   e->out_elems = 0;

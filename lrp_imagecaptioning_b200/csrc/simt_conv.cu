@@ -139,6 +139,7 @@ int simt_conv_launch(const SimtConvArgs& a, cudaStream_t stream) {
   LRPCAP_TRY(make_epi_dev(a.epi, &e));
   if (a.out_planes == 2) return launch_mode<StoreSplit>(a, e, stream);
   if (a.out_planes == 3) return launch_mode<StoreSplit3>(a, e, stream);
+  if (a.out_planes == kPlanesF16x2) return launch_mode<StoreSplitH>(a, e, stream);
   return launch_mode<StoreF32>(a, e, stream);
 }
 

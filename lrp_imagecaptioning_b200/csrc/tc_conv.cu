@@ -66,11 +66,12 @@ __device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN)
   return t;
 }
 
-template <int BN, int MODE, int NS, bool PROMO>
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
   using C = Cfg<BN, NS>;
-  using ST = typename std::conditional<NS == 3, StoreSplit3, StoreSplit>::type;
+  using ST = typename std::conditional<NS == 3, StoreSplit3,
+                                       typename std::conditional<F16, StoreSplitH, StoreSplit>::type>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -137,7 +138,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc(128, BN);
+      constexpr uint32_t idesc = make_idesc(128, BN, F16);
       uint32_t it = 0, tl = 0;   // tl counts accumulator hand-overs: one per tile, or one per `group` k-steps (promotion)
       const int gsz = PROMO ? g.group : num_k;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -332,12 +333,12 @@ int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
 
 namespace {
 
-template <int BN, int MODE, int NS, bool PROMO>
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false>
 int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   using C = Cfg<BN, NS>;
   static bool configured = false;
   if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE, NS, PROMO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE, NS, PROMO, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::kSmemBytes));
     configured = true;
   }
@@ -350,7 +351,7 @@ int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream
     LRPCAP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
-  tc_conv_kernel<BN, MODE, NS, PROMO><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
+  tc_conv_kernel<BN, MODE, NS, PROMO, F16><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -371,6 +372,17 @@ int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaS
 
 template <int BN>
 int launch_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  if (planes == kPlanesF16x2) {   // two half planes, always promoted
+    if constexpr (BN <= 128) {
+      switch (mode) {
+        case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 2, true, true>(tm, g, e, stream);
+        case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 2, true, true>(tm, g, e, stream);
+        case EPI_RAW: return launch_t<BN, EPI_RAW, 2, true, true>(tm, g, e, stream);
+      }
+    }
+    set_last_error("tc_conv: half-plane operands support forward / raw epilogues with BN <= 128 only (mode %d, BN %d)", mode, BN);
+    return kErrUnsupported;
+  }
   if (planes == 3) {
     if constexpr (BN <= 128) {
       switch (mode) {
@@ -412,7 +424,8 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   LRPCAP_REQUIRE(a.Nout > 0 && a.Nout % 64 == 0, kErrShape, "tc_conv: Nout=%d must be a positive multiple of 64", a.Nout);
   LRPCAP_REQUIRE(a.taps == 9 || a.taps == 1, kErrShape, "tc_conv: taps must be 1 or 9");
   LRPCAP_REQUIRE(a.n_items > 0 && a.H > 0 && a.W > 0, kErrShape, "tc_conv: empty problem");
-  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3, kErrInvalidArg, "tc_conv: planes must be 2 or 3");
+  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3 || a.planes == kPlanesF16x2, kErrInvalidArg,
+                 "tc_conv: planes must be 2, 3 or 4 (two half planes)");
   const int BN = (a.planes == 2 && a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
   if (tc_conv_vh_eligible(a, BN)) return tc_conv_vh_launch(a, BN, stream);   // wide shallow layers: tc_conv_vh.cu
   Geom g;
@@ -426,13 +439,14 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
-  g.group = a.planes == 3 ? (a.promote_every > 0 ? a.promote_every : 1) : (a.promote_every > 0 ? a.promote_every : 0);
+  g.group = a.planes != 2 ? (a.promote_every > 0 ? a.promote_every : 1) : (a.promote_every > 0 ? a.promote_every : 0);
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
   Maps tm;
+  const int n_planes = a.planes == 3 ? 3 : 2;
   for (int pl = 0; pl < 3; ++pl) {
-    const int q = pl < a.planes ? pl : 0;   // unused third slot aliases plane 0
+    const int q = pl < n_planes ? pl : 0;   // unused third slot aliases plane 0
     LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)q * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
     LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)q * a.B_elems, a.taps * a.Nout, a.C, BN));
   }

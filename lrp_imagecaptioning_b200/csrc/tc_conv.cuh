@@ -31,6 +31,8 @@ struct EpiParams {
   size_t out_act_elems = 0;
   float* out_f32 = nullptr;         // optional fp32 copy [items, H, W, Nout]
   float* G = nullptr;               // fp32 per-image multiplier, channel-tiled layout (epilogue.cuh: g_offset)
+  float acc_scale = 1.f;            // forward: accumulator scale (2^-k for weights pre-scaled by 2^k, half planes)
+  int* overflow = nullptr;          // forward, half planes: device flag set when an activation >= 32768
   int g_up = 1;                     // 2 when a 2x2 max-pool follows this layer (its G is read by an up-sampling epilogue)
   float* Mseed = nullptr;           // fp32 [items, H, W, Nout] seed multiplier (last layer only)
   int gmode = G_NONE;
@@ -60,7 +62,8 @@ struct TcConvArgs {
   const void* B = nullptr;  // split storage [taps * Nout, C]
   size_t B_elems = 0;
   int taps = 9, Nout = 0;
-  int planes = 2;           // bf16 planes of A, B and of the forward epilogue's activation tensors: 2 (hi, lo: 3 MMA
+  int planes = 2;           // 4 (kPlanesF16x2): two IEEE half planes, 3 products, promoted every k-step (forward / raw only);
+                            // otherwise bf16 planes of A, B and of the forward epilogue's activation tensors: 2 (hi, lo: 3 MMA
                             // products, 16-bit operands) or 3 (hi, mid, lo: 6 products, fp32-exact operands; forward only)
   int promote_every = 0;    // 2-plane only: > 0 sums partial accumulators in fp32 registers every n k-steps (64 channels
                             // of one tap each); tensor-core accumulation truncates, long chains cost ~1e-5 relative.

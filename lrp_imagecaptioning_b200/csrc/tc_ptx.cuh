@@ -116,8 +116,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+//   a_format [7,10) / b_format [10,13): 1 = bf16, 0 = IEEE half
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool half_operands = false) {
+  return (1u << 4) | (half_operands ? 0u : ((1u << 7) | (1u << 10))) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 

@@ -262,3 +262,34 @@ def test_linearity_in_head_relevance_224_property(rule):
     err = l2_rel(out[2], comb)
     record("linearity %s 224" % rule, out[2], comb)
     assert err <= 2e-4, err
+
+
+def test_half_plane_forward_falls_back_outside_the_half_range(monkeypatch):
+    """Default forward operands are two IEEE half planes; an activation >= 32768 makes the handle switch to the three
+    bf16 planes for good instead of producing inf. Also: small-magnitude inputs keep their accuracy."""
+    import torch
+    from lrp_imagecaptioning_b200 import synth, _lib
+    from lrp_imagecaptioning_b200.encoder import ImageModel, RuleSpec
+    from oracle import encoder_ref as ER
+    hw = 32
+    W = _weights()
+    rule = RuleSpec(_lib.RULE_EPSILON, epsilon=0.01, bias=True)
+    for scale in (3000.0, 1e-3):
+        x = (synth.images(2, hw, 3) * scale).astype(np.float32)
+        m = ImageModel(W, image_hw=hw, precision="bf16x3")
+        m.forward(x, rule)
+        F = m.features().cpu().numpy()
+        ref = ER.features(x, W)
+        assert np.isfinite(F).all()
+        assert linf_rel(F, ref) <= 1e-4, (scale, linf_rel(F, ref))
+        monkeypatch.setenv("LRPCAP_FWD_PLANES", "3")
+        m3 = ImageModel(W, image_hw=hw, precision="bf16x3")
+        m3.forward(x, rule)
+        F3 = m3.features().cpu().numpy()
+        monkeypatch.delenv("LRPCAP_FWD_PLANES")
+        if scale > 1:
+            assert np.array_equal(F, F3)              # the fallback is the three-plane path, bit for bit
+        else:
+            assert not np.array_equal(F, F3)          # in range: the half-plane path is what ran
+        R = torch.from_numpy((ref * 0 + 1).astype(np.float32)).cuda()
+        assert torch.isfinite(m.relevance(np.array([0, 1], dtype=np.int32), R)).all()

@@ -28,7 +28,9 @@ extern "C" {
 
 /* arithmetic of the dense contractions */
 #define LRPCAP_PREC_FP32_SIMT 0 /* fp32 FMA on CUDA cores (exact-fp32 validation mode) */
-#define LRPCAP_PREC_BF16X3_TC 1 /* tcgen05 tensor cores, split-bf16 operands (3 products), fp32 accumulate */
+#define LRPCAP_PREC_BF16X3_TC 1 /* tcgen05 tensor cores, split 16-bit operands (3 products), fp32 accumulate: two bf16 planes
+                                 * for the per-word relevance messages, two IEEE half planes (22 bits; automatic fall-back
+                                 * to three bf16 planes outside the half range) for the per-image forward */
 
 /* encoder rules; replaces the iNNvestigate analyzer classes constructed in
  * models/explainers.py:32,671,883,928 (LRPSequentialPresetA, Gradient, InputTimesGradient, GuidedBackprop) and

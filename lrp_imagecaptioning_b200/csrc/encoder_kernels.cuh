@@ -9,8 +9,8 @@ enum WeightFormat : int {
   WF_SIMT_BWD = 1,  // fp32 [tap'][cout][cin], tap' = flipped (transposed conv)
   WF_TC_FWD = 2,    // split-bf16 [tap][cout][cin]           (K-major B operand of the forward GEMM)
   WF_TC_BWD = 3,    // split-bf16 [tap'][cin][cout]          (K-major B operand of the dgrad GEMM)
-  WF_TC_FWD3 = 4,
-  WF_TC_FWDH = 5,   // as WF_TC_FWD with two IEEE half planes of 2^k * w (Layer::wpow)   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
+  WF_TC_FWD3 = 4,   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
+  WF_TC_FWDH = 5,   // as WF_TC_FWD with two IEEE half planes of 2^k * w (Layer::wpow): the default forward operands
 };
 enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
 

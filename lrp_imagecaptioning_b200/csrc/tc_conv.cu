@@ -357,7 +357,7 @@ int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream
 }
 
 // Instantiated combinations: 2 planes -> every epilogue, BN in {64,128,256}, with and without promotion;
-// 3 planes (forward / raw only, always promoted) -> BN in {64,128}.
+// 3 bf16 planes or 2 half planes (forward / raw only, always promoted) -> BN in {64,128}.
 template <int BN, bool PROMO>
 int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   switch (mode) {

@@ -67,7 +67,7 @@ struct TcConvArgs {
                             // products, 16-bit operands) or 3 (hi, mid, lo: 6 products, fp32-exact operands; forward only)
   int promote_every = 0;    // 2-plane only: > 0 sums partial accumulators in fp32 registers every n k-steps (64 channels
                             // of one tap each); tensor-core accumulation truncates, long chains cost ~1e-5 relative.
-                            // 3-plane launches always promote every k-step.
+                            // 3-plane and half-plane launches always promote (every k-step unless set here).
   EpiParams epi;
 };
 

@@ -1,17 +1,19 @@
-// tcgen05 implicit-GEMM convolution, split-bf16 operands, fp32 accumulation in TMEM (sm_100a).
+// tcgen05 implicit-GEMM convolution, split 16-bit operands (bf16 or IEEE half planes), fp32 accumulation in TMEM (sm_100a).
 //
 // Replaces, for the VGG16 encoder of the reference, the TensorFlow ops emitted by
 //   keras Conv2D forward                      (/root/reference/models/explainers.py:375 via _image_model.predict)
 //   iNNvestigate GradientWRT on a conv layer  (innvestigate/layers.py:138-157 -> utils/keras/backend.py:58-60)
 // and, with taps == 1, the dense contractions of the decoder relevance (explainers.py:156-165).
 //
-// Structure per CTA (persistent, 192 threads, tiles of 128 pixels x BN channels):
+// Structure per CTA (persistent, 320 threads, tiles of 128 pixels x BN channels):
 //   warp 0 lane 0 : TMA producer. Per k-step (tap, 64-channel block) four cp.async.bulk.tensor loads
 //                   (A_hi, A_lo as 4-D boxes shifted by the tap offset -- OOB rows/cols are zero-filled,
 //                   which *is* the 'same' padding -- and B_hi, B_lo as 2-D boxes), 128B-swizzled.
-//   warp 1 lane 0 : MMA issuer. 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi) per k-step into one
+//   warp 1 lane 0 : MMA issuer. 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi; 6 with three planes) per k-step into one
 //                   of two TMEM accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem stage.
-//   warps 2..9    : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic -> global.
+//   warps 2..9    : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic
+//                   -> global; with PROMO the partial accumulator of every k-step group is added in fp32 registers.
+// The wide shallow layers of the backward pass take the vertical-halo variant in tc_conv_vh.cu instead.
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 #include <type_traits>

@@ -473,7 +473,7 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       ep.out_msg = msg_[cur ^ 1].p;
       ep.Gin2 = inh ? (ep.up == 2 ? Gc2_[l - 1].as<float>() : G2_[l - 1].as<float>()) : nullptr;
       ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1) * mul;
-      ep.out_planar8 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only, 8 channels at a time
+      ep.out_planar8 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only: fp32, channel-planar
       LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l) * mul, m, ep, s, inh));
       cur ^= 1;
     }
@@ -485,9 +485,8 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       rec.flops = 2.0 * 9.0 * (double)m * hw_ * hw_ * 64.0 * mul * 3.0;
       LRPCAP_CUDA(cudaEventRecord(rec.a, s));
     }
-    LRPCAP_TRY(last_dgrad(msg_[cur].p, (size_t)m * layer_out_elems(0) * mul, split(), reinterpret_cast<const float*>(Wa),
-                          reinterpret_cast<const float*>(Wb), X0_.as<float>(), idx, d_R_pix + (size_t)w0 * pix_elems, m,
-                          hw_, hw_, 64 * mul, mult, s));
+    LRPCAP_TRY(last_dgrad(msg_[cur].as<float>(), reinterpret_cast<const float*>(Wa), reinterpret_cast<const float*>(Wb),
+                          X0_.as<float>(), idx, d_R_pix + (size_t)w0 * pix_elems, m, hw_, hw_, 64 * mul, mult, s));
     if (profile_) {
       LRPCAP_CUDA(cudaEventRecord(rec.b, s));
       prof_.push_back(rec);

@@ -154,29 +154,35 @@ __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict
 }
 
 // ------------------------------------------------------------------ last transposed conv (C -> 3) + re-weighting
-// fp32-FMA bound (1728 FMA per pixel; 12.85 MB in, 0.6 MB out per word at 224x224). The message arrives channel-planar,
-// [item][C/8][H][W][8] (EpiParams::out_planar8 of the layer above), so that the halo patch of one 8-channel chunk is a
-// run of contiguous 16 B pieces -- with the pixel-major layout every chunk pass touched every 128 B line of the patch
-// again and the kernel was DRAM-bound on re-fetches (ncu: 78 % DRAM, 20 % FMA). A thread owns a 2 x 4 pixel block:
-// per channel it loads its 4 x 6 window (4 LDS.128 + 4 LDS.64) and the channel's 27 weights (7 broadcast LDS.128 from a
-// shared-memory copy) for 216 FMAs, which keeps the LSU well below the FMA pipe.
+// fp32-FMA bound (1728 FMA per pixel; 12.85 MB in, 0.6 MB out per word at 224x224). The message arrives as fp32,
+// channel-planar [item][C][H][W] (EpiParams::out_planar8 of the layer above), so one TMA box {40, 34, 4} IS the
+// shared-memory operand: 4 channels of the 32 x 32 tile with its halo, OOB zero-fill = padding, no conversion pass,
+// no registers holding staged data. One thread keeps two boxes in flight (double buffer) while all threads run the FMAs:
+// a thread owns a 2 x 4 pixel block and per channel loads its 4 x 6 window (4 x (LDS.32, LDS.128, LDS.32)) and the channel's 27
+// weights (7 broadcast LDS.128 from a shared-memory copy) for 216 FMAs, which keeps the LSU well below the FMA pipe.
+// (History, measured: register-staged 16-channel chunks of the pixel-major split message were DRAM-bound on re-fetched
+// lines -- 78 % DRAM, 20 % FMA; a TMA-staged bf16 variant still spent a fifth of its issue slots converting.)
 constexpr int kLTY = 32, kLTX = 32;   // tile (rows x cols): 128 threads x (2 x 4) pixels
 constexpr int kLThreads = 128;
-constexpr int kLC = 8;                // channel chunk staged in shared memory
+constexpr int kLC = 4;                // channels per TMA box
 constexpr int kLastMaxC = 128;        // 64 channels, or 2 x 64 for the dual (beta != 0) message
-constexpr int kLPSX = kLTX + 4, kLPSY = kLTY + 2;   // halo patch; row pitch padded to a multiple of 4 floats (LDS.128)
-constexpr int kLHalo = kLPSY * (kLTX + 2), kLIters = (kLHalo + kLThreads - 1) / kLThreads;
+constexpr int kLPSX = kLTX + 8, kLPSY = kLTY + 2;   // halo box: columns x0-4 .. x0+35 (a TMA box must start 16 B aligned in
+                                                    // its innermost dimension, so the left halo column drags 3 more along)
+constexpr int kLBox = kLC * kLPSY * kLPSX;          // floats per box
 constexpr int kLWPitch = 28;          // 27 weights per channel (tap-major, 3 colours), padded to 7 x float4
 
-template <class ST, bool DUAL, int C>
-__global__ void __launch_bounds__(kLThreads, 3)
-last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* __restrict__ Wa,
-                  const float* __restrict__ Wb, const float* __restrict__ images, const int* __restrict__ img_index,
-                  float* __restrict__ out, int H, int W, int tiles_x, int tiles_y, int mult) {
-  extern __shared__ __align__(16) float last_smem[];
-  float (*S)[kLPSY * kLPSX] = reinterpret_cast<float (*)[kLPSY * kLPSX]>(last_smem);
-  float* Wsa = last_smem + kLC * kLPSY * kLPSX;      // [C][28]
-  float* Wsb = Wsa + C * kLWPitch;                   // [C][28] (DUAL only)
+template <bool DUAL, int C>
+__global__ void __launch_bounds__(kLThreads, 4)
+last_dgrad_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ Wa, const float* __restrict__ Wb,
+                  const float* __restrict__ images, const int* __restrict__ img_index, float* __restrict__ out, int H,
+                  int W, int tiles_x, int tiles_y, int mult) {
+  using namespace tcptx;
+  extern __shared__ __align__(128) uint8_t last_smem[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(last_smem) + 127) & ~uintptr_t(127));
+  float* S = reinterpret_cast<float*>(sm);                  // [2][kLC][kLPSY][kLPSX]
+  float* Wsa = S + 2 * kLBox;                               // [C][28]
+  float* Wsb = Wsa + C * kLWPitch;                          // [C][28] (DUAL only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(Wsb + (DUAL ? C * kLWPitch : 0));   // [2]
 
   int bid = blockIdx.x;
   const int tiles = tiles_x * tiles_y;
@@ -185,9 +191,21 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
   const int y0 = (bid / tiles_x) * kLTY, x0 = (bid % tiles_x) * kLTX;
   const int tid = threadIdx.x;
   const int ty = (tid >> 3) * 2, tx = (tid & 7) * 4;
+  constexpr int NCH = C / kLC;
+  constexpr uint32_t kBoxBytes = (uint32_t)kLBox * sizeof(float);
 
-  // weights arrive as [tap][C][3]; shared copy is [c][tap * 3 + colour]
-  for (int i = tid; i < 9 * C * 3; i += kLThreads) {
+  if (tid == 0) {
+    prefetch_tmap(&map);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      mbar_expect_tx(&full[b], kBoxBytes);
+      tma_load_3d(&map, S + b * kLBox, &full[b], x0 - 4, y0 - 1, item * C + b * kLC);
+    }
+  }
+  for (int i = tid; i < 9 * C * 3; i += kLThreads) {   // weights [tap][C][3] -> shared [c][tap * 3 + colour]
     const int tap = i / (C * 3), rem = i - tap * C * 3, c = rem / 3, ci = rem - c * 3;
     Wsa[c * kLWPitch + tap * 3 + ci] = __ldg(Wa + i);
     if (DUAL) Wsb[c * kLWPitch + tap * 3 + ci] = __ldg(Wb + i);
@@ -200,50 +218,30 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
     for (int px = 0; px < 4; ++px)
 #pragma unroll
       for (int ci = 0; ci < 3; ++ci) ca[py][px][ci] = cb[py][px][ci] = 0.f;
+  __syncthreads();   // barriers initialised, weights in place
 
 #pragma unroll 1
-  for (int c0 = 0; c0 < C; c0 += kLC) {
-    // stage the halo patch of this channel chunk: all global loads are issued before the barrier (they overlap the
-    // other warps' FMAs on the previous chunk), the shared-memory stores after it
-    float v[kLIters][kLC];
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int b = ch & 1;
+    mbar_wait(&full[b], (uint32_t)((ch >> 1) & 1));
+    const float* Sb = S + b * kLBox;
 #pragma unroll
-    for (int it = 0; it < kLIters; ++it) {
-      const int pix = tid + it * kLThreads;
-      const int py = pix / (kLTX + 2), px = pix - py * (kLTX + 2);
-      const int gy = y0 + py - 1, gx = x0 + px - 1;
-#pragma unroll
-      for (int i = 0; i < kLC; ++i) v[it][i] = 0.f;
-      if (pix < kLHalo && gy >= 0 && gy < H && gx >= 0 && gx < W)
-        ST::template load<kLC>(msg, msg_elems, ((((size_t)item * (C / kLC) + c0 / kLC) * H + gy) * W + gx) * kLC, v[it]);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < kLIters; ++it) {
-      const int pix = tid + it * kLThreads;
-      const int py = pix / (kLTX + 2), px = pix - py * (kLTX + 2);
-      if (pix < kLHalo) {
-#pragma unroll
-        for (int i = 0; i < kLC; ++i) S[i][py * kLPSX + px] = v[it][i];
-      }
-    }
-    __syncthreads();
-#pragma unroll 2
     for (int k = 0; k < kLC; ++k) {
       float win[4][6];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float* row = &S[k][(ty + r) * kLPSX + tx];
-        const float4 a = *reinterpret_cast<const float4*>(row);
-        const float2 b = *reinterpret_cast<const float2*>(row + 4);
-        win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w; win[r][4] = b.x; win[r][5] = b.y;
+        const float* row = Sb + (k * kLPSY + ty + r) * kLPSX + tx;     // box column j holds image column x0 - 4 + j
+        const float4 a = *reinterpret_cast<const float4*>(row + 4);
+        win[r][0] = row[3]; win[r][1] = a.x; win[r][2] = a.y; win[r][3] = a.z; win[r][4] = a.w; win[r][5] = row[8];
       }
+      const int cc = ch * kLC + k;
       float wa[kLWPitch], wb[kLWPitch];
 #pragma unroll
       for (int i = 0; i < kLWPitch / 4; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(Wsa + (c0 + k) * kLWPitch + 4 * i);
+        const float4 t = *reinterpret_cast<const float4*>(Wsa + cc * kLWPitch + 4 * i);
         wa[4 * i] = t.x; wa[4 * i + 1] = t.y; wa[4 * i + 2] = t.z; wa[4 * i + 3] = t.w;
         if (DUAL) {
-          const float4 u = *reinterpret_cast<const float4*>(Wsb + (c0 + k) * kLWPitch + 4 * i);
+          const float4 u = *reinterpret_cast<const float4*>(Wsb + cc * kLWPitch + 4 * i);
           wb[4 * i] = u.x; wb[4 * i + 1] = u.y; wb[4 * i + 2] = u.z; wb[4 * i + 3] = u.w;
         }
       }
@@ -262,149 +260,11 @@ last_dgrad_kernel(const void* __restrict__ msg, size_t msg_elems, const float* _
           }
       }
     }
-  }
-  const int img = mult ? __ldg(img_index + item) : 0;
-#pragma unroll
-  for (int py = 0; py < 2; ++py) {
-    const int y = y0 + ty + py;
-    if (y >= H) continue;
-#pragma unroll
-    for (int px = 0; px < 4; ++px) {
-      const int x = x0 + tx + px;
-      if (x >= W) continue;
-      const size_t pix = (size_t)y * W + x;
-      float* o = out + ((size_t)item * H * W + pix) * 3;
-      if (mult) {
-        const float* xi = images + ((size_t)img * H * W + pix) * 3;
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-          const float xv = __ldg(xi + ci);
-          o[ci] = DUAL ? (xv >= 0.f ? xv * ca[py][px][ci] : xv * cb[py][px][ci]) : xv * ca[py][px][ci];
-        }
-      } else {
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) o[ci] = ca[py][px][ci];
-      }
-    }
-  }
-}
-
-// Same computation with the staging done by TMA (split-bf16 messages only): one elected thread pulls the 34 x 34 x 8
-// halo box of the NEXT channel chunk (both planes; OOB zero-fill = padding) into a raw buffer while all threads run the
-// FMAs of the current one, so no thread ever waits on a global load and no registers hold staged data. ncu on the
-// register-staged kernel above: 3.8 long-scoreboard stalls per issue, FMA pipe 31 % busy at 12 warps / SM.
-constexpr int kLHalf = 4;   // channels converted to fp32 at a time
-constexpr int kLRawPlane = ((kLPSY * (kLTX + 2) * 8 * 2 + 127) / 128) * 128;   // bytes of one bf16 plane of the halo box
-
-template <bool DUAL, int C>
-__global__ void __launch_bounds__(kLThreads, 3)
-last_dgrad_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                      const float* __restrict__ Wa, const float* __restrict__ Wb, const float* __restrict__ images,
-                      const int* __restrict__ img_index, float* __restrict__ out, int H, int W, int tiles_x, int tiles_y,
-                      int mult) {
-  using namespace tcptx;
-  extern __shared__ __align__(128) uint8_t last_raw_smem[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(last_raw_smem) + 127) & ~uintptr_t(127));
-  const uint4* raw_hi = reinterpret_cast<const uint4*>(sm);
-  const uint4* raw_lo = reinterpret_cast<const uint4*>(sm + kLRawPlane);
-  float (*S)[kLPSY * kLPSX] = reinterpret_cast<float (*)[kLPSY * kLPSX]>(sm + 2 * kLRawPlane);   // [kLHalf][...]
-  float* Wsa = reinterpret_cast<float*>(sm + 2 * kLRawPlane) + kLHalf * kLPSY * kLPSX;
-  float* Wsb = Wsa + C * kLWPitch;
-  uint64_t* full = reinterpret_cast<uint64_t*>(Wsb + (DUAL ? C * kLWPitch : 0));
-
-  int bid = blockIdx.x;
-  const int tiles = tiles_x * tiles_y;
-  const int item = bid / tiles;
-  bid -= item * tiles;
-  const int y0 = (bid / tiles_x) * kLTY, x0 = (bid % tiles_x) * kLTX;
-  const int tid = threadIdx.x;
-  const int ty = (tid >> 3) * 2, tx = (tid & 7) * 4;
-  constexpr int NCH = C / kLC;
-  constexpr uint32_t kBoxBytes = (uint32_t)kLPSY * (kLTX + 2) * 8 * 2;
-
-  if (tid == 0) {
-    prefetch_tmap(&map_hi);
-    prefetch_tmap(&map_lo);
-    mbar_init(full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(full, 2 * kBoxBytes);
-    tma_load_4d(&map_hi, sm, full, 0, x0 - 1, y0 - 1, item * NCH);
-    tma_load_4d(&map_lo, sm + kLRawPlane, full, 0, x0 - 1, y0 - 1, item * NCH);
-  }
-  for (int i = tid; i < 9 * C * 3; i += kLThreads) {   // weights [tap][C][3] -> shared [c][tap * 3 + colour]
-    const int tap = i / (C * 3), rem = i - tap * C * 3, c = rem / 3, ci = rem - c * 3;
-    Wsa[c * kLWPitch + tap * 3 + ci] = __ldg(Wa + i);
-    if (DUAL) Wsb[c * kLWPitch + tap * 3 + ci] = __ldg(Wb + i);
-  }
-
-  float ca[2][4][3], cb[2][4][3];
-#pragma unroll
-  for (int py = 0; py < 2; ++py)
-#pragma unroll
-    for (int px = 0; px < 4; ++px)
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) ca[py][px][ci] = cb[py][px][ci] = 0.f;
-  __syncthreads();   // barrier initialised, weights in place
-
-#pragma unroll 1
-  for (int ch = 0; ch < NCH; ++ch) {
-    mbar_wait(full, (uint32_t)(ch & 1));
-#pragma unroll 1
-    for (int half = 0; half < kLC / kLHalf; ++half) {
-      // raw [pixel][8 ch] (hi, lo) -> fp32 S[ch % 4][pixel] (row pitch padded for LDS.128), four channels at a time so
-      // that three CTAs fit an SM
-      for (int pix = tid; pix < kLHalo; pix += kLThreads) {
-        const int py = pix / (kLTX + 2), px = pix - py * (kLTX + 2);
-        const uint2 a = reinterpret_cast<const uint2*>(raw_hi + pix)[half], b = reinterpret_cast<const uint2*>(raw_lo + pix)[half];
-        S[0][py * kLPSX + px] = bf16lo_to_float(a.x) + bf16lo_to_float(b.x);
-        S[1][py * kLPSX + px] = bf16hi_to_float(a.x) + bf16hi_to_float(b.x);
-        S[2][py * kLPSX + px] = bf16lo_to_float(a.y) + bf16lo_to_float(b.y);
-        S[3][py * kLPSX + px] = bf16hi_to_float(a.y) + bf16hi_to_float(b.y);
-      }
-      if (half == kLC / kLHalf - 1) fence_proxy_async();   // raw-buffer reads ordered before the TMA writes issued below
-      __syncthreads();
-      if (half == kLC / kLHalf - 1 && tid == 0 && ch + 1 < NCH) {
-        mbar_expect_tx(full, 2 * kBoxBytes);
-        tma_load_4d(&map_hi, sm, full, 0, x0 - 1, y0 - 1, item * NCH + ch + 1);
-        tma_load_4d(&map_lo, sm + kLRawPlane, full, 0, x0 - 1, y0 - 1, item * NCH + ch + 1);
-      }
-#pragma unroll 2
-      for (int k = 0; k < kLHalf; ++k) {
-        float win[4][6];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const float* row = &S[k][(ty + r) * kLPSX + tx];
-          const float4 a = *reinterpret_cast<const float4*>(row);
-          const float2 b = *reinterpret_cast<const float2*>(row + 4);
-          win[r][0] = a.x; win[r][1] = a.y; win[r][2] = a.z; win[r][3] = a.w; win[r][4] = b.x; win[r][5] = b.y;
-        }
-        const int cc = ch * kLC + half * kLHalf + k;
-        float wa[kLWPitch], wb[kLWPitch];
-#pragma unroll
-        for (int i = 0; i < kLWPitch / 4; ++i) {
-          const float4 t = *reinterpret_cast<const float4*>(Wsa + cc * kLWPitch + 4 * i);
-          wa[4 * i] = t.x; wa[4 * i + 1] = t.y; wa[4 * i + 2] = t.z; wa[4 * i + 3] = t.w;
-          if (DUAL) {
-            const float4 u = *reinterpret_cast<const float4*>(Wsb + cc * kLWPitch + 4 * i);
-            wb[4 * i] = u.x; wb[4 * i + 1] = u.y; wb[4 * i + 2] = u.z; wb[4 * i + 3] = u.w;
-          }
-        }
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-          for (int py = 0; py < 2; ++py)
-#pragma unroll
-            for (int px = 0; px < 4; ++px) {
-              const float sv = win[tap / 3 + py][tap % 3 + px];
-#pragma unroll
-              for (int ci = 0; ci < 3; ++ci) {
-                ca[py][px][ci] = fmaf(sv, wa[tap * 3 + ci], ca[py][px][ci]);
-                if (DUAL) cb[py][px][ci] = fmaf(sv, wb[tap * 3 + ci], cb[py][px][ci]);
-              }
-            }
-        }
-      }
-      __syncthreads();   // S is rewritten by the next conversion
+    fence_proxy_async();   // this thread's reads of buffer b are ordered before the TMA write issued below
+    __syncthreads();
+    if (tid == 0 && ch + 2 < NCH) {
+      mbar_expect_tx(&full[b], kBoxBytes);
+      tma_load_3d(&map, S + b * kLBox, &full[b], x0 - 4, y0 - 1, item * C + (ch + 2) * kLC);
     }
   }
   const int img = mult ? __ldg(img_index + item) : 0;
@@ -522,70 +382,35 @@ int seed_message(const float* R, const float* M, const float* M2, const int* img
   return kOk;
 }
 
-template <class ST, bool DUAL, int C>
-int launch_last(const void* msg, size_t msg_elems, const float* Wa, const float* Wb, const float* images,
-                const int* img_index, float* out, int H, int W, int tiles_x, int tiles_y, int mult, unsigned grid,
-                cudaStream_t s) {
-  const int smem = (kLC * kLPSY * kLPSX + (DUAL ? 2 : 1) * C * kLWPitch) * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(last_dgrad_kernel<ST, DUAL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
-  last_dgrad_kernel<ST, DUAL, C><<<grid, kLThreads, smem, s>>>(msg, msg_elems, Wa, Wb, images, img_index, out, H, W,
-                                                               tiles_x, tiles_y, mult);
-  LRPCAP_CUDA(cudaGetLastError());
-  return kOk;
-}
-
 template <bool DUAL, int C>
-int launch_last_tma(const CUtensorMap& mh, const CUtensorMap& ml, const float* Wa, const float* Wb, const float* images,
-                    const int* img_index, float* out, int H, int W, int tiles_x, int tiles_y, int mult, unsigned grid,
-                    cudaStream_t s) {
-  const int smem = 2 * kLRawPlane + (kLHalf * kLPSY * kLPSX + (DUAL ? 2 : 1) * C * kLWPitch) * (int)sizeof(float) + 16 + 128;
+int launch_last(const CUtensorMap& map, const float* Wa, const float* Wb, const float* images, const int* img_index,
+                float* out, int H, int W, int tiles_x, int tiles_y, int mult, unsigned grid, cudaStream_t s) {
+  const int smem = (2 * kLBox + (DUAL ? 2 : 1) * C * kLWPitch) * (int)sizeof(float) + 16 + 128;
   static bool configured = false;
   if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(last_dgrad_tma_kernel<DUAL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LRPCAP_CUDA(cudaFuncSetAttribute(last_dgrad_kernel<DUAL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  last_dgrad_tma_kernel<DUAL, C><<<grid, kLThreads, smem, s>>>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x,
-                                                               tiles_y, mult);
+  last_dgrad_kernel<DUAL, C><<<grid, kLThreads, smem, s>>>(map, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 
-int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, const float* Wb, const float* images,
-               const int* img_index, float* out, int items, int H, int W, int C, int mult, cudaStream_t s) {
+int last_dgrad(const float* msg, const float* Wa, const float* Wb, const float* images, const int* img_index, float* out,
+               int items, int H, int W, int C, int mult, cudaStream_t s) {
   LRPCAP_REQUIRE(C == 64 || C == 128, kErrShape, "last_dgrad: C must be 64 (or 128 for the dual message), got %d", C);
   const int tiles_x = ceil_div(W, kLTX), tiles_y = ceil_div(H, kLTY);
   const long long blocks = (long long)items * tiles_x * tiles_y;
   LRPCAP_REQUIRE(blocks > 0 && blocks < (1ll << 31), kErrShape, "last_dgrad: grid out of range");
   const unsigned g = (unsigned)blocks;
-  static const bool use_tma = [] { const char* v = std::getenv("LRPCAP_LAST_TMA"); return !(v && v[0] == '0'); }();
-  if (split && use_tma) {   // split-bf16 message: TMA-staged kernel
-    CUtensorMap mh, ml;
-    const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(msg);
-    LRPCAP_TRY(make_map_planar8(&mh, hi, items * (C / 8), H, W, kLTX + 2, kLPSY));
-    LRPCAP_TRY(make_map_planar8(&ml, hi + msg_elems, items * (C / 8), H, W, kLTX + 2, kLPSY));
-    if (Wb) {
-      if (C == 64) return launch_last_tma<true, 64>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
-      return launch_last_tma<true, 128>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
-    }
-    if (C == 64) return launch_last_tma<false, 64>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
-    return launch_last_tma<false, 128>(mh, ml, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+  CUtensorMap map;
+  LRPCAP_TRY(make_map_planar_f32(&map, msg, items * C, H, W, kLPSX, kLPSY, kLC));
+  if (Wb) {
+    if (C == 64) return launch_last<true, 64>(map, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+    return launch_last<true, 128>(map, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
   }
-#define LRPCAP_LAUNCH_LAST(ST, DUAL, CC) \
-  return launch_last<ST, DUAL, CC>(msg, msg_elems, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s)
-#define LRPCAP_LAUNCH_LAST_C(ST, DUAL) \
-  do { if (C == 64) LRPCAP_LAUNCH_LAST(ST, DUAL, 64); else LRPCAP_LAUNCH_LAST(ST, DUAL, 128); } while (0)
-  if (split) {
-    if (Wb) LRPCAP_LAUNCH_LAST_C(StoreSplit, true); else LRPCAP_LAUNCH_LAST_C(StoreSplit, false);
-  } else {
-    if (Wb) LRPCAP_LAUNCH_LAST_C(StoreF32, true); else LRPCAP_LAUNCH_LAST_C(StoreF32, false);
-  }
-#undef LRPCAP_LAUNCH_LAST_C
-#undef LRPCAP_LAUNCH_LAST
-  return kOk;
+  if (C == 64) return launch_last<false, 64>(map, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
+  return launch_last<false, 128>(map, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult, g, s);
 }
 
 int make_posneg(const float* x, float* out, size_t pixels, cudaStream_t s) {

@@ -43,8 +43,8 @@ int seed_message(const float* R, const float* M, const float* M2, const int* img
 //   c_a = Wa^T (*) s,  c_b = Wb^T (*) s (only if Wb != null)
 //   out = mult ? (x >= 0 ? x * c_a : x * c_b) : c_a            x = image[img_index[item]]
 // Wa/Wb: fp32 [tap'][C][3] (WF_SIMT_BWD of the first layer).
-int last_dgrad(const void* msg, size_t msg_elems, bool split, const float* Wa, const float* Wb, const float* images,
-               const int* img_index, float* out, int items, int H, int W, int C, int mult, cudaStream_t s);
+int last_dgrad(const float* msg, const float* Wa, const float* Wb, const float* images, const int* img_index, float* out,
+               int items, int H, int W, int C, int mult, cudaStream_t s);
 
 // [x] (3 ch) -> [x+, x-] (6 ch), fp32 NHWC.
 int make_posneg(const float* x, float* out, size_t pixels, cudaStream_t s);

@@ -32,7 +32,7 @@ struct EpiDev {
   float acc_scale;    // forward: z = acc * acc_scale (+ bias); 2^-k when the weights were pre-scaled by 2^k (half planes)
   int* overflow;      // forward, half planes: set to 1 when an activation leaves the half range
   int g_up;           // layout of G written by the forward epilogues (see g_offset)
-  int out_planar8;    // backward: message written as [items][Nout/8][H][W][8]
+  int out_planar8;    // backward: message written as fp32 [items][NO][H][W] (the last message; name kept from its first layout)
 };
 
 // Per-image multipliers G are only ever touched by epilogues (never by TMA), so they are stored in the order the
@@ -263,15 +263,11 @@ __device__ __forceinline__ void epi_store_msg(const EpiDev& e, size_t item_pixel
   if (!e.out_planar8) {
     ST::template store<NV>(e.out, e.out_elems, ((size_t)item * item_pixels + pix) * NO + n, o);
   } else {
-    constexpr int R = NV < 8 ? NV : 8;
+    // last message: fp32, fully channel-planar [item][NO][pixels] -- what the 64 -> 3 transposed conv (fp32 FMA, reads a
+    // 3x3 window per channel through TMA) consumes; adjacent lanes are adjacent pixels, so the stores coalesce
+    float* dst = reinterpret_cast<float*>(e.out) + ((size_t)item * NO + n) * item_pixels + pix;
 #pragma unroll
-    for (int h = 0; h < NV; h += R) {
-      float t[R];
-#pragma unroll
-      for (int i = 0; i < R; ++i) t[i] = o[h + i];
-      const size_t off = (((size_t)item * (NO >> 3) + ((n + h) >> 3)) * item_pixels + pix) * 8 + ((n + h) & 7);
-      ST::template store<R>(e.out, e.out_elems, off, t);
-    }
+    for (int i = 0; i < NV; ++i) dst[(size_t)i * item_pixels] = o[i];
   }
 }
 

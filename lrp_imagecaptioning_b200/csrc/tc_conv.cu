@@ -305,14 +305,15 @@ int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, in
   return kOk;
 }
 
-int make_map_planar8(CUtensorMap* m, const void* base, int n_groups, int H, int W, int box_w, int box_h) {
+int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, int W, int box_w, int box_h, int box_c) {
   EncodeTiledFn fn = get_encode_fn();
   LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_groups};
-  cuuint64_t strides[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  cuuint32_t box[4] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  LRPCAP_REQUIRE(W % 4 == 0 && box_w % 4 == 0, kErrShape, "planar message: row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_planes};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_c};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   LRPCAP_REQUIRE(r == CUDA_SUCCESS, kErrCuda, "cuTensorMapEncodeTiled(planar message) failed: %d", (int)r);

@@ -50,6 +50,12 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -153,8 +159,8 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, fl
 // 128B-swizzled, OOB zero-filled.  Weights: bf16 [rows, C] read as boxes {64 ch, box_rows}.
 int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int box_w, int box_h);
 int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int box_rows);
-// Channel-planar message [n_groups][H][W][8] bf16 (EpiParams::out_planar8) read as boxes {8 ch, box_w, box_h, 1}, unswizzled.
-int make_map_planar8(CUtensorMap* m, const void* base, int n_groups, int H, int W, int box_w, int box_h);
+// Channel-planar fp32 message [n_planes][H][W] (EpiParams::out_planar8) read as boxes {box_w, box_h, box_c}, OOB zero-filled.
+int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, int W, int box_w, int box_h, int box_c);
 
 // Vertical-halo variant of the transposed-conv kernel (tc_conv_vh.cu); returns kErrUnsupported when the shape does
 // not qualify so that the caller can fall back to the generic kernel.

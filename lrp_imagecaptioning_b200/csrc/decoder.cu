@@ -17,6 +17,10 @@ inline unsigned nblk(size_t n, int b) { return (unsigned)((n + b - 1) / b); }
 }  // namespace
 
 Decoder::~Decoder() {
+  if (fwd_exec_) cudaGraphExecDestroy(fwd_exec_);
+  if (graph_stream_) cudaStreamDestroy(graph_stream_);
+  if (graph_ev_in_) cudaEventDestroy(graph_ev_in_);
+  if (graph_ev_out_) cudaEventDestroy(graph_ev_out_);
   for (void* p : owned_) cudaFree(p);
   DevBuf* bufs[] = {&F_, &Vp_, &P_, &a_, &gp_, &tok_, &logitk_, &logits_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_,
                     &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
@@ -221,6 +225,7 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
     d->WifTC_ = p;
     d->tc_features_ = true;
   }
+  if (const char* gv = getenv("LRPCAP_DECODER_GRAPH")) d->graph_enabled_ = gv[0] != '0';
   {
     const char* v = getenv("LRPCAP_DECODER_TC_FWD");
     const bool want = v ? (v[0] != '0') : true;   // LRPCAP_DECODER_TC_FWD=0: all forward GEMMs in fp64
@@ -283,22 +288,14 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   LRPCAP_TRY(tok_.ensure((size_t)N * T * sizeof(int)));
   LRPCAP_TRY(logitk_.ensure((size_t)N * T * 8));
   DevBuf* states[] = {&h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_, &ctx_, &s_, &chat_};
-  for (DevBuf* b : states) {
-    LRPCAP_TRY(b->ensure(st * 8));
-    LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, st * 8, s));
-  }
+  DevBuf* states2[] = {&h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_};
+  for (DevBuf* b : states) LRPCAP_TRY(b->ensure(st * 8));
   if (td) {
-    DevBuf* states2[] = {&h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_};
-    for (DevBuf* b : states2) {
-      LRPCAP_TRY(b->ensure(st * 8));
-      LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, st * 8, s));
-    }
+    for (DevBuf* b : states2) LRPCAP_TRY(b->ensure(st * 8));
     LRPCAP_TRY(XH2_.ensure((size_t)N * T * Kin2_ * 8));
   }
   LRPCAP_TRY(alpha_.ensure((size_t)N * (T + 1) * L * 8));
   LRPCAP_TRY(beta_.ensure((size_t)N * (T + 1) * 8));
-  LRPCAP_CUDA(cudaMemsetAsync(alpha_.p, 0, (size_t)N * (T + 1) * L * 8, s));
-  LRPCAP_CUDA(cudaMemsetAsync(beta_.p, 0, (size_t)N * (T + 1) * 8, s));
   LRPCAP_TRY(XH1_.ensure((size_t)N * T * Kin1_ * 8));
   LRPCAP_TRY(Z_.ensure((size_t)N * 4 * H * 8));
   LRPCAP_TRY(hp_.ensure((size_t)N * H * 8));
@@ -309,9 +306,18 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   if (greedy) LRPCAP_TRY(logits_.ensure((size_t)N * V * 8));
   else LRPCAP_CUDA(cudaMemcpyAsync(tok_.p, h_captions, (size_t)N * T * sizeof(int), cudaMemcpyHostToDevice, s));
 
+  // the caller's feature tensor may move between calls: it is converted outside the (pointer-baking) graph
+  f32_to_f64_kernel<<<nblk(NL * D, 256), 256, 0, s>>>(d_features, F_.as<double>(), NL * D);
+  ++launches_;
+  // everything else the forward enqueues on the stream (memsets + ~25 small launches per step)
+  auto issue = [&](cudaStream_t s) -> int {   // (parameter shadows the caller's stream on purpose)
+  for (DevBuf* b : states) LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, st * 8, s));
+  if (td)
+    for (DevBuf* b : states2) LRPCAP_CUDA(cudaMemsetAsync(b->p, 0, st * 8, s));
+  LRPCAP_CUDA(cudaMemsetAsync(alpha_.p, 0, (size_t)N * (T + 1) * L * 8, s));
+  LRPCAP_CUDA(cudaMemsetAsync(beta_.p, 0, (size_t)N * (T + 1) * 8, s));
   double *F = F_.as<double>(), *Vp = Vp_.as<double>(), *P = P_.as<double>(), *Vf = UV_.as<double>();
-  // image_features / global_img_feature heads (explainers.py:375-388)
-  f32_to_f64_kernel<<<nblk(NL * D, 256), 256, 0, s>>>(d_features, F, NL * D);
+  // image_features / global_img_feature heads (explainers.py:375-388); F was filled from d_features by the caller part
   LRPCAP_TRY(gemm(F, D, Wif_, H, Vp, H, (int)NL, H, D, bif_, s));
   round_f32_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, NL * H);   // rows are float32 results in the reference
   relu_copy_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, Vf, NL * H);
@@ -319,7 +325,7 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   mean_feat_kernel<<<N, 256, 0, s>>>(F, a_.as<double>(), L, D);
   LRPCAP_TRY(gemm(a_.as<double>(), D, Wgf_, E, gp_.as<double>(), E, N, E, D, bgf_, s));
   round_f32_kernel<<<nblk((size_t)N * E, 256), 256, 0, s>>>(gp_.as<double>(), (size_t)N * E);
-  launches_ += 5;
+  launches_ += 4;
 
   int* tok = tok_.as<int>();
   for (int i = 0; i < T; ++i) {
@@ -365,8 +371,75 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
     ++launches_;
   }
   LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+  };
+
+  // The greedy loop is a fixed sequence of ~500 small launches for a given (N, T, buffers): the first call with a
+  // configuration runs it eagerly (and sizes every scratch buffer), the second captures it into a CUDA graph, later ones
+  // replay the graph -- the launch gaps between its latency-bound kernels are a third of this phase.
+  bool done = false;
+  if (greedy && graph_enabled_) {
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+    mix((uint64_t)N); mix((uint64_t)T); mix((uint64_t)L); mix((uint64_t)(int64_t)eos_token);
+    mix((uint64_t)(uintptr_t)s);
+    DevBuf* all[] = {&F_, &Vp_, &P_, &UV_, &a_, &gp_, &tok_, &logitk_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_, &ctx_, &s_,
+                     &chat_, &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &XH1_, &XH2_, &alpha_, &beta_, &Z_, &hp_, &sg_,
+                     &sp_, &e_, &hc_, &logits_, &gemm_ws_, &As3_, &C32_};
+    for (DevBuf* b : all) mix((uint64_t)(uintptr_t)b->p);
+    // the legacy default stream cannot be captured: graphs run on a private stream ordered after / before it by events
+    cudaStream_t gs = s;
+    if (!s) {
+      if (!graph_stream_) {
+        LRPCAP_CUDA(cudaStreamCreateWithFlags(&graph_stream_, cudaStreamNonBlocking));
+        LRPCAP_CUDA(cudaEventCreateWithFlags(&graph_ev_in_, cudaEventDisableTiming));
+        LRPCAP_CUDA(cudaEventCreateWithFlags(&graph_ev_out_, cudaEventDisableTiming));
+      }
+      gs = graph_stream_;
+    }
+    auto launch_graph = [&]() -> int {
+      if (!s) {
+        LRPCAP_CUDA(cudaEventRecord(graph_ev_in_, s));
+        LRPCAP_CUDA(cudaStreamWaitEvent(gs, graph_ev_in_, 0));
+      }
+      LRPCAP_CUDA(cudaGraphLaunch(fwd_exec_, gs));
+      if (!s) {
+        LRPCAP_CUDA(cudaEventRecord(graph_ev_out_, gs));
+        LRPCAP_CUDA(cudaStreamWaitEvent(s, graph_ev_out_, 0));
+      }
+      return kOk;
+    };
+    if (fwd_exec_ && key == fwd_key_) {
+      LRPCAP_TRY(launch_graph());
+      launches_ += fwd_graph_launches_;
+      done = true;
+    } else if (key == fwd_seen_key_) {
+      if (fwd_exec_) { cudaGraphExecDestroy(fwd_exec_); fwd_exec_ = nullptr; }
+      const long long l0 = launches_;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int ist = issue(gs);
+        const cudaError_t ce = cudaStreamEndCapture(gs, &g);
+        if (ist == kOk && ce == cudaSuccess && g && cudaGraphInstantiate(&fwd_exec_, g, 0) == cudaSuccess) {
+          fwd_key_ = key;
+          fwd_graph_launches_ = launches_ - l0;
+          LRPCAP_TRY(launch_graph());
+          done = true;
+        } else {
+          fwd_exec_ = nullptr;
+          launches_ = l0;
+          cudaGetLastError();      // a failed capture leaves a sticky-free error behind; fall back to eager launches
+          graph_enabled_ = false;
+        }
+        if (g) cudaGraphDestroy(g);
+      }
+    } else {
+      fwd_seen_key_ = key;
+    }
+  }
+  if (!done) LRPCAP_TRY(issue(s));
   if (greedy) {
-    LRPCAP_CUDA(cudaMemcpyAsync(h_captions, tok, (size_t)N * T * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LRPCAP_CUDA(cudaMemcpyAsync(h_captions, tok_.p, (size_t)N * T * sizeof(int), cudaMemcpyDeviceToHost, s));
     LRPCAP_CUDA(cudaStreamSynchronize(s));
   }
   N_ = N; T_ = T; L_ = L;

@@ -63,6 +63,13 @@ class Decoder {
   int Kin1_ = 0, Kin2_ = 0;   // LSTM input widths incl. recurrent part (adaptive: Kin1 = 2E+H)
   long long launches_ = 0;
   bool tc_features_ = false;
+  // CUDA graph of the greedy forward (decoder.cu: Decoder::forward); LRPCAP_DECODER_GRAPH=0 disables it
+  bool graph_enabled_ = true;
+  cudaGraphExec_t fwd_exec_ = nullptr;
+  cudaStream_t graph_stream_ = nullptr;
+  cudaEvent_t graph_ev_in_ = nullptr, graph_ev_out_ = nullptr;
+  uint64_t fwd_key_ = 0, fwd_seen_key_ = 0;
+  long long fwd_graph_launches_ = 0;
   bool tc_forward_ = false;                       // gate / logit GEMMs of the forward on tensor cores (gemm_tc3)
   void *WcatB1TC_ = nullptr, *WcatB2TC_ = nullptr;   // [Kin, 4H] split-bf16: B operand of the gradient decoder's GEMMs
   void *Wcat1TC3_ = nullptr, *Wcat2TC3_ = nullptr, *WoTC3_ = nullptr;

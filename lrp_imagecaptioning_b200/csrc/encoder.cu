@@ -455,8 +455,10 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
   }
   const int mul = inh ? 2 : 1;
 
-  for (int w0 = 0; w0 < n_words; w0 += CW) {
-    const int m = (n_words - w0) < CW ? (n_words - w0) : CW;
+  for (int w0 = 0, m = 0; w0 < n_words; w0 += m) {
+    m = (n_words - w0) < CW ? (n_words - w0) : CW;
+    // streaming to the host: the copy of the last chunk is not overlapped with anything, so make that chunk small
+    if (h_R_pix && w0 + m == n_words && m >= 128) m = (m / 2 + 31) / 32 * 32;
     const int* idx = idx_.as<int>() + w0;
     int cur = 0;
     LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr, idx,

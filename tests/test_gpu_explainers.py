@@ -164,3 +164,24 @@ def test_streamed_engine_lanes_give_identical_maps():
     host = se.explain_batch_host(x, cap_h, greedy=True)
     assert np.array_equal(cap_h, ref_cap)
     assert np.array_equal(host, ref_maps)
+
+
+def test_host_buffer_call_equals_resident_path_with_shrinking_tail_chunks():
+    """lrpcap_explain_batch_host streams every chunk of maps to the host and halves the last chunks (>= 128 words):
+    the partition must still cover every word exactly once, bit-identically to the device-resident path."""
+    import torch
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.engine import ExplainEngine
+    from lrp_imagecaptioning_b200.model import CaptioningModel
+    vgg = synth.vgg16_weights(2)
+    dec = synth.decoder_weights("adaptive", V=V, H=H, E=H, D=512, seed=5)
+    model = CaptioningModel("adaptive", vgg, dec, image_hw=32, precision="bf16x3")
+    model.image_model.set_chunk_words(192)
+    eng = ExplainEngine(model)
+    x = synth.images(18, 32, 4)
+    T = 20                                           # 360 words: chunks 192, then 96 + 64 + ... of the 168-word remainder
+    maps, cap = eng.explain_batch(torch.from_numpy(x).cuda(), T=T, greedy=True)
+    cap_h = np.zeros((18, T), dtype=np.int32)
+    host = eng.explain_batch_host(x, cap_h, greedy=True)
+    assert np.array_equal(cap_h, cap)
+    assert np.array_equal(host, maps.cpu().numpy())

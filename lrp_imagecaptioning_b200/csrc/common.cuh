@@ -102,4 +102,32 @@ __device__ __forceinline__ float safe_den(float z) { return z + (z == 0.f ? 1e-7
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Per-device launch bookkeeping (a process may drive several GPUs, several host threads may launch concurrently).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline int device_sm_count() {
+  static int sms[kMaxDevices] = {};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 1;
+    sms[dev] = n;   // benign race: every writer stores the same value
+  }
+  return sms[dev];
+}
+// Raises a kernel's dynamic shared-memory limit once per device (and again if a larger size is asked for).
+// `state` is a function-local static of the caller: one slot per device.
+template <class Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes, int (&state)[kMaxDevices]) {
+  const int dev = current_device();
+  if (state[dev] >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) state[dev] = bytes;
+  return e;
+}
+
 }  // namespace lrpcap

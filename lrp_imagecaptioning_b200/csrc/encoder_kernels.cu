@@ -386,11 +386,8 @@ template <bool DUAL, int C>
 int launch_last(const CUtensorMap& map, const float* Wa, const float* Wb, const float* images, const int* img_index,
                 float* out, int H, int W, int tiles_x, int tiles_y, int mult, unsigned grid, cudaStream_t s) {
   const int smem = (2 * kLBox + (DUAL ? 2 : 1) * C * kLWPitch) * (int)sizeof(float) + 16 + 128;
-  static bool configured = false;
-  if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(last_dgrad_kernel<DUAL, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static int smem_state[kMaxDevices] = {};
+  LRPCAP_CUDA(ensure_dynamic_smem(last_dgrad_kernel<DUAL, C>, smem, smem_state));
   last_dgrad_kernel<DUAL, C><<<grid, kLThreads, smem, s>>>(map, Wa, Wb, images, img_index, out, H, W, tiles_x, tiles_y, mult);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;

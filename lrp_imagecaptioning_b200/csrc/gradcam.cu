@@ -146,7 +146,8 @@ extern "C" int lrpcap_gradcam(const float* d_features, const int* h_img_index, c
     LRPCAP_CUDA(cudaMemcpyAsync(d_idx, h_img_index, (size_t)n_words * sizeof(int), cudaMemcpyHostToDevice, s));
     LRPCAP_CUDA(cudaMemcpyAsync(d_A, A.data(), A.size() * sizeof(float), cudaMemcpyHostToDevice, s));
     cam_kernel<<<n_words, 256, D * sizeof(float), s>>>(d_features, d_idx, d_grads, d_small, L, D);
-    LRPCAP_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static int smem_state[kMaxDevices] = {};
+    LRPCAP_CUDA(ensure_dynamic_smem(expand_kernel, (int)smem, smem_state));
     expand_kernel<<<n_words, 256, smem, s>>>(d_small, d_A, d_cam, fh, hw);
     LRPCAP_CUDA(cudaGetLastError());
     LRPCAP_CUDA(cudaStreamSynchronize(s));

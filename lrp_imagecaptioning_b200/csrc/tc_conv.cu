@@ -339,20 +339,11 @@ namespace {
 template <int BN, int MODE, int NS, bool PROMO, bool F16 = false>
 int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   using C = Cfg<BN, NS>;
-  static bool configured = false;
-  if (!configured) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MODE, NS, PROMO, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::kSmemBytes));
-    configured = true;
-  }
+  static int smem_state[kMaxDevices] = {};
+  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_kernel<BN, MODE, NS, PROMO, F16>, C::kSmemBytes, smem_state));
   const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv: %lld tiles out of range", tiles);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LRPCAP_CUDA(cudaGetDevice(&dev));
-    LRPCAP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
   tc_conv_kernel<BN, MODE, NS, PROMO, F16><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());

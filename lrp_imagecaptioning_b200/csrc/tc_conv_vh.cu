@@ -288,19 +288,11 @@ int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) 
   LRPCAP_REQUIRE(nb >= 2, kErrUnsupported, "tc_conv_vh: no room for a weight ring (BN=%d)", BN);
   g.NB = nb;
   const int smem = kNA * kASlot + nb * kBSlot + 1024 + 512;
-  static int configured = 0;
-  if (configured < smem) {
-    LRPCAP_CUDA(cudaFuncSetAttribute(tc_conv_vh_kernel<BN, MODE, NCAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  static int smem_state[kMaxDevices] = {};
+  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_vh_kernel<BN, MODE, NCAT>, smem, smem_state));
   const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv_vh: %lld tiles out of range", tiles);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LRPCAP_CUDA(cudaGetDevice(&dev));
-    LRPCAP_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
   tc_conv_vh_kernel<BN, MODE, NCAT><<<grid, kThreads, smem, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());

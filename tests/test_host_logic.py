@@ -102,3 +102,24 @@ def test_explainer_classes_exist_with_reference_signatures():
         for meth in ("_forward_beam_search", "_explain_sentence", "_explain_CNN", "_beam_search"):
             assert hasattr(cls, meth)
     assert E.EPS == 0.01
+
+
+def test_evaluation_argument_checks_need_no_gpu():
+    """Mode / pooling names are validated on the host before anything touches the device."""
+    from lrp_imagecaptioning_b200 import evaluation as EV
+    m = np.zeros((1, 32, 32, 3), dtype=np.float32)
+    with pytest.raises(ValueError):
+        EV.heatmaps(m, "median")
+    with pytest.raises(ValueError):
+        EV.heatmaps(m, "mean", pooling="min")
+    assert EV.THRESHOLDS == (0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9)    # evaluate_bbox.py:251
+
+
+def test_streamed_engine_split_is_a_partition():
+    from lrp_imagecaptioning_b200.engine import StreamedEngine
+    se = object.__new__(StreamedEngine)
+    se.lanes = [None] * 3
+    for n in (0, 1, 2, 3, 7, 64):
+        b = se._split(n)
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(2))
+        assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1

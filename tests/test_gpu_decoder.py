@@ -118,3 +118,36 @@ def test_ragged_word_list_and_order_independence():
     perm = np.array([5, 3, 1, 0, 4, 2])
     R2, _, _ = eng.relevance(wi[perm], wt[perm])
     assert np.array_equal(R2.cpu().numpy(), R[perm])
+
+
+@pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
+def test_greedy_forward_graph_replay_is_identical(kind, monkeypatch):
+    """The greedy forward is captured into a CUDA graph on a repeated configuration and replayed afterwards: eager,
+    captured and replayed calls must give the same captions and the same relevance, also for new features, and the
+    same as a decoder that never uses a graph."""
+    import torch
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.decoder import DecoderEngine
+    dec, F, _ = _setup(kind, SMALL, seed=31)
+    F2 = synth.features(SMALL["N"], L=SMALL["L"], D=SMALL["D"], seed=99)
+    wi = np.array([0, 1, 2, 2], dtype=np.int32)
+    wt = np.array([3, 6, 1, 4], dtype=np.int32)
+
+    def run(eng, feats):
+        cap = eng.forward(feats, T=SMALL["T"], greedy=True, eos=2)
+        R, rw, _ = eng.relevance(wi, wt)
+        return cap.copy(), R.cpu().numpy(), np.asarray(rw).copy()
+    monkeypatch.setenv("LRPCAP_DECODER_GRAPH", "0")
+    plain = DecoderEngine(dec)
+    ref1, ref2 = run(plain, F), run(plain, F2)
+    monkeypatch.delenv("LRPCAP_DECODER_GRAPH")
+    eng = DecoderEngine(dec)
+    launches = []
+    for i, feats in enumerate([F, F, F, F, F2, F]):      # eager, eager (key seen), capture, replay, replay, replay
+        l0 = eng.launches()
+        got = run(eng, feats)
+        launches.append(eng.launches() - l0)
+        want = ref2 if feats is F2 else ref1
+        assert np.array_equal(got[0], want[0]), i
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), i
+    assert len(set(launches)) == 1                        # replayed launches are counted like eager ones

@@ -196,6 +196,8 @@ int lrpcap_bbox_correctness(const float* d_heatmaps, int n_maps, int hw, const i
 
 /* ----------------------------------------------------------------------------------------------- debug / tests
  * Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
+ * precision: LRPCAP_PREC_FP32_SIMT; LRPCAP_PREC_BF16X3_TC (two bf16 planes: the backward arithmetic); 2 = three bf16
+ * planes, promoted; 3 = two IEEE half planes, promoted (the forward arithmetic).
  * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out);

@@ -83,8 +83,13 @@ class CaptioningModel(object):
         np.savez(path, **self.state_dict())
 
     def load_weights(self, path):
-        """Counterpart of keras_model.load_weights (explainers.py:27); `.npz` with Keras tensor names."""
-        z = np.load(path)
+        """Counterpart of keras_model.load_weights (explainers.py:27): `.npz` with Keras tensor names, or the Keras
+        `.hdf5` / `.h5` file itself when h5py is importable (keras_io.read_keras_hdf5)."""
+        if str(path).endswith((".hdf5", ".h5")):
+            from .keras_io import read_keras_hdf5
+            z = read_keras_hdf5(path)
+        else:
+            z = np.load(path)
         vgg = []
         for name in ImageModel.layer_names:
             vgg.append((np.asarray(z[name + "/kernel"], dtype=np.float32), np.asarray(z[name + "/bias"], dtype=np.float32)))

@@ -123,3 +123,49 @@ def test_streamed_engine_split_is_a_partition():
         b = se._split(n)
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(2))
         assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+
+
+def test_keras_hdf5_reader_renames_datasets(monkeypatch, tmp_path):
+    """keras_io walks the HDF5 datasets `<...>/<layer>/<tensor>:0` into the container's `<layer>/<tensor>` keys; h5py is
+    absent here, so a stand-in module with the same File / visititems surface serves a synthetic model's tensors."""
+    import sys
+    import types
+    from lrp_imagecaptioning_b200 import synth, keras_io
+    from lrp_imagecaptioning_b200.model import CaptioningModel, _names
+    from lrp_imagecaptioning_b200.encoder import ImageModel
+    vgg = synth.vgg16_weights(1)
+    dec = synth.decoder_weights("gridtd", V=50, H=64, E=64, D=512, seed=2)
+    store = {}
+    for (k, b), name in zip(vgg, ImageModel.layer_names):                      # VGG16 nested as a sub-model
+        store["model_weights/vgg16/%s/kernel:0" % name] = k
+        store["model_weights/vgg16/%s/bias:0" % name] = b
+    for ours, keras_name in _names("gridtd").items():
+        layer, tensor = keras_name.split("/")
+        store["model_weights/%s/%s/%s:0" % (layer, layer, tensor)] = np.asarray(dec[ours])
+
+    class FakeFile(object):
+        def __init__(self, path, mode="r"):
+            assert mode == "r"
+        def __enter__(self):
+            return self
+        def __exit__(self, *a):
+            return False
+        def visititems(self, fn):
+            fn("model_weights", object())                                       # a group: no shape / dtype
+            for name, arr in store.items():
+                fn(name, arr)
+    monkeypatch.setitem(sys.modules, "h5py", types.SimpleNamespace(File=FakeFile))
+    w = keras_io.read_keras_hdf5("keras_model.hdf5")
+    assert "block3_conv2/kernel" in w and "embedding_1/embeddings" in w and all(v.dtype == np.float32 for v in w.values())
+    assert keras_io._key("model_weights/output/output/bias:0") == "output/bias"
+    # round trip through the container: hdf5 path -> same tensors as the synthetic source
+    m = CaptioningModel("gridtd", synth.vgg16_weights(9), synth.decoder_weights("gridtd", V=50, H=64, E=64, D=512, seed=8),
+                        image_hw=32)
+    m.load_weights("keras_model.hdf5")
+    assert np.array_equal(m.vgg[4][0], vgg[4][0]) and np.array_equal(m.dec["td_wh"], dec["td_wh"])
+    names = keras_io.convert("keras_model.hdf5", str(tmp_path / "w.npz"))
+    assert len(names) == len(store) and np.array_equal(np.load(str(tmp_path / "w.npz"))["output/kernel"], dec["output_w"])
+    monkeypatch.delitem(sys.modules, "h5py")
+    monkeypatch.setitem(sys.modules, "h5py", None)                              # import h5py -> ImportError
+    with pytest.raises(ImportError):
+        keras_io.read_keras_hdf5("keras_model.hdf5")

@@ -248,7 +248,7 @@ def run_ours(args, rank, local_rank, world):
                 "last_dgrad_ms_per_step": prof["last"][0] / max(args.steps, 1)}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32 (bf16x3 split on tensor cores, fp32 accumulate) encoder / f64 decoder" if args.precision == "bf16x3"
+           "dtype": "f32 as split 16-bit tensor-core operands (3 products: bf16 planes backward, f16 planes forward), fp32 accumulate; f64 decoder" if args.precision == "bf16x3"
                     else "f32 encoder / f64 decoder",
            "data": "synthetic", "config": config_dict(args, world), "clocks": clocks, "gpu_launches": int(launches),
            "e2e": {"value": total_words / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,

@@ -475,7 +475,7 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       ep.out_msg = msg_[cur ^ 1].p;
       ep.Gin2 = inh ? (ep.up == 2 ? Gc2_[l - 1].as<float>() : G2_[l - 1].as<float>()) : nullptr;
       ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1) * mul;
-      ep.out_planar8 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only: fp32, channel-planar
+      ep.out_planar_f32 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only: fp32, channel-planar
       LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l) * mul, m, ep, s, inh));
       cur ^= 1;
     }

@@ -155,7 +155,7 @@ __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict
 
 // ------------------------------------------------------------------ last transposed conv (C -> 3) + re-weighting
 // fp32-FMA bound (1728 FMA per pixel; 12.85 MB in, 0.6 MB out per word at 224x224). The message arrives as fp32,
-// channel-planar [item][C][H][W] (EpiParams::out_planar8 of the layer above), so one TMA box {40, 34, 4} IS the
+// channel-planar [item][C][H][W] (EpiParams::out_planar_f32 of the layer above), so one TMA box {40, 34, 4} IS the
 // shared-memory operand: 4 channels of the 32 x 32 tile with its halo, OOB zero-fill = padding, no conversion pass,
 // no registers holding staged data. One thread keeps two boxes in flight (double buffer) while all threads run the FMAs:
 // a thread owns a 2 x 4 pixel block and per channel loads its 4 x 6 window (4 x (LDS.32, LDS.128, LDS.32)) and the channel's 27

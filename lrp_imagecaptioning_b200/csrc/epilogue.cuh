@@ -32,7 +32,7 @@ struct EpiDev {
   float acc_scale;    // forward: z = acc * acc_scale (+ bias); 2^-k when the weights were pre-scaled by 2^k (half planes)
   int* overflow;      // forward, half planes: set to 1 when an activation leaves the half range
   int g_up;           // layout of G written by the forward epilogues (see g_offset)
-  int out_planar8;    // backward: message written as fp32 [items][NO][H][W] (the last message; name kept from its first layout)
+  int out_planar_f32;    // backward: message written as fp32 [items][NO][H][W] (the last message)
 };
 
 // Per-image multipliers G are only ever touched by epilogues (never by TMA), so they are stored in the order the
@@ -260,7 +260,7 @@ __device__ __forceinline__ void store_f32(float* p, const float (&v)[NV]) { Stor
 template <int NV, class ST>
 __device__ __forceinline__ void epi_store_msg(const EpiDev& e, size_t item_pixels, int item, size_t pix, int NO, int n,
                                               const float (&o)[NV]) {
-  if (!e.out_planar8) {
+  if (!e.out_planar_f32) {
     ST::template store<NV>(e.out, e.out_elems, ((size_t)item * item_pixels + pix) * NO + n, o);
   } else {
     // last message: fp32, fully channel-planar [item][NO][pixels] -- what the 64 -> 3 transposed conv (fp32 FMA, reads a
@@ -454,7 +454,7 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->g_up = p.g_up;
   e->acc_scale = p.acc_scale;
   e->overflow = p.overflow;
-  e->out_planar8 = p.out_planar8;
+  e->out_planar_f32 = p.out_planar_f32;
   e->out = nullptr;
   e->out_elems = 0;
   switch (p.mode) {

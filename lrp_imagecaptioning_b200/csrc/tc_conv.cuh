@@ -51,7 +51,7 @@ struct EpiParams {
   int up = 1;
   int relu_acc = 0;
   void* out_msg = nullptr;          // split storage [items, H*up, W*up, Nout]
-  int out_planar8 = 0;              // 1: write the message as fp32 [items][NO][H*up][W*up] (read by last_dgrad only)
+  int out_planar_f32 = 0;              // 1: write the message as fp32 [items][NO][H*up][W*up] (read by last_dgrad only)
   size_t out_msg_elems = 0;
 };
 

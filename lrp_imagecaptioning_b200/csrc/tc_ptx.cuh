@@ -159,7 +159,7 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, fl
 // 128B-swizzled, OOB zero-filled.  Weights: bf16 [rows, C] read as boxes {64 ch, box_rows}.
 int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int box_w, int box_h);
 int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int box_rows);
-// Channel-planar fp32 message [n_planes][H][W] (EpiParams::out_planar8) read as boxes {box_w, box_h, box_c}, OOB zero-filled.
+// Channel-planar fp32 message [n_planes][H][W] (EpiParams::out_planar_f32) read as boxes {box_w, box_h, box_c}, OOB zero-filled.
 int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, int W, int box_w, int box_h, int box_c);
 
 // Vertical-halo variant of the transposed-conv kernel (tc_conv_vh.cu); returns kErrUnsupported when the shape does

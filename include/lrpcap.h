@@ -84,9 +84,13 @@ int lrpcap_encoder_relevance(lrpcap_encoder_t* enc, const int* h_img_index, cons
 int lrpcap_encoder_relevance_host(lrpcap_encoder_t* enc, const int* h_img_index, const float* h_R_head, int n_words,
                                   float* h_R_pix, void* stream);
 int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words);
-/* Tensor-core mode: the transposed-conv GEMMs move their TMEM accumulator into fp32 registers every `every_k_steps`
- * k-steps (one k-step = 64 channels of one tap); 0 (default) disables it: measured to change nothing at the 1e-4 level
- * (profiles/r01_promote_sweep.json) because the backward chain is insensitive to 1e-5 operand noise.  DESIGN.md section 5. */
+/* Tensor-core mode: the transposed-conv GEMMs hand their TMEM accumulator to fp32 registers every `every_k_steps`
+ * k-steps (one k-step = 64 channels of one tap). tcgen05 accumulation rounds toward zero: a chain of n accumulates
+ * shrinks every output by ~1.5e-8 n, i.e. -1.6e-5 per 512-channel layer and -1e-4 over the 12 layers -- a uniform scale
+ * error that alone breaks the 1e-4 conservation tolerance for the same-sign alpha-beta chains (profiles/r02_diag_parity.jsonl).
+ * -1 (default): once per filter tap on the layers with >= 256 input channels for the alpha-beta family and z+ (sum error
+ * 1.5e-5, +5 % time), never for the mixed-sign rules (their sums are unaffected: 6e-7); 0: never; n > 0: every n k-steps
+ * on every layer. */
 int lrpcap_encoder_set_promote(lrpcap_encoder_t* enc, int every_k_steps);
 long long lrpcap_encoder_launches(lrpcap_encoder_t* enc);
 /* Kernel timing (CUDA events on the launching stream around every convolution launch) for roofline reporting.
@@ -195,7 +199,17 @@ int lrpcap_bbox_correctness(const float* d_heatmaps, int n_maps, int hw, const i
                             const float* h_thresholds, int n_thresholds, float* h_ratio, void* stream);
 
 /* ----------------------------------------------------------------------------------------------- debug / tests
- * Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
+ * Discrete decisions of the resident forward state, for parity tests: every rule is discontinuous at max-pool arg-max
+ * ties (TF MaxPoolGrad routes to the first maximum, innvestigate relevance_analyzer.py:459-480) and the gradient
+ * family / Z rule also at ReLU kinks, so a test pins the oracle to the decisions this forward pass took.
+ * lrpcap_encoder_debug_pool_routes: conv layer `layer` (0-based; 1, 3, 6, 9 are followed by a pool), h_routes
+ * [n_images, H/2, W/2, C] bytes = window position (sy * 2 + sx) each pooled element routes to.
+ * lrpcap_encoder_debug_multiplier: h_G [n_images, H, W, C] fp32 = dense per-image multiplier of conv layer `layer` < 12
+ * (x/stab(z), x/safe(z+), [z > 0] ... by rule; zero away from the pool arg-max); branch 1 = inhibitor (beta != 0).
+ * Both synchronise the device. */
+int lrpcap_encoder_debug_pool_routes(lrpcap_encoder_t* enc, int layer, unsigned char* h_routes);
+int lrpcap_encoder_debug_multiplier(lrpcap_encoder_t* enc, int layer, int branch, float* h_G);
+/* Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
  * precision: LRPCAP_PREC_FP32_SIMT; LRPCAP_PREC_BF16X3_TC (two bf16 planes: the backward arithmetic); 2 = three bf16
  * planes, promoted; 3 = two IEEE half planes, promoted (the forward arithmetic).
  * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */

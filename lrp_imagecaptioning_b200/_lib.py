@@ -66,6 +66,8 @@ PROTOTYPES = {
     "lrpcap_lrp_inference_scores": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_heatmaps": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_float_p, c_void_p]),
     "lrpcap_bbox_correctness": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, c_void_p]),
+    "lrpcap_encoder_debug_pool_routes": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p]),
+    "lrpcap_encoder_debug_multiplier": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_float_p]),
     "lrpcap_debug_conv": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p]),
 }
 

@@ -108,7 +108,7 @@ int lrpcap_encoder_set_chunk_words(lrpcap_encoder_t* enc, int chunk_words) {
 }
 
 int lrpcap_encoder_set_promote(lrpcap_encoder_t* enc, int every_k_steps) {
-  LRPCAP_REQUIRE(enc && enc->impl && every_k_steps >= 0, kErrInvalidArg, "encoder_set_promote: bad argument");
+  LRPCAP_REQUIRE(enc && enc->impl && every_k_steps >= -1, kErrInvalidArg, "encoder_set_promote: bad argument");
   enc->impl->set_promote(every_k_steps);
   return kOk;
 }
@@ -124,6 +124,16 @@ int lrpcap_encoder_profile(lrpcap_encoder_t* enc, int enable) {
 int lrpcap_encoder_profile_read(lrpcap_encoder_t* enc, double* h_out12) {
   LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_profile_read: null handle");
   return enc->impl->profile_read(h_out12);
+}
+
+int lrpcap_encoder_debug_pool_routes(lrpcap_encoder_t* enc, int layer, unsigned char* h_routes) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_debug_pool_routes: null handle");
+  return enc->impl->debug_pool_routes(layer, h_routes);
+}
+
+int lrpcap_encoder_debug_multiplier(lrpcap_encoder_t* enc, int layer, int branch, float* h_G) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_debug_multiplier: null handle");
+  return enc->impl->debug_multiplier(layer, branch, h_G);
 }
 
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,

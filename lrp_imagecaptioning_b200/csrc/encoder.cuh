@@ -65,8 +65,10 @@ class Encoder {
   int relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s,
                 float* h_R_pix = nullptr);
   void set_chunk_words(int n) { chunk_words_ = n > 0 ? n : 1; }
-  // k-steps between fp32 promotions of the tensor-core accumulator in the backward GEMMs (0 = never)
-  void set_promote(int every) { bwd_promote_ = every > 0 ? every : 0; }
+  // k-steps between fp32 promotions of the tensor-core accumulator in the backward GEMMs: 0 = never, n > 0 = every n
+  // k-steps on every layer, -1 (default) = once per filter tap on the layers with >= 256 input channels when the rule
+  // builds same-sign chains (alpha-beta family, z+), else never
+  void set_promote(int every) { bwd_promote_ = every >= -1 ? every : -1; }
   // kernels launched by this object since construction (bench.py's gpu_launches)
   long long launches() const { return launches_; }
   // Kernel timing with CUDA events on the launching stream (bench.py roofline): when enabled every conv launch is
@@ -74,6 +76,13 @@ class Encoder {
   // out[3*c + 0] = total ms, out[3*c + 1] = algorithmic FLOPs (2*MAC), out[3*c + 2] = launches; then resets.
   void set_profile(bool on) { profile_ = on; }
   int profile_read(double* out9);
+  // Test / diagnostics exports of the resident per-image state (synchronous, host outputs):
+  //   pool routes: h_out [n_images, H/2, W/2, C] bytes, window position (sy * 2 + sx) the max-pool after conv layer
+  //                `layer` routes to (TF MaxPoolGrad's first maximum as this forward pass saw it);
+  //   multiplier:  h_out [n_images, H, W, C] fp32, the dense multiplier G_l of conv layer `layer` (< 12) with the pool
+  //                routing folded in (zeros away from the arg-max); branch 1 = inhibitor multiplier (beta != 0).
+  int debug_pool_routes(int layer, unsigned char* h_out);
+  int debug_multiplier(int layer, int branch, float* h_out);
 
  private:
   struct ProfRec {
@@ -106,7 +115,7 @@ class Encoder {
   int fwd_planes() const { return split() ? fwd_planes_ : 0; }
   size_t layer_out_elems(int l) const { return (size_t)L_[l].hw * L_[l].hw * L_[l].cout; }
 
-  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = 0, fwd_promote_ = 1, fwd_planes_ = kPlanesF16x2;
+  int hw_ = 0, precision_ = 0, n_images_ = 0, chunk_words_ = 256, bwd_promote_ = -1, fwd_promote_ = 1, fwd_planes_ = kPlanesF16x2;
   int* d_overflow_ = nullptr;   // half-plane forward: set by the epilogue when an activation leaves the half range
   void set_wpow(int l, const float* h_w);
   long long launches_ = 0;

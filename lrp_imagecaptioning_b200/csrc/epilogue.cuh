@@ -308,7 +308,9 @@ __device__ __forceinline__ void epi_bwd(const EpiDev& e, int H, int W, int Nout,
 // parallelism to hide a load -> use latency per chunk (ncu: the epilogue, not the tensor pipe, paced the 64-channel layers).
 // load_acc(c, v) must fetch chunk c of the accumulator and is called by every lane (tcgen05.ld is warp-collective);
 // `valid` only guards global-memory traffic. Chunk c covers channels [n_first + c * n_step, +16).
-template <int UP, int NCH, class ST, class AccLoader>
+// PIPE = false keeps one multiplier run in flight instead of two (the promoted path holds the whole accumulator row in
+// registers and has none to spare).
+template <int UP, int NCH, class ST, bool PIPE = true, class AccLoader>
 __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, int Nout, int item, int y, int x,
                                                int n_first, int n_step, bool valid, AccLoader&& load_acc) {
   constexpr int SUBS = UP * UP;
@@ -320,9 +322,10 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
   const size_t gpix = ((size_t)img * (Nout >> 4)) * gplane + (size_t)y * W + x;
   for (int pass = 0; pass < (e.Gin2 ? 2 : 1); ++pass) {
     const float* G = pass ? e.Gin2 : e.Gin;
-    float gg[2][16];
-    unsigned gi[2] = {0u, 0u};
-    if (valid) {
+    constexpr int NB = PIPE ? 2 : 1;
+    float gg[NB][16];
+    unsigned gi[NB] = {};
+    if (PIPE && valid) {
       const size_t o0 = gpix + (size_t)(n_first >> 4) * gplane;
       load_f32<16>(G + o0 * 16, gg[0]);
       if (UP == 2) gi[0] = __ldg(e.Gidx + o0);
@@ -337,17 +340,23 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
         for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
       }
       const int n = n_first + c * n_step;
-      if (c + 1 < NCH && valid) {
-        const size_t o1 = gpix + (size_t)((n + n_step) >> 4) * gplane;
-        load_f32<16>(G + o1 * 16, gg[(c + 1) & 1]);
-        if (UP == 2) gi[(c + 1) & 1] = __ldg(e.Gidx + o1);
+      if (PIPE) {
+        if (c + 1 < NCH && valid) {
+          const size_t o1 = gpix + (size_t)((n + n_step) >> 4) * gplane;
+          load_f32<16>(G + o1 * 16, gg[(c + 1) % NB]);
+          if (UP == 2) gi[(c + 1) % NB] = __ldg(e.Gidx + o1);
+        }
+      } else if (valid) {
+        const size_t o1 = gpix + (size_t)(n >> 4) * gplane;
+        load_f32<16>(G + o1 * 16, gg[0]);
+        if (UP == 2) gi[0] = __ldg(e.Gidx + o1);
       }
       if (valid) {
 #pragma unroll
         for (int sub = 0; sub < SUBS; ++sub) {
           float o[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = v[i] * g_select<UP>(gg[c & 1][i], gi[c & 1], i, sub);
+          for (int i = 0; i < 16; ++i) o[i] = v[i] * g_select<UP>(gg[c % NB][i], gi[c % NB], i, sub);
           const size_t pix = (size_t)(y * UP + sub / UP) * WW + (x * UP + sub % UP);
           epi_store_msg<16, ST>(e, item_pixels, item, pix, NO, pass * Nout + n, o);
         }

@@ -5,14 +5,16 @@
 //   iNNvestigate GradientWRT on a conv layer  (innvestigate/layers.py:138-157 -> utils/keras/backend.py:58-60)
 // and, with taps == 1, the dense contractions of the decoder relevance (explainers.py:156-165).
 //
-// Structure per CTA (persistent, 320 threads, tiles of 128 pixels x BN channels):
+// Structure per CTA (persistent, 384 threads = one producer warpgroup + two epilogue warpgroups, tiles of 128 pixels x BN channels):
 //   warp 0 lane 0 : TMA producer. Per k-step (tap, 64-channel block) four cp.async.bulk.tensor loads
 //                   (A_hi, A_lo as 4-D boxes shifted by the tap offset -- OOB rows/cols are zero-filled,
 //                   which *is* the 'same' padding -- and B_hi, B_lo as 2-D boxes), 128B-swizzled.
 //   warp 1 lane 0 : MMA issuer. 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi; 6 with three planes) per k-step into one
 //                   of two TMEM accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem stage.
-//   warps 2..9    : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic
-//                   -> global; with PROMO the partial accumulator of every k-step group is added in fp32 registers.
+//   warps 2, 3    : idle (they complete the producer warpgroup, which gives most of its registers away: setmaxnreg)
+//   warps 4..11   : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic
+//                   -> global; with PROMO the partial accumulator of every k-step group is added in fp32 registers
+//                   (a whole 128-column accumulator row per thread, hence the register hand-over).
 // The wide shallow layers of the backward pass take the vertical-halo variant in tc_conv_vh.cu instead.
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
@@ -47,9 +49,11 @@ struct Maps {
 // Persistent, warp-specialised: grid = #SMs, each CTA walks tiles  t = blockIdx.x, blockIdx.x + gridDim.x, ...
 //   warp 0 (one lane) : TMA producer      -- smem ring runs across tile boundaries, never drains
 //   warp 1 (one lane) : MMA issuer        -- accumulators double-buffered in TMEM (2 x BN columns)
-//   warps 2..9        : epilogue          -- tcgen05.ld -> fused rule arithmetic -> global, overlapping the next tile's MMAs
+//   warps 4..11       : epilogue          -- tcgen05.ld -> fused rule arithmetic -> global, overlapping the next tile's MMAs
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over column chunks
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarp0 = 4;                       // first epilogue warp: warps 0..3 are the producer warpgroup
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
+constexpr int kProducerRegs = 40, kEpilogueRegs = 232;   // 128 * 48 + 256 * 224 <= 64 K registers
 
 
 struct TileCoord {
@@ -109,6 +113,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
   const int num_k = g.taps * g.cblocks;
   const uint32_t stage_tx = (uint32_t)NS * ((uint32_t)(g.TW * g.TH) * 128u + (uint32_t)C::kBTileBytes);
 
+  if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
@@ -185,10 +190,11 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         }
       }
     }
-  } else {
+  } else if (warp >= kEpiWarp0) {
     // ---------------- epilogue warps (warp w owns TMEM lanes [32 (w % 4), +32)) ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
     const int ty = r / g.TW;
     const int tx = r - ty * g.TW;
@@ -207,6 +213,11 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         for (int ci = 0; ci < kChunks; ++ci)
 #pragma unroll
           for (int i = 0; i < 16; ++i) acc[ci][i] = 0.f;
+        if (MODE == EPI_BWD && row_ok) {   // multipliers of this tile -> L2 while its MMAs run
+          if (y < g.H && x < g.W)
+            for (int c = half; c < BN / 16; c += kEpiWarps / 4)
+              epi_prefetch_bwd(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16);
+        }
         for (int kk0 = 0; kk0 < num_k; kk0 += g.group, ++tl) {
           const uint32_t buf = tl & 1u;
           mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
@@ -223,7 +234,17 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[buf]);
         }
-        if (valid) {
+        if constexpr (MODE == EPI_BWD) {
+          constexpr int kStep = kEpiWarps / 4;
+          auto load_acc = [&](int c, float (&v)[16]) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = acc[c][i];
+          };
+          if (e.up == 2)
+            epi_bwd_chunks<2, kChunks, ST, false>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+          else
+            epi_bwd_chunks<1, kChunks, ST, false>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+        } else if (valid) {
 #pragma unroll
           for (int ci = 0; ci < kChunks; ++ci)
             epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + (half + ci * (kEpiWarps / 4)) * 16, acc[ci]);

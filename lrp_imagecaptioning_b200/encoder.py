@@ -140,5 +140,27 @@ class ImageModel(object):
         _lib.check(_lib.load().lrpcap_encoder_profile_read(self.handle(), _lib.dptr(out)))
         return {k: tuple(out[3 * i:3 * i + 3]) for i, k in enumerate(("tc_bwd", "tc_fwd", "simt", "last"))}
 
+    # -- diagnostics for the parity tests (discrete decisions of the resident forward state)
+    def pool_routes(self):
+        """{conv layer index: uint8 [N, H/2, W/2, C]} window position (sy*2+sx) each pooled element routes to."""
+        n = self._state[1]
+        out = {}
+        for l, (_, _, cout, pool) in enumerate(VGG16_CFG):
+            if not pool:
+                continue
+            ho = (self.image_hw >> sum(1 for c in VGG16_CFG[:l] if c[3])) // 2
+            a = np.empty((n, ho, ho, cout), dtype=np.uint8)
+            _lib.check(_lib.load().lrpcap_encoder_debug_pool_routes(self.handle(), l, _lib.c_void_p(a.ctypes.data)))
+            out[l] = a
+        return out
+
+    def multiplier(self, layer, branch=0):
+        """Dense per-image multiplier G of conv layer `layer` (< 12), [N, H, W, C] float32, pool routing folded in."""
+        n = self._state[1]
+        h = self.image_hw >> sum(1 for c in VGG16_CFG[:layer] if c[3])
+        a = np.empty((n, h, h, VGG16_CFG[layer][2]), dtype=np.float32)
+        _lib.check(_lib.load().lrpcap_encoder_debug_multiplier(self.handle(), int(layer), int(branch), _lib.fptr(a)))
+        return a
+
     def launches(self):
         return int(_lib.load().lrpcap_encoder_launches(self.handle()))

@@ -42,7 +42,46 @@ def _conv(x, k_hwio, b):
     return Fn.conv2d(x, w, None if b is None else torch.from_numpy(np.ascontiguousarray(b)), padding=1)
 
 
-def forward(images_nhwc, weights, n_layers=None):
+class Forced(object):
+    """Discrete decisions taken from another implementation's forward pass (tests pin the oracle to them: every rule
+    is discontinuous at max-pool arg-max ties, the gradient family and the Z rule also at ReLU kinks).
+
+    routes: {conv layer index l in POOL_AFTER: uint8 [N, H/2, W/2, C]}, window position sy*2+sx the pool after layer l
+            routes to (instead of torch's own arg-max);
+    masks:  optional {conv layer index: bool [N, H, W, C]} = [z_l > 0] (instead of the oracle's own ReLU decision).
+    """
+
+    def __init__(self, routes=None, masks=None):
+        self.routes = {} if routes is None else {int(l): torch.from_numpy(np.ascontiguousarray(r)).permute(0, 3, 1, 2).long()
+                                                 for l, r in routes.items()}
+        self.masks = {} if masks is None else {int(l): torch.from_numpy(np.ascontiguousarray(m).astype(np.float32)).permute(0, 3, 1, 2).contiguous()
+                                               for l, m in masks.items()}
+
+    def subset(self, idx):
+        f = Forced()
+        idx = torch.as_tensor(np.asarray(idx), dtype=torch.long)
+        f.routes = {l: r[idx] for l, r in self.routes.items()}
+        f.masks = {l: m[idx] for l, m in self.masks.items()}
+        return f
+
+
+def _pool(x, l, force=None):
+    """2x2/2 max-pool after conv layer l; with forced routes the pooled value is x at the forced window position, so
+    that autograd routes the cotangent there (what TF MaxPoolGrad does for the arg-max it found)."""
+    if force is None or l not in force.routes:
+        return Fn.max_pool2d(x, 2, 2)
+    N, C, H, W = x.shape
+    win = x.reshape(N, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(N, C, H // 2, W // 2, 4)
+    return torch.gather(win, 4, force.routes[l].unsqueeze(-1)).squeeze(-1)
+
+
+def _relu(z, l, force=None):
+    if force is None or l not in force.masks:
+        return torch.relu(z)
+    return z * force.masks[l]
+
+
+def forward(images_nhwc, weights, n_layers=None, force=None):
     """Returns list of layer inputs xs[l] (NCHW tensors) and the final post-ReLU features (NHWC)."""
     x = _to_nchw(images_nhwc)
     xs = []
@@ -50,15 +89,42 @@ def forward(images_nhwc, weights, n_layers=None):
     for l in range(n_layers):
         k, b = weights[l]
         xs.append(x)
-        x = torch.relu(_conv(x, k, b))
+        x = _relu(_conv(x, k, b), l, force)
         if l in POOL_AFTER:
             xs.append(x)
-            x = Fn.max_pool2d(x, 2, 2)
+            x = _pool(x, l, force)
     return xs, _to_nhwc(x)
+
+
+def pool_routes(images_nhwc, weights):
+    """The oracle's own arg-max routes, same format as Forced.routes input: {l: uint8 [N, H/2, W/2, C]} (first maximum)."""
+    xs, _ = forward(images_nhwc, weights)
+    out, j = {}, 0
+    for l in range(len(weights)):
+        j += 1
+        if l in POOL_AFTER:
+            x = xs[j]
+            j += 1
+            N, C, H, W = x.shape
+            win = x.reshape(N, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(N, C, H // 2, W // 2, 4)
+            out[l] = torch.argmax((win == win.max(dim=4, keepdim=True).values).to(torch.uint8), dim=4).permute(0, 2, 3, 1).to(torch.uint8).numpy()
+    return out
 
 
 def features(images_nhwc, weights):
     return forward(images_nhwc, weights)[1]
+
+
+def relu_masks(images_nhwc, weights):
+    """The oracle's own ReLU decisions {conv layer l < 12: bool [N, H, W, C]} = [z_l > 0] (same format as Forced.masks)."""
+    xs, _ = forward(images_nhwc, weights)
+    out, j = {}, 0
+    for l in range(len(weights) - 1):
+        j += 1                      # xs[j] is relu(z_l): the pool's input when a pool follows, else the next conv's input
+        out[l] = (xs[j] > 0).permute(0, 2, 3, 1).numpy()
+        if l in POOL_AFTER:
+            j += 1
+    return out
 
 
 def _safe_div(a, b):
@@ -121,14 +187,14 @@ def _infer_alpha_beta(alpha, beta):
     return alpha, beta
 
 
-def analyze(method, images_nhwc, R_head_nhwc, weights, epsilon=1e-7, alpha=None, beta=None, bias=True):
+def analyze(method, images_nhwc, R_head_nhwc, weights, epsilon=1e-7, alpha=None, beta=None, bias=True, force=None):
     """Relevance / gradient of the supplied head tensor at block5_conv3's output, at the input image.
 
     method: 'lrp.epsilon' | 'lrp.z' | 'lrp.alpha_beta' | 'lrp.alpha_1_beta_0' | 'lrp.alpha_2_beta_1' |
             'lrp.z_plus' | 'lrp.z_plus_fast' | 'lrp.sequential_preset_a' |
             'gradient' | 'input_t_gradient' | 'guided_backprop'
     """
-    xs, _ = forward(images_nhwc, weights)
+    xs, _ = forward(images_nhwc, weights, force=force)
     R = _to_nchw(R_head_nhwc)
     img = xs[0]
     if method in ("gradient", "input_t_gradient", "guided_backprop"):
@@ -136,11 +202,11 @@ def analyze(method, images_nhwc, R_head_nhwc, weights, epsilon=1e-7, alpha=None,
         for l in range(len(weights) - 1, -1, -1):
             k, b = weights[l]
             if l in POOL_AFTER:
-                R = _grad(lambda v: Fn.max_pool2d(v, 2, 2), xs[j], R)
+                R = _grad(lambda v: _pool(v, l, force), xs[j], R)
                 j -= 1
             if method == "guided_backprop":
                 R = torch.relu(R)
-            R = _grad(lambda v: torch.relu(_conv(v, k, b)), xs[j], R)
+            R = _grad(lambda v: _relu(_conv(v, k, b), l, force), xs[j], R)
             j -= 1
         if method == "input_t_gradient":
             R = R * img
@@ -162,7 +228,7 @@ def analyze(method, images_nhwc, R_head_nhwc, weights, epsilon=1e-7, alpha=None,
     for l in range(len(weights) - 1, -1, -1):
         k, b = weights[l]
         if l in POOL_AFTER:
-            R = _grad(lambda v: Fn.max_pool2d(v, 2, 2), xs[j], R)
+            R = _grad(lambda v: _pool(v, l, force), xs[j], R)
             j -= 1
         x = xs[j]
         j -= 1

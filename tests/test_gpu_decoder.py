@@ -8,7 +8,7 @@ from tests.util import assert_parity, topk_features
 pytestmark = pytest.mark.gpu
 
 SMALL = dict(V=60, H=64, E=64, D=96, L=16, T=6, N=3)
-FULL = dict(V=1000, H=512, E=512, D=512, L=196, T=8, N=2)
+FULL = dict(V=10000, H=512, E=512, D=512, L=196, T=20, N=2)   # BASELINE.json sizes: V = 10 000, 20 words
 
 
 def _setup(kind, cfg, seed=11):

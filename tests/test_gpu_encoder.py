@@ -1,22 +1,30 @@
 """GPU parity: CUDA encoder relevance (through the C ABI) vs the torch-CPU oracle (oracle/encoder_ref.py).
 
-How the tolerance is applied (tools/oracle_noise.py, profiles/r01_promote_sweep.json):
-every rule is discontinuous at max-pool arg-max ties (and Z / gradient / guided-backprop also at ReLU kinks): an
-activation pair within rounding noise of a tie routes a whole back-propagation path differently.  Two fp32
-implementations therefore agree to ~1e-5 on most images and differ by 1e-3..5e-2 (abs-max-relative, a localized blob)
-on the few where one of the ~1e7 comparisons per image flips -- the fp32 oracle itself moves by 3e-4 (eps) to 9e-3
-(gradient) at 224x224 when recomputed in float64.  So each case runs several independent images and asserts
-  * median over images of the abs-max-relative and L2 errors <= 1e-3   (the north-star tolerance), and
-  * every image <= FLIP_TOL (bounded damage of a flipped decision).
+How the north-star tolerance (per-pixel error <= 1e-3 of the map's abs-max, identical top-k regions, conservation sums to
+1e-4) is applied -- DESIGN.md section 5, tools/diag_parity.py, profiles/r02_diag_parity.jsonl:
+
+Every rule is discontinuous in the forward activations at max-pool arg-max ties, and the gradient family and the Z rule
+also at ReLU kinks: TF's MaxPoolGrad (and torch's) route a whole back-propagation path to whichever window entry compares
+larger, so two correct fp32 forward passes that differ in the last bit of one of ~1.5e6 comparisons per 224 x 224 image
+produce maps that differ by a localized 1e-3..5e-2 blob.  Measured: 0 or 1 of those comparisons flips per image, and with
+the oracle pinned to the decisions the CUDA forward took (oracle Forced: same arg-max routes, same ReLU masks -- exported
+through lrpcap_encoder_debug_pool_routes / _multiplier) EVERY image agrees to <= 1e-3.  So each case asserts, per image:
+  * against the pinned oracle: abs-max-relative error and relative L2 <= tol, conservation sum <= 1e-4, same top-k cells;
+  * against the oracle as-is: the same bounds whenever no decision differs, and otherwise a bounded blob (FLIP_TOL);
+and reports the number of differing decisions.  tol = 1e-3, except the Z rule (R / z without stabiliser amplifies the
+1e-6 forward rounding without bound as z -> 0; 3e-3; not a north-star rule).
 """
 import numpy as np
 import pytest
 
-from tests.util import assert_parity, linf_rel, l2_rel, record, topk_cells
+from tests.util import assert_parity, linf_rel, l2_rel, record, sum_err, topk_cells
 
 pytestmark = pytest.mark.gpu
 
 FLIP_TOL = 8e-2
+SUM_TOL = 1e-4
+MASK_RULES = ("z", "gradient", "ixg", "guided")     # rules whose multipliers are ReLU masks: discontinuous at z = 0
+TOL = {"z": 3e-3}
 
 RULES = {
     # name: (oracle method, oracle kwargs, analyzer name, analyzer kwargs)
@@ -48,15 +56,60 @@ def _head(model, x, idx, seed):
     return F, (F[idx] * g.standard_normal((len(idx),) + F.shape[1:])).astype(np.float32)
 
 
-def _assert_robust(got, ref, what, **extra):
-    li = [linf_rel(g, r) for g, r in zip(got, ref)]
-    l2 = [l2_rel(g, r) for g, r in zip(got, ref)]
-    for i, (g, r) in enumerate(zip(got, ref)):
-        record("%s item %d" % (what, i), g, r, **extra)
-    assert np.median(li) <= 1e-3, "%s: median abs-max-relative error %.3e > 1e-3 (all: %s)" % (what, np.median(li), li)
-    assert np.median(l2) <= 1e-3, "%s: median L2 error %.3e > 1e-3 (all: %s)" % (what, np.median(l2), l2)
-    assert max(li) <= FLIP_TOL, "%s: worst abs-max-relative error %.3e > %.0e" % (what, max(li), FLIP_TOL)
-    return li, l2
+def _decisions(m, x, W, rule):
+    """(Forced built from the CUDA forward state, per-image count of decisions that differ from the oracle's own)."""
+    from oracle import encoder_ref as ER
+    routes = m.pool_routes()
+    own = ER.pool_routes(x, W)
+    n = x.shape[0]
+    flips = np.zeros(n, dtype=np.int64)
+    for l in routes:
+        flips += (routes[l] != own[l]).reshape(n, -1).sum(axis=1)
+    masks = None
+    if rule in MASK_RULES:
+        masks = {l: m.multiplier(l) != 0 for l in range(12)}
+        own_m = ER.relu_masks(x, W)
+        for l in masks:
+            mine = masks[l]
+            theirs = own_m[l]
+            if l in routes:      # the exported multiplier is zero away from the arg-max: compare where it routes
+                theirs = theirs & _argmax_positions(routes[l], theirs.shape)
+            flips += (mine != theirs).reshape(n, -1).sum(axis=1)
+    return ER.Forced(routes, masks), flips
+
+
+def _argmax_positions(routes, shape):
+    """bool [N, H, W, C]: True at the window position each pooled element routes to."""
+    N, H, W, C = shape
+    keep = np.zeros(shape, dtype=bool)
+    win = keep.reshape(N, H // 2, 2, W // 2, 2, C)
+    for p in range(4):
+        sel = routes == p
+        win[:, :, p >> 1, :, p & 1, :] = sel
+    return keep
+
+
+def _assert_pinned(got, ref_pinned, ref_plain, flips, what, rule, topk=10, head=None, **extra):
+    """Per image: the pinned-oracle bounds always; the plain-oracle bounds when no discrete decision differs.
+    head: the head relevance fed in; its mass enters the conservation denominator (tests/util.py: sum_err)."""
+    tol = TOL.get(rule, 1e-3)
+    rows = []
+    for i in range(len(got)):
+        mp = record("%s item %d pinned" % (what, i), got[i], ref_pinned[i], rule=rule, flips=int(flips[i]), **extra)
+        mo = record("%s item %d as-is" % (what, i), got[i], ref_plain[i], rule=rule, flips=int(flips[i]), **extra)
+        se = mp["sum_err"] if head is None else sum_err(got[i], ref_pinned[i], mass=np.abs(head[i]).astype(np.float64).sum())
+        rows.append((int(flips[i]), mp["linf_rel"], mp["l2_rel"], se, mo["linf_rel"]))
+    for i, (nf, li, l2, se, lo) in enumerate(rows):
+        assert li <= tol and l2 <= tol, "%s image %d: pinned error linf %.3e l2 %.3e > %.0e (rows: %s)" % (what, i, li, l2, tol, rows)
+        assert se <= SUM_TOL, "%s image %d: conservation sum differs by %.3e > 1e-4 (rows: %s)" % (what, i, se, rows)
+        if topk and got[i].shape[0] >= 64:
+            k = topk if got[i].shape[0] >= 224 else 5
+            assert topk_cells(got[i], k) == topk_cells(ref_pinned[i], k), "%s image %d: top-%d cells differ" % (what, i, k)
+        if nf == 0:
+            assert lo <= tol, "%s image %d: no decision differs but the plain oracle is %.3e away" % (what, i, lo)
+        else:
+            assert lo <= FLIP_TOL, "%s image %d: %d flipped decisions moved the map by %.3e" % (what, i, nf, lo)
+    return rows
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
@@ -86,13 +139,12 @@ def test_relevance_matches_oracle_small(hw, rule, precision):
     m = ImageModel(W, image_hw=hw, precision=precision)
     F, R = _head(m, x, idx, 2)
     om, okw, an, akw = RULES[rule]
-    ref = ER.analyze(om, x[idx], R, W, **okw)
     got = create_analyzer(an, m, **akw).analyze_batch(x, idx, R).cpu().numpy()
+    force, flips = _decisions(m, x, W, rule)
+    ref = ER.analyze(om, x[idx], R, W, **okw)
+    ref_p = ER.analyze(om, x[idx], R, W, force=force, **okw)
     assert got.shape == ref.shape == (n, hw, hw, 3)
-    li, _ = _assert_robust(got, ref, "%s hw=%d %s" % (rule, hw, precision), rule=rule, hw=hw, precision=precision)
-    if hw >= 64:
-        same = [topk_cells(got[w], 5) == topk_cells(ref[w], 5) for w in range(n) if li[w] <= 1e-3]
-        assert all(same)
+    _assert_pinned(got, ref_p, ref, flips, "%s hw=%d %s" % (rule, hw, precision), rule, head=R, hw=hw, precision=precision)
 
 
 def test_words_of_one_image_share_the_forward_state():
@@ -125,7 +177,9 @@ def test_analyze_replace_mode_api():
     F, R = _head(m, x, idx, 3)
     out = LRPSequentialPresetA(m, epsilon=0.01, neuron_selection_mode="replace").analyze([x, R])
     assert isinstance(out, np.ndarray) and out.shape == x.shape
-    _assert_robust(out, ER.analyze("lrp.sequential_preset_a", x, R, W), "analyze()")
+    force, flips = _decisions(m, x, W, "presetA")
+    _assert_pinned(out, ER.analyze("lrp.sequential_preset_a", x, R, W, force=force),
+                   ER.analyze("lrp.sequential_preset_a", x, R, W), flips, "analyze()", "presetA")
 
 
 def test_chunking_is_invisible():
@@ -143,12 +197,12 @@ def test_chunking_is_invisible():
     assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("rule,precision", [("presetA", "bf16x3"), ("eps", "bf16x3"), ("presetA", "fp32"), ("eps", "fp32"), ("a2b1", "bf16x3"),
+@pytest.mark.parametrize("rule,precision", [("presetA", "bf16x3"), ("eps", "bf16x3"), ("presetA", "fp32"), ("eps", "fp32"),
+                                            ("a2b1", "bf16x3"), ("zplus", "bf16x3"), ("z", "bf16x3"), ("gradient", "bf16x3"),
                                             ("guided", "bf16x3"), ("ixg", "bf16x3")])
 def test_relevance_matches_oracle_224(rule, precision):
-    """BASELINE.json full image size.  Three images, one word each; ~4e7 discrete decisions per image, so a flipped
-    tie is the rule rather than the exception here: the L2 error (which a localized blob barely moves) carries the
-    1e-3-class check, the abs-max error is bounded by FLIP_TOL."""
+    """BASELINE.json full image size, three images: every image within tolerance of the oracle pinned to the CUDA
+    forward's arg-max routes (and ReLU masks for the mask rules), identical top-10 cells, sums to 1e-4."""
     from lrp_imagecaptioning_b200 import synth
     from lrp_imagecaptioning_b200.encoder import ImageModel
     from lrp_imagecaptioning_b200.analyzers import create_analyzer
@@ -160,17 +214,11 @@ def test_relevance_matches_oracle_224(rule, precision):
     m = ImageModel(W, image_hw=224, precision=precision)
     F, R = _head(m, x, idx, 5)
     om, okw, an, akw = RULES[rule]
-    ref = ER.analyze(om, x[idx], R, W, **okw)
     got = create_analyzer(an, m, **akw).analyze_batch(x, idx, R).cpu().numpy()
-    li = [linf_rel(got[w], ref[w]) for w in range(n)]
-    l2 = [l2_rel(got[w], ref[w]) for w in range(n)]
-    for w in range(n):
-        record("%s 224 %s image %d" % (rule, precision, w), got[w], ref[w], rule=rule, hw=224, precision=precision)
-    assert np.median(l2) <= 5e-3, (li, l2)
-    assert max(li) <= FLIP_TOL, (li, l2)
-    if rule == "presetA":
-        assert np.median(l2) <= 1e-3 and np.median(li) <= 5e-3, (li, l2)
-        assert sum(topk_cells(got[w], 10) == topk_cells(ref[w], 10) for w in range(n)) >= 2
+    force, flips = _decisions(m, x, W, rule)
+    ref = ER.analyze(om, x[idx], R, W, **okw)
+    ref_p = ER.analyze(om, x[idx], R, W, force=force, **okw)
+    _assert_pinned(got, ref_p, ref, flips, "%s 224 %s" % (rule, precision), rule, hw=224, precision=precision)
 
 
 def test_conservation_bias_free_224_property():

@@ -46,9 +46,16 @@ def floor_rel(got, ref, floor=1e-3):
     return float(np.max(np.abs(got - ref) / (np.abs(ref) + floor * scale)))
 
 
-def sum_err(got, ref):
+def sum_err(got, ref, mass=None):
+    """Relevance-conservation error: |sum(got) - sum(ref)| relative to the relevance mass sum|ref|.  `mass` (optional):
+    the mass that was fed in, sum|R_head| -- a synthetic mixed-sign head can cancel to a map whose own mass is hundreds of
+    times smaller than what was propagated, and the rounding of the propagation is relative to the latter; the
+    denominator is then the larger of the two masses."""
     got, ref = _f64(got), _f64(ref)
-    return float(abs(got.sum() - ref.sum()) / (np.abs(ref).sum() + 1e-300))
+    den = np.abs(ref).sum()
+    if mass is not None:
+        den = max(den, float(mass))
+    return float(abs(got.sum() - ref.sum()) / (den + 1e-300))
 
 
 def topk_cells(R, k=10, cell=16):

@@ -32,6 +32,13 @@ extern "C" {
                                  * for the per-word relevance messages, two IEEE half planes (22 bits; automatic fall-back
                                  * to three bf16 planes outside the half range) for the per-image forward */
 
+#define LRPCAP_PREC_F16X2_TC 2  /* as BF16X3_TC, but the per-word relevance messages are ONE fp16 plane scaled by a power of
+                                 * two per word and layer, against two fp16 weight planes: 2 products per MAC instead of 3
+                                 * and half the message bytes; 11-bit messages (alpha-beta family: 2e-5 maps) */
+
+#define LRPCAP_PREC_TC_AUTO 3   /* tensor cores, products per rule: two for the alpha-beta family / z+ (same-sign chains),
+                                 * three for epsilon, z and the gradient family (mixed-sign chains need the 16-bit message) */
+
 /* encoder rules; replaces the iNNvestigate analyzer classes constructed in
  * models/explainers.py:32,671,883,928 (LRPSequentialPresetA, Gradient, InputTimesGradient, GuidedBackprop) and
  * innvestigate/analyzer/relevance_based/relevance_analyzer.py:531-721 */
@@ -59,6 +66,12 @@ int lrpcap_version(void);
  * block1_conv1 .. block5_conv3.  image_hw: 224 (any multiple of 16 is accepted). */
 int lrpcap_encoder_create(lrpcap_encoder_t** out, const float* const* h_kernels_hwio, const float* const* h_biases,
                           int image_hw, int precision);
+/* Other encoders the reference offers (models/model.py:419-429, `img_encoder`): arch LRPCAP_ENCODER_VGG16 (13 convs) or
+ * LRPCAP_ENCODER_VGG19 (16 convs: block1_conv1 .. block5_conv4), both cut at their last conv layer (14 x 14 x 512 head). */
+#define LRPCAP_ENCODER_VGG16 0
+#define LRPCAP_ENCODER_VGG19 1
+int lrpcap_encoder_create_arch(lrpcap_encoder_t** out, int arch, const float* const* h_kernels_hwio,
+                               const float* const* h_biases, int image_hw, int precision);
 /* Replaces the weights of an existing handle in place (same layouts as lrpcap_encoder_create) and invalidates the
  * per-image state: what `LRPInferenceLayer*` needs between fine-tuning steps (train.py:569-577), where the reference
  * explains the model that is being trained; the large state and message buffers are kept. Synchronises the device. */
@@ -128,8 +141,10 @@ int lrpcap_decoder_destroy(lrpcap_decoder_t* dec);
 /* Replaces `_forward_beam_search(X, caption)` (explainers.py:370-436, 690-778, 1092-1178, 1344-1450) for a batch:
  * teacher-forced decoder forward over T steps storing every intermediate the relevance pass reads.
  * d_features: [n_images, L, D]; h_captions: [n_images, T] tokenizer ids (model index = id - 1).
- * greedy != 0: h_captions is an OUTPUT -- token t is the arg-max of step t's logits (EOS never suppressed here;
- * pass eos_token < 0 to disable; when >= 0 that id is excluded from the arg-max so every caption has T words). */
+ * greedy != 0: h_captions is an OUTPUT -- token t is the arg-max of step t's logits. eos_token >= 1: that tokenizer id is
+ * excluded from the arg-max (every caption then has exactly T words); eos_token <= 0: plain arg-max. Captions are never
+ * truncated at EOS: every image has T positions, and a caller that wants the reference's "stop at EOS" restricts the word
+ * list it passes to lrpcap_decoder_relevance itself. */
 int lrpcap_decoder_forward(lrpcap_decoder_t* dec, const float* d_features, int n_images, int L, int* h_captions, int T,
                            int greedy, int eos_token, void* stream);
 
@@ -209,9 +224,15 @@ int lrpcap_bbox_correctness(const float* d_heatmaps, int n_maps, int hw, const i
  * Both synchronise the device. */
 int lrpcap_encoder_debug_pool_routes(lrpcap_encoder_t* enc, int layer, unsigned char* h_routes);
 int lrpcap_encoder_debug_multiplier(lrpcap_encoder_t* enc, int layer, int branch, float* h_G);
+/* Two-product backward: the power-of-two scale bookkeeping of the LAST chunk of the last lrpcap_encoder_relevance call.
+ * h_max [layers + 1][*chunk]: largest |stored fp16 value| of the message entering conv layer l's transposed conv, per
+ * word (row `layers`: the seed's true maximum); h_kt [layers][*chunk]: log2 of that message's scale. cap_words: room (in
+ * words) of both arrays; *chunk = words of that chunk, 0 when the handle does not run the two-product path. */
+int lrpcap_encoder_debug_message_scales(lrpcap_encoder_t* enc, float* h_max, int* h_kt, int cap_words, int* chunk);
 /* Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
  * precision: LRPCAP_PREC_FP32_SIMT; LRPCAP_PREC_BF16X3_TC (two bf16 planes: the backward arithmetic); 2 = three bf16
- * planes, promoted; 3 = two IEEE half planes, promoted (the forward arithmetic).
+ * planes, promoted; 3 = two IEEE half planes, promoted (the forward arithmetic); 4 = the two-product backward arithmetic
+ * (A rounded to one fp16 plane x two fp16 weight planes).
  * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblrpcap.so")
 
 OK = 0
-PREC_FP32_SIMT, PREC_BF16X3_TC = 0, 1
+PREC_FP32_SIMT, PREC_BF16X3_TC, PREC_F16X2_TC, PREC_TC_AUTO = 0, 1, 2, 3
 RULE_EPSILON, RULE_Z, RULE_ALPHA_BETA, RULE_ZPLUS_FAST, RULE_GRADIENT, RULE_INPUT_T_GRADIENT, RULE_GUIDED_BACKPROP = range(7)
 DECODER_ADAPTIVE, DECODER_GRIDTD = 0, 1
 
@@ -40,6 +40,7 @@ PROTOTYPES = {
     "lrpcap_last_error": (ctypes.c_char_p, []),
     "lrpcap_version": (ctypes.c_int, []),
     "lrpcap_encoder_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), ctypes.c_int, ctypes.c_int]),
+    "lrpcap_encoder_create_arch": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.c_int, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), ctypes.c_int, ctypes.c_int]),
     "lrpcap_encoder_set_weights": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p)]),
     "lrpcap_encoder_destroy": (ctypes.c_int, [c_void_p]),
     "lrpcap_encoder_forward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_void_p]),
@@ -68,6 +69,7 @@ PROTOTYPES = {
     "lrpcap_bbox_correctness": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, c_float_p, ctypes.c_int, c_float_p, c_void_p]),
     "lrpcap_encoder_debug_pool_routes": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p]),
     "lrpcap_encoder_debug_multiplier": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_float_p]),
+    "lrpcap_encoder_debug_message_scales": (ctypes.c_int, [c_void_p, c_float_p, c_int_p, ctypes.c_int, c_int_p]),
     "lrpcap_debug_conv": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p]),
 }
 

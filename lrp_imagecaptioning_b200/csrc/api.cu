@@ -33,6 +33,15 @@ int lrpcap_encoder_create(lrpcap_encoder_t** out, const float* const* h_kernels_
   return kOk;
 }
 
+int lrpcap_encoder_create_arch(lrpcap_encoder_t** out, int arch, const float* const* h_kernels_hwio,
+                               const float* const* h_biases, int image_hw, int precision) {
+  LRPCAP_REQUIRE(out != nullptr, kErrInvalidArg, "encoder_create_arch: null out");
+  Encoder* e = nullptr;
+  LRPCAP_TRY(Encoder::create(&e, h_kernels_hwio, h_biases, image_hw, precision, arch));
+  *out = new lrpcap_encoder{e};
+  return kOk;
+}
+
 int lrpcap_encoder_set_weights(lrpcap_encoder_t* enc, const float* const* h_kernels_hwio, const float* const* h_biases) {
   LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_set_weights: null handle");
   return enc->impl->set_weights(h_kernels_hwio, h_biases);
@@ -136,6 +145,11 @@ int lrpcap_encoder_debug_multiplier(lrpcap_encoder_t* enc, int layer, int branch
   return enc->impl->debug_multiplier(layer, branch, h_G);
 }
 
+int lrpcap_encoder_debug_message_scales(lrpcap_encoder_t* enc, float* h_max, int* h_kt, int cap_words, int* chunk) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_debug_message_scales: null handle");
+  return enc->impl->debug_message_scales(h_max, h_kt, cap_words, chunk);
+}
+
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out) {
   LRPCAP_REQUIRE(h_A && h_B && h_out, kErrInvalidArg, "debug_conv: null argument");
@@ -154,13 +168,15 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
     EpiParams ep;
     ep.mode = EPI_RAW;
     ep.out_f32 = dO.as<float>();
-    if (precision == PREC_BF16X3_TC || precision == 2 || precision == 3) {
-      // 2: three bf16 planes (the forward pass's arithmetic); 3: two IEEE half planes, promoted (optional forward mode)
-      const int planes = precision == 2 ? 3 : precision == 3 ? kPlanesF16x2 : 2;
+    if (precision == PREC_BF16X3_TC || precision == 2 || precision == 3 || precision == 4) {
+      // 2: three bf16 planes (the forward pass's arithmetic); 3: two IEEE half planes, promoted (optional forward mode);
+      // 4: two-product backward arithmetic (A rounded to ONE fp16 plane x two fp16 weight planes)
+      const int planes = precision == 2 ? 3 : precision == 3 ? kPlanesF16x2 : precision == 4 ? kPlanesH1x2 : 2;
+      const int store_planes = planes == kPlanesH1x2 ? kPlanesF16x2 : planes;
       LRPCAP_TRY(sA.ensure(nA * 2 * 3));
       LRPCAP_TRY(sB.ensure(nB * 2 * 3));
-      LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0, planes));
-      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps, planes));
+      LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0, store_planes));
+      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps, store_planes));
       TcConvArgs a;
       a.A = sA.p; a.A_elems = nA; a.n_items = items; a.H = H; a.W = W; a.C = C;
       a.B = sB.p; a.B_elems = nB; a.taps = taps; a.Nout = Nout; a.planes = planes; a.epi = ep;

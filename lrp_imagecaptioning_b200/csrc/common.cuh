@@ -82,6 +82,7 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t
 // ---- split-fp16 storage (forward activations / weights, optional): v ~= float(hi) + float(lo) with two IEEE half planes,
 //      22 mantissa bits inside the half range (|v| < 65504; lo underflows gradually below |v| ~ 0.1).  Plane code 4. ----
 constexpr int kPlanesF16x2 = 4;
+constexpr int kPlanesH1x2 = 5;    // two-product backward: A one fp16 plane, B two fp16 planes
 __device__ __forceinline__ void split2h(float a, float b, uint32_t& hi2, uint32_t& lo2) {
   const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
   const __half al = __float2half_rn(a - __half2float(ah)), bl = __float2half_rn(b - __half2float(bh));

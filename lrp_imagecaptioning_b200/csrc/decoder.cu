@@ -1,6 +1,7 @@
 // Decoder: batched forward with stored state + batched word-level relevance (see decoder.cuh).
 #include "decoder.cuh"
 #include "decoder_kernels.cuh"
+#include "decoder_fused.cuh"
 #include "tc_conv.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -25,7 +26,8 @@ Decoder::~Decoder() {
   DevBuf* bufs[] = {&F_, &Vp_, &P_, &a_, &gp_, &tok_, &logitk_, &logits_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_,
                     &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
                     &Z_, &hp_, &sg_, &sp_, &e_, &hc_, &d_wimg_, &d_wt_, &d_order_, &Rh1_, &Rh2_, &Rh2n_, &Rc1_, &Rc2_,
-                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_, &As_, &C32_, &As3_};
+                    &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_, &As_, &C32_, &As3_,
+                    &Axh_, &Ahs_, &Axh2_, &Ahc_, &C1_, &C2_, &C3_, &C4_, &Vf32_};
   for (DevBuf* b : bufs) b->release();
 }
 
@@ -109,6 +111,19 @@ int Decoder::gemm_tc(const double* A, int M, int K, const void* Bsplit, int N, d
   return kOk;
 }
 
+int Decoder::gemm_tc_direct(int M, int K, size_t nA, const void* Bsplit, int N, cudaStream_t s) {
+  if (M <= 0) return kOk;
+  const int Hrows = (M + 15) / 16;   // rows beyond M hold stale data: every output row depends on its own A row only
+  TcConvArgs a;
+  a.A = As_.p; a.A_elems = nA; a.n_items = 1; a.H = Hrows; a.W = 16; a.C = K;
+  a.B = Bsplit; a.B_elems = (size_t)N * K; a.taps = 1; a.Nout = N;
+  a.epi.mode = EPI_RAW;
+  a.epi.out_f32 = C32_.as<float>();
+  LRPCAP_TRY(tc_conv_launch(a, s));
+  ++launches_;
+  return kOk;
+}
+
 int Decoder::split3_weights(const double* d_Wt, int N, int K, int* Npad, void** out) {
   const int np = (N + 63) / 64 * 64;
   void* p = nullptr;
@@ -140,6 +155,18 @@ int Decoder::gemm_tc3(const double* A, int lda, int M, int K, const void* B3, in
   f32_to_f64_bias_kernel<<<nblk((size_t)M * N, 256), 256, 0, s>>>(C32_.as<float>(), Npad, C, ldc, M, N, bias);
   launches_ += 3;
   LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int Decoder::tc3(const void* A3, int Mpad, int K, const void* B3, int Npad, float* C32, cudaStream_t s) {
+  TcConvArgs a;
+  a.A = A3; a.A_elems = (size_t)Mpad * K; a.n_items = 1; a.H = Mpad / 16; a.W = 16; a.C = K;
+  a.B = B3; a.B_elems = (size_t)Npad * K; a.taps = 1; a.Nout = Npad;
+  a.planes = 3;
+  a.epi.mode = EPI_RAW;
+  a.epi.out_f32 = C32;
+  LRPCAP_TRY(tc_conv_launch(a, s));
+  ++launches_;
   return kOk;
 }
 
@@ -234,6 +261,31 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
       if (w->kind == LRPCAP_DECODER_GRIDTD) UP(d->split3_weights(d->Wcat2T_, 4 * H, d->Kin2_, &d->G4pad_, &d->Wcat2TC3_));
       UP(d->split3_weights(d->WoT_, V, H, &d->Vpad_, &d->WoTC3_));
       d->tc_forward_ = true;
+      const char* fv = getenv("LRPCAP_DECODER_FUSED");
+      if (!(fv && fv[0] == '0') && D % 64 == 0) {
+        // rows [W_cat1^T ; W_sx^T] (gates | sentinel gate) and [W_hp^T ; W_ss^T] as single B operands
+        const bool ad = w->kind == LRPCAP_DECODER_ADAPTIVE;
+        const int K1 = d->Kin1_;
+        double *sxT = nullptr, *hpT = nullptr, *ssT = nullptr, *pT = nullptr, *cat = nullptr;
+        UP(d->upload_cat(ad ? w->Wx : w->W_x, K1 - H, ad ? w->Wh : w->W_h, H, H, 0, H, true, &sxT));
+        UP(d->upload_t(ad ? w->Wg : w->W_ha, H, H, &hpT));
+        UP(d->upload_t(ad ? w->Ws : w->W_s, H, H, &ssT));
+        UP(d->upload_t(ad ? w->Wv : w->W_va, H, H, &pT));
+        if (cudaMalloc(&cat, (size_t)5 * H * K1 * sizeof(double)) != cudaSuccess) {
+          set_last_error("decoder_create: device allocation failed");
+          return fail(kErrCuda);
+        }
+        d->owned_.push_back(cat);
+        cudaMemcpy(cat, d->Wcat1T_, (size_t)4 * H * K1 * sizeof(double), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(cat + (size_t)4 * H * K1, sxT, (size_t)H * K1 * sizeof(double), cudaMemcpyDeviceToDevice);
+        UP(d->split3_weights(cat, 5 * H, K1, &d->Npad1_, &d->W1cat3_));
+        cudaMemcpy(cat, hpT, (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice);
+        cudaMemcpy(cat + (size_t)H * H, ssT, (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice);
+        UP(d->split3_weights(cat, 2 * H, H, &d->Npad2_, &d->W2cat3_));
+        UP(d->split3_weights(d->WifT_, H, D, &d->Hpad_, &d->WifTC3_));
+        UP(d->split3_weights(pT, H, H, &d->Hpad_, &d->WpTC3_));
+        d->fused_ = true;
+      }
     }
   }
 #undef UP
@@ -303,6 +355,24 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   LRPCAP_TRY(sp_.ensure((size_t)N * H * 8));
   LRPCAP_TRY(e_.ensure((size_t)N * (L + 1) * 8));
   LRPCAP_TRY(hc_.ensure((size_t)N * H * 8));
+  const bool fused = fused_ && L <= 256;
+  const int Mpad = (N + 15) / 16 * 16, Mpad2 = (2 * N + 15) / 16 * 16;
+  const size_t nAxh = (size_t)Mpad * Kin1_, nAhs = (size_t)Mpad2 * H, nAxh2 = (size_t)Mpad * (td ? Kin2_ : 0), nAhc = (size_t)Mpad * H;
+  if (fused) {
+    LRPCAP_TRY(Axh_.ensure(nAxh * 3 * sizeof(__nv_bfloat16)));
+    LRPCAP_TRY(Ahs_.ensure(nAhs * 3 * sizeof(__nv_bfloat16)));
+    LRPCAP_TRY(Ahc_.ensure(nAhc * 3 * sizeof(__nv_bfloat16)));
+    if (td) LRPCAP_TRY(Axh2_.ensure(nAxh2 * 3 * sizeof(__nv_bfloat16)));
+    LRPCAP_TRY(C1_.ensure((size_t)Mpad * Npad1_ * sizeof(float)));
+    LRPCAP_TRY(C2_.ensure((size_t)Mpad2 * Npad2_ * sizeof(float)));
+    if (td) LRPCAP_TRY(C3_.ensure((size_t)Mpad * G4pad_ * sizeof(float)));
+    if (greedy) LRPCAP_TRY(C4_.ensure((size_t)Mpad * Vpad_ * sizeof(float)));
+    LRPCAP_TRY(Vf32_.ensure(NL * H * sizeof(float)));
+    // the startup GEMMs (M = N * L rows) go through gemm_tc3: size its scratch here, outside any graph capture
+    const size_t mp = (NL + 15) / 16 * 16;
+    LRPCAP_TRY(As3_.ensure(mp * std::max(D, H) * 3 * sizeof(__nv_bfloat16)));
+    LRPCAP_TRY(C32_.ensure(mp * Hpad_ * sizeof(float)));
+  }
   if (greedy) LRPCAP_TRY(logits_.ensure((size_t)N * V * 8));
   else LRPCAP_CUDA(cudaMemcpyAsync(tok_.p, h_captions, (size_t)N * T * sizeof(int), cudaMemcpyHostToDevice, s));
 
@@ -318,17 +388,61 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   LRPCAP_CUDA(cudaMemsetAsync(beta_.p, 0, (size_t)N * (T + 1) * 8, s));
   double *F = F_.as<double>(), *Vp = Vp_.as<double>(), *P = P_.as<double>(), *Vf = UV_.as<double>();
   // image_features / global_img_feature heads (explainers.py:375-388); F was filled from d_features by the caller part
-  LRPCAP_TRY(gemm(F, D, Wif_, H, Vp, H, (int)NL, H, D, bif_, s));
+  if (fused) LRPCAP_TRY(gemm_tc3(F, D, (int)NL, D, WifTC3_, Hpad_, H, bif_, Vp, H, s));
+  else LRPCAP_TRY(gemm(F, D, Wif_, H, Vp, H, (int)NL, H, D, bif_, s));
   round_f32_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, NL * H);   // rows are float32 results in the reference
   relu_copy_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, Vf, NL * H);
-  LRPCAP_TRY(gemm(Vf, H, Wp_, H, P, H, (int)NL, H, H, nullptr, s));
+  if (fused) {
+    LRPCAP_TRY(gemm_tc3(Vf, H, (int)NL, H, WpTC3_, Hpad_, H, nullptr, P, H, s));
+    relu_f32_copy_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, Vf32_.as<float>(), NL * H);
+    ++launches_;
+    LRPCAP_CUDA(cudaMemsetAsync(Axh_.p, 0, nAxh * 3 * sizeof(__nv_bfloat16), s));   // rows >= N of the A operands stay zero
+    LRPCAP_CUDA(cudaMemsetAsync(Ahs_.p, 0, nAhs * 3 * sizeof(__nv_bfloat16), s));
+    LRPCAP_CUDA(cudaMemsetAsync(Ahc_.p, 0, nAhc * 3 * sizeof(__nv_bfloat16), s));
+    if (td) LRPCAP_CUDA(cudaMemsetAsync(Axh2_.p, 0, nAxh2 * 3 * sizeof(__nv_bfloat16), s));
+  } else {
+    LRPCAP_TRY(gemm(Vf, H, Wp_, H, P, H, (int)NL, H, H, nullptr, s));
+  }
   mean_feat_kernel<<<N, 256, 0, s>>>(F, a_.as<double>(), L, D);
   LRPCAP_TRY(gemm(a_.as<double>(), D, Wgf_, E, gp_.as<double>(), E, N, E, D, bgf_, s));
   round_f32_kernel<<<nblk((size_t)N * E, 256), 256, 0, s>>>(gp_.as<double>(), (size_t)N * E);
   launches_ += 4;
 
   int* tok = tok_.as<int>();
-  for (int i = 0; i < T; ++i) {
+  for (int i = 0; fused && i < T; ++i) {   // fused step: 9 launches (grid-TD, greedy); see decoder_fused.cuh
+    __nv_bfloat16 *Axh = Axh_.as<__nv_bfloat16>(), *Ahs = Ahs_.as<__nv_bfloat16>(), *Ahc = Ahc_.as<__nv_bfloat16>();
+    __nv_bfloat16* Axh2 = td ? Axh2_.as<__nv_bfloat16>() : nullptr;
+    fwd_xh_kernel<<<N, 256, 0, s>>>(XH1_.as<double>(), Axh, nAxh, Emb_, gp_.as<double>(), h1_.as<double>(),
+                                    td ? h2_.as<double>() : nullptr, tok, i, T, H, E, sos_, td ? 1 : 0);
+    LRPCAP_TRY(tc3(Axh, Mpad, Kin1_, W1cat3_, Npad1_, C1_.as<float>(), s));
+    fwd_lstm_kernel<<<N, 256, 0, s>>>(C1_.as<float>(), Npad1_, b1_, h1_.as<double>(), c1_.as<double>(), zg1_.as<double>(),
+                                      ia1_.as<double>(), fa1_.as<double>(), ga1_.as<double>(), oa1_.as<double>(),
+                                      s_.as<double>(), Ahs, nAhs, N, nullptr, nullptr, nullptr, 0, 0, i, T, H);
+    LRPCAP_TRY(tc3(Ahs, Mpad2, H, W2cat3_, Npad2_, C2_.as<float>(), s));
+    fwd_scores_kernel<<<dim3((L + 1 + 7) / 8, N), 256, 0, s>>>(P, C2_.as<float>(), Npad2_, N, Va_, e_.as<double>(), L, H);
+    fwd_ctx_kernel<<<dim3(N, H / 64), 256, 0, s>>>(Vf32_.as<float>(), e_.as<double>(), alpha_.as<double>(), beta_.as<double>(),
+                                                   s_.as<double>(), ctx_.as<double>(), chat_.as<double>(), h1_.as<double>(),
+                                                   td ? h2_.as<double>() : nullptr, td ? nullptr : hc_.as<double>(),
+                                                   td ? nullptr : Ahc, nAhc, td ? XH2_.as<double>() : nullptr, Axh2, nAxh2,
+                                                   i, T, L, H);
+    launches_ += 4;
+    if (td) {
+      LRPCAP_TRY(tc3(Axh2, Mpad, Kin2_, Wcat2TC3_, G4pad_, C3_.as<float>(), s));
+      fwd_lstm_kernel<<<N, 256, 0, s>>>(C3_.as<float>(), G4pad_, b2_, h2_.as<double>(), c2_.as<double>(), zg2_.as<double>(),
+                                        ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(), nullptr,
+                                        nullptr, 0, N, chat_.as<double>(), hc_.as<double>(), Ahc, nAhc, keras_logits_, i, T, H);
+      ++launches_;
+    }
+    if (greedy) {
+      LRPCAP_TRY(tc3(Ahc, Mpad, H, WoTC3_, Vpad_, C4_.as<float>(), s));
+      fwd_argmax_kernel<<<N, 256, 0, s>>>(C4_.as<float>(), Vpad_, bo_, V, eos_token >= 1 ? eos_token - 1 : -1, tok,
+                                          logitk_.as<double>(), i, T);
+    } else {
+      logitk_kernel<<<N, 128, 0, s>>>(hc_.as<double>(), WoT_, bo_, tok, logitk_.as<double>(), i, T, H);
+    }
+    ++launches_;
+  }
+  for (int i = 0; !fused && i < T; ++i) {
     build_xh_kernel<<<N, 256, 0, s>>>(XH1_.as<double>(), Emb_, gp_.as<double>(), h1_.as<double>(),
                                       td ? h2_.as<double>() : nullptr, tok, i, T, H, E, sos_, td ? 1 : 0);
     const double* xh = XH1_.as<double>() + (size_t)i * Kin1_;
@@ -385,7 +499,7 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
     mix((uint64_t)(uintptr_t)s);
     DevBuf* all[] = {&F_, &Vp_, &P_, &UV_, &a_, &gp_, &tok_, &logitk_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_, &ctx_, &s_,
                      &chat_, &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &XH1_, &XH2_, &alpha_, &beta_, &Z_, &hp_, &sg_,
-                     &sp_, &e_, &hc_, &logits_, &gemm_ws_, &As3_, &C32_};
+                     &sp_, &e_, &hc_, &logits_, &gemm_ws_, &As3_, &C32_, &Axh_, &Ahs_, &Axh2_, &Ahc_, &C1_, &C2_, &C3_, &C4_, &Vf32_};
     for (DevBuf* b : all) mix((uint64_t)(uintptr_t)b->p);
     // the legacy default stream cannot be captured: graphs run on a private stream ordered after / before it by events
     cudaStream_t gs = s;
@@ -554,6 +668,14 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
   }
   WordRef wr{d_wimg_.as<int>(), d_wt_.as<int>()};
   const int* tok = tok_.as<int>();
+  // direct path: the cell kernel writes the gate GEMM's bf16 planes, the scatter kernels read its fp32 result
+  const bool direct = Wgate1TC_ && (!td || Wgate2TC_) && !getenv("LRPCAP_DECODER_FUSED_OFF");
+  const size_t nAs = (size_t)((W + 15) / 16) * 16 * H;
+  if (direct) {
+    LRPCAP_TRY(As_.ensure(nAs * 4));
+    LRPCAP_TRY(C32_.ensure((size_t)((W + 15) / 16) * 16 * std::max(Kin1_, Kin2_) * 4));
+  }
+  __nv_bfloat16* Us = direct ? As_.as<__nv_bfloat16>() : nullptr;
 
   if (!td) {
     lrp_init_kernel<<<W, 256, 0, s>>>(wr, h1_.as<double>(), chat_.as<double>(), ctx_.as<double>(), s_.as<double>(),
@@ -563,12 +685,19 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
     for (int i = T - 1; i >= 0; --i) {
       const int na = nact_[i];
       if (na == 0) continue;
+      const size_t nA = (size_t)((na + 15) / 16) * 16 * H;
       lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), zg1_.as<double>(), c1_.as<double>(),
-                                         Rc1_.as<double>(), Rh1_.as<double>(), nullptr, U_.as<double>(), T, H);
-      if (Wgate1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate1TC_, Kin1_, Y_.as<double>(), s));
-      else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
-      lrp_scatter_adaptive_kernel<<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh1_.as<double>(),
-                                                     Rglob_.as<double>(), rword_.as<double>(), T, H, E);
+                                         Rc1_.as<double>(), Rh1_.as<double>(), nullptr, U_.as<double>(), T, H, Us, nA);
+      if (direct) {
+        LRPCAP_TRY(gemm_tc_direct(na, H, nA, Wgate1TC_, Kin1_, s));
+        lrp_scatter_adaptive_kernel<float><<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), C32_.as<float>(), Rh1_.as<double>(),
+                                                              Rglob_.as<double>(), rword_.as<double>(), T, H, E);
+      } else {
+        if (Wgate1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate1TC_, Kin1_, Y_.as<double>(), s));
+        else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
+        lrp_scatter_adaptive_kernel<double><<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh1_.as<double>(),
+                                                               Rglob_.as<double>(), rword_.as<double>(), T, H, E);
+      }
       launches_ += 2;
     }
   } else {
@@ -579,23 +708,39 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
     for (int i = T - 1; i >= 0; --i) {
       const int na = nact_[i];
       if (na == 0) continue;
+      const size_t nA = (size_t)((na + 15) / 16) * 16 * H;
       lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia2_.as<double>(), fa2_.as<double>(), zg2_.as<double>(), c2_.as<double>(),
-                                         Rc2_.as<double>(), Rh2_.as<double>(), nullptr, U_.as<double>(), T, H);
-      if (Wgate2TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate2TC_, Kin2_, Y_.as<double>(), s));
-      else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, H, nullptr, s));
+                                         Rc2_.as<double>(), Rh2_.as<double>(), nullptr, U_.as<double>(), T, H, Us, nA);
       // Rctx_ doubles as the "extra" (r_s + R_h1) buffer of the top-down cell
-      lrp_scatter_lang_kernel<<<na, 256, 0, s>>>(wr, i, XH2_.as<double>(), Y_.as<double>(), chat_.as<double>(),
-                                                 ctx_.as<double>(), s_.as<double>(), beta_.as<double>(),
-                                                 Rchat_.as<double>(), Rh1_.as<double>(), Rh2n_.as<double>(),
-                                                 Rctx_.as<double>(), Q_.as<double>(), T, H);
+      if (direct) {
+        LRPCAP_TRY(gemm_tc_direct(na, H, nA, Wgate2TC_, Kin2_, s));
+        lrp_scatter_lang_kernel<float><<<na, 256, 0, s>>>(wr, i, XH2_.as<double>(), C32_.as<float>(), chat_.as<double>(),
+                                                          ctx_.as<double>(), s_.as<double>(), beta_.as<double>(),
+                                                          Rchat_.as<double>(), Rh1_.as<double>(), Rh2n_.as<double>(),
+                                                          Rctx_.as<double>(), Q_.as<double>(), T, H);
+      } else {
+        if (Wgate2TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate2TC_, Kin2_, Y_.as<double>(), s));
+        else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate2T_, Kin2_, Y_.as<double>(), Kin2_, na, Kin2_, H, nullptr, s));
+        lrp_scatter_lang_kernel<double><<<na, 256, 0, s>>>(wr, i, XH2_.as<double>(), Y_.as<double>(), chat_.as<double>(),
+                                                           ctx_.as<double>(), s_.as<double>(), beta_.as<double>(),
+                                                           Rchat_.as<double>(), Rh1_.as<double>(), Rh2n_.as<double>(),
+                                                           Rctx_.as<double>(), Q_.as<double>(), T, H);
+      }
       // top-down cell: Rc1 += extra (Rh1 is already folded into extra, so pass a zero-free "Rh" = extra, extra = null)
       lrp_cell_kernel<<<na, 256, 0, s>>>(wr, i, ia1_.as<double>(), fa1_.as<double>(), zg1_.as<double>(), c1_.as<double>(),
-                                         Rc1_.as<double>(), Rctx_.as<double>(), nullptr, U_.as<double>(), T, H);
-      if (Wgate1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate1TC_, Kin1_, Y_.as<double>(), s));
-      else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
-      lrp_scatter_td_kernel<<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh2n_.as<double>(),
-                                               Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
-                                               rword_.as<double>(), T, H, E);
+                                         Rc1_.as<double>(), Rctx_.as<double>(), nullptr, U_.as<double>(), T, H, Us, nA);
+      if (direct) {
+        LRPCAP_TRY(gemm_tc_direct(na, H, nA, Wgate1TC_, Kin1_, s));
+        lrp_scatter_td_kernel<float><<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), C32_.as<float>(), Rh2n_.as<double>(),
+                                                        Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
+                                                        rword_.as<double>(), T, H, E);
+      } else {
+        if (Wgate1TC_) LRPCAP_TRY(gemm_tc(U_.as<double>(), na, H, Wgate1TC_, Kin1_, Y_.as<double>(), s));
+        else LRPCAP_TRY(gemm(U_.as<double>(), H, Wgate1T_, Kin1_, Y_.as<double>(), Kin1_, na, Kin1_, H, nullptr, s));
+        lrp_scatter_td_kernel<double><<<na, 256, 0, s>>>(wr, i, XH1_.as<double>(), Y_.as<double>(), Rh2n_.as<double>(),
+                                                         Rh2_.as<double>(), Rh1_.as<double>(), Rglob_.as<double>(),
+                                                         rword_.as<double>(), T, H, E);
+      }
       launches_ += 4;
     }
   }

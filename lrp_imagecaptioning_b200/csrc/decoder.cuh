@@ -51,11 +51,16 @@ class Decoder {
   int features_gemm(int m, cudaStream_t s);
   // C[M,N] (fp64) = A[M,K] (fp64) * B^T with B given as split-bf16 [N][K]: tcgen05 path for the per-step relevance GEMMs
   int gemm_tc(const double* A, int M, int K, const void* Bsplit, int N, double* C, cudaStream_t s);
+  // the same contraction with A already in As_ as two bf16 planes of stride nA (written by the producing kernel) and the
+  // result left in C32_ as fp32 [*, N] (read by the consuming kernel): one launch instead of three
+  int gemm_tc_direct(int M, int K, size_t nA, const void* Bsplit, int N, cudaStream_t s);
   // forward GEMMs on tensor cores with fp32-exact operands (three bf16 planes, accumulator promoted every k-step):
   // C[M, N] = A[M, K] (row stride lda) * B^T (+ bias), B3 = planes of B^T [Npad, K] from split3_weights()
   int gemm_tc3(const double* A, int lda, int M, int K, const void* B3, int Npad, int N, const double* bias, double* C,
                int ldc, cudaStream_t s);
   int split3_weights(const double* d_Wt, int N, int K, int* Npad, void** out);
+  // C32[Mpad, Npad] (fp32) = A3 (three bf16 planes [Mpad, K]) * B3^T: the bare tensor-core launch of the fused forward
+  int tc3(const void* A3, int Mpad, int K, const void* B3, int Npad, float* C32, cudaStream_t s);
   int upload_split(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, void** out);   // YF_[m*L, D] = UV_[m*L, H] * W_if^T (tensor cores when shapes allow)
   int sort_words(const int* h_word_img, const int* h_word_t, int n_words, cudaStream_t s);
 
@@ -71,6 +76,12 @@ class Decoder {
   uint64_t fwd_key_ = 0, fwd_seen_key_ = 0;
   long long fwd_graph_launches_ = 0;
   bool tc_forward_ = false;                       // gate / logit GEMMs of the forward on tensor cores (gemm_tc3)
+  // fused forward (decoder_fused.cuh): point-wise stages read the GEMM results in fp32 and write the next GEMM's operand
+  // planes; [W_cat1 | W_sx] and [W_hp | W_ss] are single GEMMs; LRPCAP_DECODER_FUSED=0 restores the unfused sequence
+  bool fused_ = false;
+  void *W1cat3_ = nullptr, *W2cat3_ = nullptr, *WifTC3_ = nullptr, *WpTC3_ = nullptr;
+  int Npad1_ = 0, Npad2_ = 0, Hpad_ = 0;
+  DevBuf Axh_, Ahs_, Axh2_, Ahc_, C1_, C2_, C3_, C4_, Vf32_;
   void *WcatB1TC_ = nullptr, *WcatB2TC_ = nullptr;   // [Kin, 4H] split-bf16: B operand of the gradient decoder's GEMMs
   void *Wcat1TC3_ = nullptr, *Wcat2TC3_ = nullptr, *WoTC3_ = nullptr;
   int Vpad_ = 0, G4pad_ = 0;

@@ -384,7 +384,9 @@ __global__ void lrp_init_kernel(WordRef w, const double* __restrict__ hlast, con
 __global__ void lrp_cell_kernel(WordRef w, int i, const double* __restrict__ ia, const double* __restrict__ fa,
                                 const double* __restrict__ zg, const double* __restrict__ c, double* __restrict__ Rc,
                                 const double* __restrict__ Rh, const double* __restrict__ extra,
-                                double* __restrict__ U, int T, int H) {
+                                double* __restrict__ U, int T, int H, __nv_bfloat16* __restrict__ Us = nullptr,
+                                size_t nUs = 0) {
+  // Us != null: U goes straight to the two bf16 planes (hi at Us, lo at Us + nUs) the gate GEMM reads as its A operand
   const int p = blockIdx.x;
   const int n = w.img[p];
   const size_t s0 = ((size_t)n * (T + 1) + i) * H, s1 = s0 + H;
@@ -394,22 +396,31 @@ __global__ void lrp_cell_kernel(WordRef w, int i, const double* __restrict__ ia,
     const double den = stabd(c[s1 + j]);
     const double rg = ia[s1 + j] * tanh(zg[s1 + j]) * rc / den;
     Rc[q] = fa[s1 + j] * c[s0 + j] * rc / den;
-    U[q] = rg / stabd(zg[s1 + j]);
+    const double u = rg / stabd(zg[s1 + j]);
+    if (Us) {
+      __nv_bfloat16 hi, lo;
+      split_bf16((float)u, hi, lo);
+      Us[q] = hi;
+      Us[nUs + q] = lo;
+    } else {
+      U[q] = u;
+    }
   }
 }
 // adaptive: R_xh = [x_i, h_i] * Y -> word / global / hidden parts (explainers.py:620-630)
+template <typename YT>
 __global__ void __launch_bounds__(256)
-lrp_scatter_adaptive_kernel(WordRef w, int i, const double* __restrict__ XH, const double* __restrict__ Y,
+lrp_scatter_adaptive_kernel(WordRef w, int i, const double* __restrict__ XH, const YT* __restrict__ Y,
                             double* __restrict__ Rh, double* __restrict__ Rglob, double* __restrict__ rword, int T,
                             int H, int E) {
   const int p = blockIdx.x;
   const int n = w.img[p];
   const int Kin = 2 * E + H;
   const double* x = XH + ((size_t)n * T + i) * Kin;
-  const double* y = Y + (size_t)p * Kin;
+  const YT* y = Y + (size_t)p * Kin;
   double wsum = 0.0;
   for (int j = threadIdx.x; j < Kin; j += 256) {
-    const double v = x[j] * y[j];
+    const double v = x[j] * (double)y[j];
     if (j < E) wsum += v;
     else if (j < 2 * E) Rglob[(size_t)p * E + j - E] += v;
     else Rh[(size_t)p * H + j - 2 * E] = v;
@@ -426,7 +437,8 @@ lrp_scatter_adaptive_kernel(WordRef w, int i, const double* __restrict__ XH, con
 // grid-TD, language LSTM input split + sentinel/context split (explainers.py:1252-1269)
 //   R_x2 = [c_hat_{i+1}, h1_{i+1}, h2_i] * Y2 ; Rchat_i = (i == t-1 ? init : 0) + R_x2[:H] ; Rh1 += R_x2[H:2H] ;
 //   Rh2n = R_x2[2H:] ; extra = r_s + Rh1 (added to Rc1 by the next cell kernel) ; Q = R_ctx / stab(ctx_{i+1})
-__global__ void lrp_scatter_lang_kernel(WordRef w, int i, const double* __restrict__ XH2, const double* __restrict__ Y2,
+template <typename YT>
+__global__ void lrp_scatter_lang_kernel(WordRef w, int i, const double* __restrict__ XH2, const YT* __restrict__ Y2,
                                         const double* __restrict__ chat, const double* __restrict__ ctx,
                                         const double* __restrict__ s, const double* __restrict__ beta,
                                         const double* __restrict__ Rchat_init, double* __restrict__ Rh1,
@@ -435,14 +447,14 @@ __global__ void lrp_scatter_lang_kernel(WordRef w, int i, const double* __restri
   const int p = blockIdx.x;
   const int n = w.img[p], t = w.t[p];
   const double* x = XH2 + ((size_t)n * T + i) * 3 * H;
-  const double* y = Y2 + (size_t)p * 3 * H;
+  const YT* y = Y2 + (size_t)p * 3 * H;
   const size_t s1 = ((size_t)n * (T + 1) + i + 1) * H;
   const double b = beta[(size_t)n * (T + 1) + i + 1];
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
     const size_t q = (size_t)p * H + j;
-    const double rchat = ((i == t - 1) ? Rchat_init[q] : 0.0) + x[j] * y[j];
-    const double rh1 = Rh1[q] + x[H + j] * y[H + j];
-    Rh2n[q] = x[2 * H + j] * y[2 * H + j];
+    const double rchat = ((i == t - 1) ? Rchat_init[q] : 0.0) + x[j] * (double)y[j];
+    const double rh1 = Rh1[q] + x[H + j] * (double)y[H + j];
+    Rh2n[q] = x[2 * H + j] * (double)y[2 * H + j];
     const double den = stabd(chat[s1 + j]);
     const double r_s = b * s[s1 + j] * rchat / den;
     const double r_ctx = ctx[s1 + j] * (1.0 - b) * rchat / den;
@@ -451,18 +463,19 @@ __global__ void lrp_scatter_lang_kernel(WordRef w, int i, const double* __restri
   }
 }
 // grid-TD, top-down LSTM input split (explainers.py:1288-1300): [h2_i, g, emb, h1_i]
+template <typename YT>
 __global__ void __launch_bounds__(256)
-lrp_scatter_td_kernel(WordRef w, int i, const double* __restrict__ XH1, const double* __restrict__ Y1,
+lrp_scatter_td_kernel(WordRef w, int i, const double* __restrict__ XH1, const YT* __restrict__ Y1,
                       const double* __restrict__ Rh2n, double* __restrict__ Rh2, double* __restrict__ Rh1,
                       double* __restrict__ Rglob, double* __restrict__ rword, int T, int H, int E) {
   const int p = blockIdx.x;
   const int n = w.img[p];
   const int Kin = 2 * H + 2 * E;
   const double* x = XH1 + ((size_t)n * T + i) * Kin;
-  const double* y = Y1 + (size_t)p * Kin;
+  const YT* y = Y1 + (size_t)p * Kin;
   double wsum = 0.0;
   for (int j = threadIdx.x; j < Kin; j += 256) {
-    const double v = x[j] * y[j];
+    const double v = x[j] * (double)y[j];
     if (j < H) Rh2[(size_t)p * H + j] = Rh2n[(size_t)p * H + j] + v;
     else if (j < H + E) Rglob[(size_t)p * E + j - H] += v;
     else if (j < H + 2 * E) wsum += v;

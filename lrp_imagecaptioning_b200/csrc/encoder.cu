@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include "encoder_kernels.cuh"
 #include "tc_conv.cuh"
 
@@ -22,10 +23,18 @@ void DevBuf::release() {
 }
 
 namespace {
-const int kCin[13] = {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512};
-const int kCout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
-const int kShift[13] = {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4};
-const bool kPool[13] = {false, true, false, true, false, false, true, false, false, true, false, false, false};
+struct Arch {
+  int layers;
+  int cin[16], cout[16], shift[16];
+  bool pool[16];
+};
+const Arch kArch[2] = {
+    {13, {3, 64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512}, {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512},
+     {0, 0, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4}, {false, true, false, true, false, false, true, false, false, true, false, false, false}},
+    {16, {3, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512},
+     {64, 64, 128, 128, 256, 256, 256, 256, 512, 512, 512, 512, 512, 512, 512, 512}, {0, 0, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4},
+     {false, true, false, true, false, false, false, true, false, false, false, true, false, false, false, false}},
+};
 constexpr int kForwardChunk = 64;   // images per forward pass: fills the 148 SMs on the 14x14 layers (1.2 GB per activation buffer)
 }  // namespace
 
@@ -50,7 +59,7 @@ Encoder::~Encoder() {
   for (auto& l : L_)
     for (auto& p : l.dual)
       if (p) cudaFree(p);
-  X0_.release(); F_.release(); Mseed_.release(); posneg_.release(); idx_.release();
+  X0_.release(); F_.release(); Mseed_.release(); posneg_.release(); idx_.release(); scale_.release();
   for (auto& g : G_) g.release();
   for (auto& g : Gc_) g.release();
   for (auto& g : Gc2_) g.release();
@@ -60,16 +69,25 @@ Encoder::~Encoder() {
 }
 
 int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float* const* biases, int image_hw,
-                    int precision) {
+                    int precision, int arch) {
+  LRPCAP_REQUIRE(arch == 0 || arch == 1, kErrInvalidArg, "encoder_create: unknown architecture %d (0 = VGG16, 1 = VGG19)", arch);
+  const Arch& A = kArch[arch];
   LRPCAP_REQUIRE(out && kernels_hwio && biases, kErrInvalidArg, "encoder_create: null argument");
   LRPCAP_REQUIRE(image_hw >= 16 && image_hw % 16 == 0, kErrShape, "encoder_create: image size %d must be a multiple of 16", image_hw);
-  LRPCAP_REQUIRE(precision == PREC_FP32_SIMT || precision == PREC_BF16X3_TC, kErrInvalidArg, "encoder_create: unknown precision %d", precision);
+  LRPCAP_REQUIRE(precision >= PREC_FP32_SIMT && precision <= PREC_TC_AUTO, kErrInvalidArg,
+                 "encoder_create: unknown precision %d", precision);
   Encoder* e = new Encoder();
   e->hw_ = image_hw;
   e->precision_ = precision;
+  e->nl_ = A.layers;
+  const int kLayers = A.layers;
   if (const char* v = std::getenv("LRPCAP_FWD_PLANES")) {    // knob: forward operand storage: 3 bf16 planes (default), 2 bf16
     const int n = std::atoi(v);                               // planes, or 4 = two IEEE half planes (kPlanesF16x2)
     if (n == 2 || n == 3 || n == kPlanesF16x2) e->fwd_planes_ = n;
+  }
+  if (const char* v = std::getenv("LRPCAP_MSG_TARGET_EXP")) {   // experiment knob: two-product message scale target
+    const int n = std::atoi(v);
+    if (n >= -8 && n <= 15) e->msg_target_exp_ = n;
   }
   if (const char* v = std::getenv("LRPCAP_FWD_PROMOTE")) {   // experiment knob: k-steps per accumulator hand-over, forward
     const int n = std::atoi(v);
@@ -77,10 +95,10 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
   }
   for (int l = 0; l < kLayers; ++l) {
     Layer& L = e->L_[l];
-    L.cin = kCin[l];
-    L.cout = kCout[l];
-    L.hw = image_hw >> kShift[l];
-    L.pool_after = kPool[l];
+    L.cin = A.cin[l];
+    L.cout = A.cout[l];
+    L.hw = image_hw >> A.shift[l];
+    L.pool_after = A.pool[l];
     const size_t nw = (size_t)9 * L.cin * L.cout;
     if (!kernels_hwio[l] || !biases[l]) {
       delete e;
@@ -115,6 +133,7 @@ void Encoder::set_wpow(int l, const float* h_w) {
 }
 
 int Encoder::set_weights(const float* const* kernels_hwio, const float* const* biases) {
+  const int kLayers = nl_;
   LRPCAP_REQUIRE(kernels_hwio && biases, kErrInvalidArg, "encoder_set_weights: null argument");
   for (int l = 0; l < kLayers; ++l)
     LRPCAP_REQUIRE(kernels_hwio[l] && biases[l], kErrInvalidArg, "encoder_set_weights: layer %d weights missing", l);
@@ -145,6 +164,8 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
     LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * (fmt == WF_TC_FWD3 ? 6 : 4)));
     L.prepared[fmt][sign] = p;
     if (fmt == WF_TC_FWD3) LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, 3));
+    else if (fmt == WF_TC_BWDH)
+      LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_BWD, sign, s, 9, kPlanesF16x2, std::ldexp(1.f, L.wpow)));
     else if (fmt == WF_TC_FWDH)
       LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, kPlanesF16x2, std::ldexp(1.f, L.wpow)));
     else LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, fmt, sign, s));
@@ -156,11 +177,13 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
 
 int Encoder::get_dual_weights(int l, bool tc, void** out, cudaStream_t s) {
   Layer& L = L_[l];
-  void*& slot = L.dual[tc ? 1 : 0];
+  const bool h = tc && two_product();
+  void*& slot = L.dual[tc ? (h ? 2 : 1) : 0];
   if (!slot) {
     LRPCAP_CUDA(cudaMalloc(&slot, (size_t)9 * L.cin * 2 * L.cout * sizeof(float)));
-    LRPCAP_TRY(prep_weights_dual(L.w_hwio, slot, L.cin, L.cout, tc ? WF_TC_BWD : WF_SIMT_BWD, WS_PLUS, rule_.alpha, WS_MINUS,
-                                 -rule_.beta, s));
+    const float ws = h ? std::ldexp(1.f, L.wpow) : 1.f;
+    LRPCAP_TRY(prep_weights_dual(L.w_hwio, slot, L.cin, L.cout, tc ? WF_TC_BWD : WF_SIMT_BWD, WS_PLUS, rule_.alpha * ws, WS_MINUS,
+                                 -rule_.beta * ws, s, h ? 1 : 0));
     ++launches_;
   }
   *out = slot;
@@ -177,7 +200,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
   const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
   if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
   if (dual) LRPCAP_TRY(get_dual_weights(l, tc, &B, s));
-  else LRPCAP_TRY(get_weights(l, tc ? (backward ? WF_TC_BWD : (fwd_planes_ == 3 ? WF_TC_FWD3 : fwd_planes_ == kPlanesF16x2 ? WF_TC_FWDH : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  else LRPCAP_TRY(get_weights(l, tc ? (backward ? (two_product() ? WF_TC_BWDH : WF_TC_BWD) : (fwd_planes_ == 3 ? WF_TC_FWD3 : fwd_planes_ == kPlanesF16x2 ? WF_TC_FWDH : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
   ProfRec rec{};
   if (profile_) {
     LRPCAP_CUDA(cudaEventCreate(&rec.a));
@@ -191,7 +214,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     TcConvArgs a;
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout * (dual ? 2 : 1); a.taps = 9; a.Nout = Nout;
-    a.planes = backward ? 2 : fwd_planes_;
+    a.planes = backward ? (two_product() ? kPlanesH1x2 : 2) : fwd_planes_;
     // backward: tensor-core fp32 accumulation rounds toward zero, which shrinks every output of a chain of n accumulates
     // by ~1.5e-8 n (measured, tools/diag_parity.py trunc: -1.6e-5 at K = 4608, -1e-4 over the 12 layers). A uniform 1e-4
     // scale error is inside the per-pixel tolerance of every rule, but for the same-sign chains of the alpha-beta family
@@ -205,6 +228,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     }
     a.promote_every = backward ? pe : fwd_promote_;
     a.epi = epi;
+    if (backward && two_product()) a.epi.acc_scale = std::ldexp(1.f, -L.wpow);   // the half-plane weights hold 2^wpow * w
     if (!backward && fwd_planes_ == kPlanesF16x2) {
       a.epi.acc_scale = std::ldexp(1.f, -L.wpow);
       a.epi.overflow = d_overflow_;
@@ -214,6 +238,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     SimtConvArgs a;
     a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout;
+    LRPCAP_REQUIRE(!(backward && two_product()), kErrState, "encoder: layer %d backward has no tensor-core shape", l);
     a.out_planes = split() ? (backward ? 2 : fwd_planes_) : 0;
     a.epi = epi;
     if (!backward && split() && fwd_planes_ == kPlanesF16x2) a.epi.overflow = d_overflow_;
@@ -244,6 +269,7 @@ int Encoder::profile_read(double* out) {
 }
 
 int Encoder::debug_pool_routes(int l, unsigned char* h_out) {
+  const int kLayers = nl_;
   LRPCAP_REQUIRE(n_images_ > 0, kErrState, "debug_pool_routes: call encoder_forward first");
   LRPCAP_REQUIRE(l >= 0 && l < kLayers - 1 && L_[l].pool_after && h_out, kErrInvalidArg,
                  "debug_pool_routes: layer %d is not followed by a max-pool", l);
@@ -264,7 +290,29 @@ int Encoder::debug_pool_routes(int l, unsigned char* h_out) {
   return kOk;
 }
 
+int Encoder::debug_message_scales(float* h_max, int* h_kt, int cap_words, int* chunk) {
+  LRPCAP_REQUIRE(h_max && h_kt && chunk, kErrInvalidArg, "debug_message_scales: null argument");
+  *chunk = 0;
+  if (!scale_.p || scale_m_ == 0) return kOk;
+  LRPCAP_REQUIRE(cap_words >= scale_m_, kErrInvalidArg, "debug_message_scales: room for %d words needed", scale_m_);
+  LRPCAP_CUDA(cudaDeviceSynchronize());
+  std::vector<unsigned> mx((size_t)(nl_ + 1) * scale_cw_);
+  std::vector<int> kt((size_t)nl_ * scale_cw_);
+  LRPCAP_CUDA(cudaMemcpy(mx.data(), scale_.p, mx.size() * 4, cudaMemcpyDeviceToHost));
+  LRPCAP_CUDA(cudaMemcpy(kt.data(), scale_.as<unsigned>() + mx.size(), kt.size() * 4, cudaMemcpyDeviceToHost));
+  for (int l = 0; l <= nl_; ++l)
+    for (int w = 0; w < scale_m_; ++w) {
+      float f;
+      std::memcpy(&f, &mx[(size_t)l * scale_cw_ + w], 4);
+      h_max[(size_t)l * scale_m_ + w] = f;
+      if (l < nl_) h_kt[(size_t)l * scale_m_ + w] = kt[(size_t)l * scale_cw_ + w];
+    }
+  *chunk = scale_m_;
+  return kOk;
+}
+
 int Encoder::debug_multiplier(int l, int branch, float* h_out) {
+  const int kLayers = nl_;
   LRPCAP_REQUIRE(n_images_ > 0, kErrState, "debug_multiplier: call encoder_forward first");
   LRPCAP_REQUIRE(l >= 0 && l < kLayers - 1 && h_out && (branch == 0 || branch == 1), kErrInvalidArg,
                  "debug_multiplier: layer %d / branch %d out of range", l, branch);
@@ -303,6 +351,7 @@ int Encoder::debug_multiplier(int l, int branch, float* h_out) {
 }
 
 int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cudaStream_t s) {
+  const int kLayers = nl_;
   LRPCAP_REQUIRE(d_images && n > 0, kErrInvalidArg, "encoder_forward: no images");
   switch (rule.kind) {
     case RULE_EPSILON:
@@ -335,8 +384,8 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
       LRPCAP_TRY(Gi_[l].ensure((size_t)n * layer_out_elems(l) / 64 * sizeof(unsigned)));
     }
   }
-  LRPCAP_TRY(Mseed_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
-  LRPCAP_TRY(F_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
+  LRPCAP_TRY(Mseed_.ensure((size_t)n * layer_out_elems(kLayers - 1) * sizeof(float)));
+  LRPCAP_TRY(F_.ensure((size_t)n * layer_out_elems(kLayers - 1) * sizeof(float)));
   const int FC = n < kForwardChunk ? n : kForwardChunk;
   const size_t act_bytes = (size_t)FC * hw_ * hw_ * 64 * (split() ? 6 : 4);
   for (auto& a : act_) LRPCAP_TRY(a.ensure(act_bytes));
@@ -348,7 +397,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
       LRPCAP_TRY(G2_[l].ensure((size_t)n * layer_out_elems(l) * sizeof(float)));
       if (L_[l].pool_after) LRPCAP_TRY(Gc2_[l].ensure((size_t)n * layer_out_elems(l) / 4 * sizeof(float)));
     }
-    LRPCAP_TRY(Mseed2_.ensure((size_t)n * layer_out_elems(12) * sizeof(float)));
+    LRPCAP_TRY(Mseed2_.ensure((size_t)n * layer_out_elems(kLayers - 1) * sizeof(float)));
     if (dual_alpha_ != rule.alpha || dual_beta_ != rule.beta) {   // cached stacked weights depend on (alpha, beta)
       for (auto& L : L_)
         for (auto& p : L.dual)
@@ -490,6 +539,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
 
 int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_words, float* d_R_pix, cudaStream_t s,
                        float* h_R_pix) {
+  const int kLayers = nl_;
   LRPCAP_REQUIRE(n_images_ > 0, kErrState, "encoder_relevance: call encoder_forward first");
   LRPCAP_REQUIRE(h_img_index && d_R_head && d_R_pix && n_words > 0, kErrInvalidArg, "encoder_relevance: bad argument");
   for (int w = 0; w < n_words; ++w)
@@ -507,7 +557,7 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
   const int sign = (ab || zpf) ? WS_PLUS : WS_ALL;
   const int mult = (rule_.kind == RULE_GRADIENT || guided) ? 0 : 1;
   const int fh = hw_ / 16;
-  const size_t head_elems = layer_out_elems(12);
+  const size_t head_elems = layer_out_elems(kLayers - 1);
   const size_t pix_elems = (size_t)hw_ * hw_ * 3;
 
   void *Wa = nullptr, *Wb = nullptr;
@@ -526,6 +576,10 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
     if (ab) LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, WS_MINUS, &Wb, s));
   }
   const int mul = inh ? 2 : 1;
+  const bool tp = two_product();
+  if (tp) LRPCAP_TRY(scale_.ensure((size_t)(2 * kLayers + 1) * CW * sizeof(unsigned)));
+  unsigned* mxb = scale_.as<unsigned>();   // [layers + 1][CW]: row l = stored max of message l, last row = the seed's true max
+  int* ktb = reinterpret_cast<int*>(mxb + (size_t)(kLayers + 1) * CW);   // [layers][CW]: log2 scale of message l
 
   for (int w0 = 0, m = 0; w0 < n_words; w0 += m) {
     m = (n_words - w0) < CW ? (n_words - w0) : CW;
@@ -533,8 +587,18 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
     if (h_R_pix && w0 + m == n_words && m >= 128) m = (m / 2 + 31) / 32 * 32;
     const int* idx = idx_.as<int>() + w0;
     int cur = 0;
-    LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr, idx,
-                            msg_[cur].p, (size_t)m * head_elems * mul, split(), m, fh * fh, 512, guided ? 1 : 0, s));
+    if (tp) {
+      scale_cw_ = CW;
+      scale_m_ = m;
+      LRPCAP_CUDA(cudaMemsetAsync(mxb, 0, (size_t)(kLayers + 1) * CW * sizeof(unsigned), s));
+      LRPCAP_TRY(seed_message_scaled(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr,
+                                     idx, msg_[cur].p, m, fh * fh, 512, guided ? 1 : 0, mxb + (size_t)kLayers * CW,
+                                     mxb + (size_t)(kLayers - 1) * CW, ktb + (size_t)(kLayers - 1) * CW, msg_target_exp_, s));
+      ++launches_;
+    } else {
+      LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr, idx,
+                              msg_[cur].p, (size_t)m * head_elems * mul, split(), m, fh * fh, 512, guided ? 1 : 0, s));
+    }
     ++launches_;
     for (int l = kLayers - 1; l >= 1; --l) {
       EpiParams ep;
@@ -548,6 +612,13 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       ep.Gin2 = inh ? (ep.up == 2 ? Gc2_[l - 1].as<float>() : G2_[l - 1].as<float>()) : nullptr;
       ep.out_msg_elems = (size_t)m * layer_out_elems(l - 1) * mul;
       ep.out_planar_f32 = (l == 1) ? 1 : 0;   // the last message is read by last_dgrad only: fp32, channel-planar
+      if (tp) {
+        ep.mx_in = mxb + (size_t)l * CW;
+        ep.kt_in = ktb + (size_t)l * CW;
+        ep.mx_out = l > 1 ? mxb + (size_t)(l - 1) * CW : nullptr;
+        ep.kt_out = l > 1 ? ktb + (size_t)(l - 1) * CW : nullptr;
+        ep.target_exp = msg_target_exp_;
+      }
       LRPCAP_TRY(conv(l, true, sign, msg_[cur].p, (size_t)m * layer_out_elems(l) * mul, m, ep, s, inh));
       cur ^= 1;
     }

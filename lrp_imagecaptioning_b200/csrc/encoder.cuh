@@ -16,7 +16,7 @@
 
 namespace lrpcap {
 
-enum Precision : int { PREC_FP32_SIMT = 0, PREC_BF16X3_TC = 1 };
+enum Precision : int { PREC_FP32_SIMT = 0, PREC_BF16X3_TC = 1, PREC_F16X2_TC = 2, PREC_TC_AUTO = 3 };
 
 enum RuleKind : int {
   RULE_EPSILON = 0,       // LRPEpsilon            (relevance_analyzer.py:531-552)
@@ -45,10 +45,13 @@ struct DevBuf {
 
 class Encoder {
  public:
-  static constexpr int kLayers = 13;
+  static constexpr int kMaxLayers = 16;
   ~Encoder();
+  // arch 0: VGG16 (13 convs, pools after 2/2/3/3), arch 1: VGG19 (16 convs, pools after 2/2/4/4), both up to the last
+  // conv of block 5 (models/model.py:419-421: the reference cuts both at their last conv layer; 14 x 14 x 512 head)
   static int create(Encoder** out, const float* const* kernels_hwio, const float* const* biases, int image_hw,
-                    int precision);
+                    int precision, int arch = 0);
+  int n_layers() const { return nl_; }
   // Replaces the 13 kernels / biases in place (fine-tuning: the explained model changes every step); keeps every large
   // state / message buffer, drops the prepared weight layouts and the per-image state.
   int set_weights(const float* const* kernels_hwio, const float* const* biases);
@@ -83,6 +86,10 @@ class Encoder {
   //                routing folded in (zeros away from the arg-max); branch 1 = inhibitor multiplier (beta != 0).
   int debug_pool_routes(int layer, unsigned char* h_out);
   int debug_multiplier(int layer, int branch, float* h_out);
+  //   message scales (two-product backward): for the LAST chunk of the last relevance call, h_max [layers + 1][chunk]
+  //                = largest |stored fp16 value| of message l per word (row `layers`: the seed's true maximum) and
+  //                h_kt [layers][chunk] = log2 of its scale; returns the chunk size through *chunk (0: not two-product)
+  int debug_message_scales(float* h_max, int* h_kt, int cap_words, int* chunk);
 
  private:
   struct ProfRec {
@@ -99,15 +106,24 @@ class Encoder {
     bool pool_after;
     float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
     float* bias = nullptr;    // device fp32 [cout]
-    void* prepared[6][3] = {};  // [WeightFormat][WeightSign]
+    void* prepared[7][3] = {};  // [WeightFormat][WeightSign]
     int wpow = 0;             // half-plane forward: weights are stored as 2^wpow * w (keeps the low plane out of the subnormals)
-    void* dual[2] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC} backward layouts
+    void* dual[3] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC, half-plane TC} backward layouts
   };
   int get_weights(int l, int fmt, int sign, void** out, cudaStream_t s);
   int conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const struct EpiParams& epi,
            cudaStream_t s, bool dual = false);
   int get_dual_weights(int l, bool tc, void** out, cudaStream_t s);
-  bool split() const { return precision_ == PREC_BF16X3_TC; }
+  bool split() const { return precision_ != PREC_FP32_SIMT; }
+  // two-product backward (PREC_F16X2_TC): the relevance message is ONE fp16 plane scaled by a power of two per word and
+  // layer, the weights two fp16 planes: 2 MMA products per algorithmic MAC instead of 3, half the message bytes; the
+  // message keeps 11 bits instead of 16 (DESIGN.md section 5 for what that costs per rule)
+  // PREC_TC_AUTO: two products for the rules whose chains are same-sign sums (alpha-beta family, z+: an 11-bit message
+  // costs them 2e-4 of the map maximum), three for the mixed-sign rules (epsilon, z, gradients: 7e-4 -- too close to 1e-3)
+  bool two_product() const {
+    return precision_ == PREC_F16X2_TC ||
+           (precision_ == PREC_TC_AUTO && (rule_.kind == RULE_ALPHA_BETA || rule_.kind == RULE_ZPLUS_FAST));
+  }
   // storage planes of forward activations in tensor-core mode (fp32 otherwise). The per-image forward decides ReLU signs
   // and pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level map errors, so its
   // operands carry >= 22 bits: two IEEE half planes (default, 3 MMA products; falls back for good when an activation
@@ -120,18 +136,22 @@ class Encoder {
   void set_wpow(int l, const float* h_w);
   long long launches_ = 0;
   EncoderRule rule_;
-  Layer L_[kLayers];
+  int nl_ = 13;
+  Layer L_[kMaxLayers];
   std::vector<float> w0_host_;       // first-layer kernel (host copy) for the signed-input alpha-beta path
   float* w0_pm_ = nullptr;           // device fp32 [9][6][64]: [W+ ; W-] stacked for the [x+, x-] input
   float* w0_mp_ = nullptr;           // [W- ; W+] (inhibitor branch, beta != 0)
   float *w0_last_a_ = nullptr, *w0_last_b_ = nullptr;   // dual last-layer weights [9][128][3] for x >= 0 / x < 0
   float dual_alpha_ = 0.f, dual_beta_ = 0.f;            // (alpha, beta) the cached dual weights were built for
-  DevBuf X0_, F_, Mseed_, G_[kLayers - 1];
-  DevBuf Mseed2_, G2_[kLayers - 1];   // inhibitor-branch multipliers (beta != 0)
+  DevBuf X0_, F_, Mseed_, G_[kMaxLayers - 1];
+  DevBuf Mseed2_, G2_[kMaxLayers - 1];   // inhibitor-branch multipliers (beta != 0)
   // layers followed by a max-pool: compact multipliers (value at the window's arg-max + 2-bit position per channel)
   // read by the up-sampling epilogue; G_[l] / G2_[l] of those layers are scratch between the conv and pool_mask
-  DevBuf Gc_[kLayers - 1], Gc2_[kLayers - 1], Gi_[kLayers - 1];
+  DevBuf Gc_[kMaxLayers - 1], Gc2_[kMaxLayers - 1], Gi_[kMaxLayers - 1];
   DevBuf act_[3], posneg_, msg_[2], idx_;
+  int msg_target_exp_ = 4;   // two-product backward: predicted maximum of a stored message plane is 2^msg_target_exp_
+  int scale_cw_ = 0, scale_m_ = 0;   // chunk stride / words of the last chunk behind scale_
+  DevBuf scale_;   // two-product backward: per chunk [layers + 1][chunk] max bits + [layers][chunk] scale exponents (epilogue.cuh)
 };
 
 }  // namespace lrpcap

@@ -52,7 +52,7 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
 
 __global__ void prep_weights_dual_kernel(const float* __restrict__ w, float* __restrict__ out_f32,
                                          __nv_bfloat16* __restrict__ out_hi, int cin, int cout, int fmt, int sign_a,
-                                         float scale_a, int sign_b, float scale_b) {
+                                         float scale_a, int sign_b, float scale_b, int half_planes) {
   const size_t total = (size_t)9 * cin * 2 * cout;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -71,6 +71,11 @@ __global__ void prep_weights_dual_kernel(const float* __restrict__ w, float* __r
   v *= second ? scale_b : scale_a;
   if (fmt == WF_SIMT_BWD) {
     out_f32[idx] = v;
+  } else if (half_planes) {
+    __half* oh = reinterpret_cast<__half*>(out_hi);
+    const __half h = __float2half_rn(v);
+    oh[idx] = h;
+    oh[total + idx] = __float2half_rn(v - __half2float(h));
   } else {
     for (int p = 0; p < 2; ++p) {
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -124,33 +129,73 @@ __global__ void pool_mask_kernel(const void* __restrict__ act, size_t act_elems,
 }
 
 // ------------------------------------------------------------------ seed message
+// Two-product backward: max |R * M| (and |R * M2|) per item, so that the seed message can be stored as one fp16 plane
+// scaled by a power of two per item (epilogue.cuh: kMsgTargetExp). grid = (blocks per item, items).
+__global__ void seed_max_kernel(const float* __restrict__ R, const float* __restrict__ M, const float* __restrict__ M2,
+                                const int* __restrict__ img_index, unsigned* __restrict__ mx, size_t per_item, int relu) {
+  const int item = blockIdx.y;
+  const int img = __ldg(img_index + item);
+  const float* r0 = R + (size_t)item * per_item;
+  const float* m0 = M + (size_t)img * per_item;
+  const float* m1 = M2 ? M2 + (size_t)img * per_item : nullptr;
+  unsigned best = 0u;
+  for (size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < per_item; e += (size_t)gridDim.x * blockDim.x * 4) {
+    float r[4], m[4];
+    load_f32<4>(r0 + e, r);
+    load_f32<4>(m0 + e, m);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) best = max(best, __float_as_uint((relu ? fmaxf(r[i], 0.f) : r[i]) * m[i]) & 0x7fffffffu);
+    if (m1) {
+      load_f32<4>(m1 + e, m);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) best = max(best, __float_as_uint(r[i] * m[i]) & 0x7fffffffu);
+    }
+  }
+  best = __reduce_max_sync(0xffffffffu, best);
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(mx + item, best);
+}
+
+// mx_true != null (ST = StoreH1): the message is stored as 2^k * value, k = msg_rescale_exp(mx_true[item]); the first
+// thread of every item records k (kt_out) and the stored plane's maximum (mx_out) for the next layer's epilogue.
 template <class ST>
 __global__ void seed_kernel(const float* __restrict__ R, const float* __restrict__ M, const float* __restrict__ M2,
                             const int* __restrict__ img_index, void* msg, size_t msg_elems, int items, size_t per_item,
-                            int C, int relu) {
-  const size_t total4 = (size_t)items * per_item / 4;
+                            int C, int relu, const unsigned* __restrict__ mx_true, unsigned* __restrict__ mx_out,
+                            int* __restrict__ kt_out, int target_exp) {
+  constexpr int NV = ST::kScaled ? 8 : 4;
+  const size_t totalv = (size_t)items * per_item / NV;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total4) return;
-  const size_t e = idx * 4;
+  if (idx >= totalv) return;
+  const size_t e = idx * NV;
   const int item = e / per_item;
   const size_t in_item = e - (size_t)item * per_item;
   const int img = __ldg(img_index + item);
-  float r[4], m[4], o[4];
-  load_f32<4>(R + e, r);
-  load_f32<4>(M + (size_t)img * per_item + in_item, m);
+  float sc = 1.f;
+  if (ST::kScaled) {
+    const unsigned mb = __ldg(mx_true + item);
+    const int k = msg_rescale_exp(mb, target_exp);
+    sc = pow2i(k);
+    if (in_item == 0) {
+      kt_out[item] = k;
+      mx_out[item] = __float_as_uint(__uint_as_float(mb) * sc);
+    }
+  }
+  float r[NV], m[NV], o[NV];
+  load_f32<NV>(R + e, r);
+  load_f32<NV>(M + (size_t)img * per_item + in_item, m);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o[i] = (relu ? fmaxf(r[i], 0.f) : r[i]) * m[i];
+  for (int i = 0; i < NV; ++i) o[i] = (relu ? fmaxf(r[i], 0.f) : r[i]) * m[i] * sc;
   if (!M2) {
-    ST::template store<4>(msg, msg_elems, e, o);
+    ST::template store<NV>(msg, msg_elems, e, o);
     return;
   }
   const size_t pix = e / C;               // dual layout: [.., pixel, 2C] = [R*M | R*M2]
   const int c = (int)(e - pix * C);
-  ST::template store<4>(msg, msg_elems, pix * 2 * C + c, o);
-  load_f32<4>(M2 + (size_t)img * per_item + in_item, m);
+  ST::template store<NV>(msg, msg_elems, pix * 2 * C + c, o);
+  load_f32<NV>(M2 + (size_t)img * per_item + in_item, m);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) o[i] = r[i] * m[i];
-  ST::template store<4>(msg, msg_elems, pix * 2 * C + C + c, o);
+  for (int i = 0; i < NV; ++i) o[i] = r[i] * m[i] * sc;
+  ST::template store<NV>(msg, msg_elems, pix * 2 * C + C + c, o);
 }
 
 // ------------------------------------------------------------------ last transposed conv (C -> 3) + re-weighting
@@ -331,12 +376,12 @@ __global__ void split_to_f32_kernel(const __nv_bfloat16* __restrict__ hi, const 
 }  // namespace
 
 int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign_a, float scale_a, int sign_b,
-                      float scale_b, cudaStream_t s) {
+                      float scale_b, cudaStream_t s, int half_planes) {
   LRPCAP_REQUIRE(fmt == WF_SIMT_BWD || fmt == WF_TC_BWD, kErrInvalidArg, "prep_weights_dual: backward formats only");
   const size_t total = (size_t)9 * cin * 2 * cout;
   prep_weights_dual_kernel<<<grid_for(total, 256), 256, 0, s>>>(w_hwio, reinterpret_cast<float*>(out),
                                                                 reinterpret_cast<__nv_bfloat16*>(out), cin, cout, fmt,
-                                                                sign_a, scale_a, sign_b, scale_b);
+                                                                sign_a, scale_a, sign_b, scale_b, half_planes);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -375,9 +420,26 @@ int seed_message(const float* R, const float* M, const float* M2, const int* img
   LRPCAP_REQUIRE(per_item % 4 == 0, kErrShape, "seed_message: item size must be a multiple of 4");
   const size_t total4 = (size_t)items * per_item / 4;
   if (split)
-    seed_kernel<StoreSplit><<<grid_for(total4, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu);
+    seed_kernel<StoreSplit><<<grid_for(total4, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu,
+                                                                  nullptr, nullptr, nullptr, 0);
   else
-    seed_kernel<StoreF32><<<grid_for(total4, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu);
+    seed_kernel<StoreF32><<<grid_for(total4, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu,
+                                                                nullptr, nullptr, nullptr, 0);
+  LRPCAP_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int seed_message_scaled(const float* R, const float* M, const float* M2, const int* img_index, void* msg, int items, int pix,
+                        int C, int relu, unsigned* mx_true, unsigned* mx_out, int* kt_out, int target_exp, cudaStream_t s) {
+  const size_t per_item = (size_t)pix * C;
+  LRPCAP_REQUIRE(per_item % 8 == 0 && C % 8 == 0, kErrShape, "seed_message_scaled: item size must be a multiple of 8");
+  int bpi = (int)((per_item / 4 + 255) / 256);
+  if (bpi > 32) bpi = 32;
+  seed_max_kernel<<<dim3((unsigned)bpi, (unsigned)items), 256, 0, s>>>(R, M, M2, img_index, mx_true, per_item, relu);
+  LRPCAP_CUDA(cudaGetLastError());
+  const size_t total8 = (size_t)items * per_item / 8;
+  seed_kernel<StoreH1><<<grid_for(total8, 256), 256, 0, s>>>(R, M, M2, img_index, msg, 0, items, per_item, C, relu, mx_true,
+                                                             mx_out, kt_out, target_exp);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }

@@ -11,6 +11,7 @@ enum WeightFormat : int {
   WF_TC_BWD = 3,    // split-bf16 [tap'][cin][cout]          (K-major B operand of the dgrad GEMM)
   WF_TC_FWD3 = 4,   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
   WF_TC_FWDH = 5,   // as WF_TC_FWD with two IEEE half planes of 2^k * w (Layer::wpow): the default forward operands
+  WF_TC_BWDH = 6,   // as WF_TC_BWD with two IEEE half planes of 2^k * w: B operand of the two-product backward
 };
 enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
 
@@ -23,8 +24,9 @@ int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int
 // Backward weights of the alpha-beta rule with beta != 0, stacked along K (2*cout input channels):
 //   k <  cout : scale_a * sign_a(W)      k >= cout : scale_b * sign_b(W)
 // fmt: WF_SIMT_BWD -> fp32 [tap'][2*cout][cin]; WF_TC_BWD -> split-bf16 [tap'][cin][2*cout].
+// half_planes != 0 (WF_TC_BWD only): two IEEE half planes instead of two bf16 planes (fold 2^wpow into the scales).
 int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign_a, float scale_a, int sign_b,
-                      float scale_b, cudaStream_t s);
+                      float scale_b, cudaStream_t s, int half_planes = 0);
 
 // 2x2/2 max-pool of `act` [items,H,W,C] (storage-typed). If `pooled` != null writes [items,H/2,W/2,C];
 // if `G` != null (the layer's multiplier in the g_offset layout with up = 2) also writes its compact form: `Gc`
@@ -38,6 +40,11 @@ int pool_mask(const void* act, size_t act_elems, int planes /*0 = fp32, 2, 3*/, 
 // M2 != null: dual message with 2*C channels [R*M | R*M2].
 int seed_message(const float* R, const float* M, const float* M2, const int* img_index, void* msg, size_t msg_elems, bool split,
                  int items, int pix, int C, int relu, cudaStream_t s);
+
+// Two-product backward: the seed as ONE fp16 plane scaled by a power of two per item. mx_true [items] must be zero on
+// entry (receives max |value| per item); mx_out [items] receives the stored plane's maximum, kt_out [items] log2(scale).
+int seed_message_scaled(const float* R, const float* M, const float* M2, const int* img_index, void* msg, int items, int pix,
+                        int C, int relu, unsigned* mx_true, unsigned* mx_out, int* kt_out, int target_exp, cudaStream_t s);
 
 // Last transposed conv (64 -> 3 channels) + input re-weighting:
 //   c_a = Wa^T (*) s,  c_b = Wb^T (*) s (only if Wb != null)

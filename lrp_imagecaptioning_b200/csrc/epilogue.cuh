@@ -33,7 +33,23 @@ struct EpiDev {
   int* overflow;      // forward, half planes: set to 1 when an activation leaves the half range
   int g_up;           // layout of G written by the forward epilogues (see g_offset)
   int out_planar_f32;    // backward: message written as fp32 [items][NO][H][W] (the last message)
+  // two-product backward (StoreH1 messages): one fp16 plane holding 2^kt[item] * s, kt chosen per item and layer so that
+  // the plane's maximum sits near 2^kMsgTargetExp (fp16 keeps 11 bits over 2^-14 .. 2^16 only)
+  const unsigned* mx_in;   // [items] float bits of max |stored value| of the incoming message
+  unsigned* mx_out;        // [items] running maximum of the message being written (atomicMax on the float bits)
+  const int* kt_in;        // [items] log2 of the incoming message's scale
+  int* kt_out;             // [items] log2 of the outgoing message's scale (every tile of an item writes the same value)
+  int target_exp;          // the predicted maximum of the outgoing plane is 2^target_exp
 };
+
+constexpr int kMsgTargetExp = 4;   // default: predicted maximum 2^4: 2^12 of head-room against growth, 2^-28 of the maximum resolved
+// log2 of the factor that brings a plane whose maximum has float bits `mbits` to the target maximum 2^target
+__device__ __forceinline__ int msg_rescale_exp(unsigned mbits, int target) {
+  const int ex = (int)((mbits >> 23) & 0xffu);
+  int d = ex ? target - (ex - 127) : 0;
+  return d < -100 ? -100 : (d > 100 ? 100 : d);
+}
+__device__ __forceinline__ float pow2i(int d) { return __int_as_float((127 + d) << 23); }   // d in [-126, 127]
 
 // Per-image multipliers G are only ever touched by epilogues (never by TMA), so they are stored in the order the
 // backward epilogue reads them: 16-channel runs of consecutive accumulator pixels are contiguous,
@@ -61,6 +77,7 @@ __device__ __forceinline__ void ldg256_nc(const void* p, uint32_t (&u)[8]) {
 
 // ---- storage policies ----
 struct StoreSplit {
+  static constexpr bool kScaled = false;
   template <int NV>
   static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
     static_assert(NV % 4 == 0, "split storage moves 4 or 8 elements per vector");
@@ -128,6 +145,7 @@ struct StoreSplit {
 
 // two IEEE half planes (common.cuh: split2h); same interface and access widths as StoreSplit
 struct StoreSplitH {
+  static constexpr bool kScaled = false;
   template <int NV>
   static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
     static_assert(NV % 4 == 0, "split storage moves 4, 8 or 16 elements per vector");
@@ -170,7 +188,40 @@ struct StoreSplitH {
   }
 };
 
+// one IEEE half plane, saturating (the scaled message of the two-product backward); `elems` unused
+struct StoreH1 {
+  static constexpr bool kScaled = true;
+  template <int NV>
+  static __device__ __forceinline__ void store(void* base, size_t, size_t off, const float (&v)[NV]) {
+    static_assert(NV % 8 == 0, "single-plane storage moves 8 or 16 elements per vector");
+    __half* p = reinterpret_cast<__half*>(base) + off;
+    uint32_t u[NV / 2];
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+      const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+      const __half2 h = __floats2half2_rn(a, b);
+      u[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    if constexpr (NV == 16) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = u[i];
+      stg256(p, w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV / 8; ++j) reinterpret_cast<uint4*>(p)[j] = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+    }
+  }
+  template <int NV>
+  static __device__ __forceinline__ void load(const void* base, size_t, size_t off, float (&v)[NV]) {
+    const __half* p = reinterpret_cast<const __half*>(base) + off;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __half2float(p[i]);
+  }
+};
+
 struct StoreSplit3 {
+  static constexpr bool kScaled = false;
   template <int NV>
   static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
     static_assert(NV % 4 == 0, "split storage moves 4 elements per vector");
@@ -211,6 +262,7 @@ struct StoreSplit3 {
 };
 
 struct StoreF32 {
+  static constexpr bool kScaled = false;
   template <int NV>
   static __device__ __forceinline__ void store(void* base, size_t, size_t off, const float (&v)[NV]) {
     static_assert(NV % 4 == 0, "fp32 storage moves 4 elements per 16 B");
@@ -314,12 +366,21 @@ template <int UP, int NCH, class ST, bool PIPE = true, class AccLoader>
 __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, int Nout, int item, int y, int x,
                                                int n_first, int n_step, bool valid, AccLoader&& load_acc) {
   constexpr int SUBS = UP * UP;
+  constexpr bool SC = ST::kScaled;
   const int img = valid ? __ldg(e.img_index + item) : 0;
   const int WW = W * UP;
   const size_t item_pixels = (size_t)H * UP * WW;
   const int NO = e.Gin2 ? 2 * Nout : Nout;
   const size_t gplane = (size_t)H * W;                                   // accumulator pixels per 16-channel run plane
   const size_t gpix = ((size_t)img * (Nout >> 4)) * gplane + (size_t)y * W + x;
+  float sc = 1.f;        // SC: accumulator -> stored message (undoes the weight pre-scale, moves to the new item scale)
+  unsigned tmax = 0u;    // SC: float bits of the largest |stored value| this thread wrote
+  if (SC) {
+    const int kin = __ldg(e.kt_in + item);                              // the whole tile belongs to one item
+    const int d = e.out_planar_f32 ? -kin : msg_rescale_exp(__ldg(e.mx_in + item), e.target_exp);
+    sc = e.acc_scale * pow2i(d < -100 ? -100 : (d > 100 ? 100 : d));
+    if (e.kt_out && (threadIdx.x & 31) == 0) e.kt_out[item] = kin + d;
+  }
   for (int pass = 0; pass < (e.Gin2 ? 2 : 1); ++pass) {
     const float* G = pass ? e.Gin2 : e.Gin;
     constexpr int NB = PIPE ? 2 : 1;
@@ -357,11 +418,23 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
           float o[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = v[i] * g_select<UP>(gg[c % NB][i], gi[c % NB], i, sub);
+          if (SC) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              o[i] *= sc;
+              tmax = max(tmax, __float_as_uint(o[i]) & 0x7fffffffu);
+            }
+          }
           const size_t pix = (size_t)(y * UP + sub / UP) * WW + (x * UP + sub % UP);
           epi_store_msg<16, ST>(e, item_pixels, item, pix, NO, pass * Nout + n, o);
         }
       }
     }
+  }
+  if (SC) {
+    __syncwarp();
+    tmax = __reduce_max_sync(0xffffffffu, tmax);
+    if (e.mx_out && (threadIdx.x & 31) == 0 && tmax) atomicMax(e.mx_out + item, tmax);
   }
 }
 
@@ -464,6 +537,11 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->acc_scale = p.acc_scale;
   e->overflow = p.overflow;
   e->out_planar_f32 = p.out_planar_f32;
+  e->mx_in = p.mx_in;
+  e->mx_out = p.mx_out;
+  e->kt_in = p.kt_in;
+  e->kt_out = p.kt_out;
+  e->target_exp = p.target_exp;
   e->out = nullptr;
   e->out_elems = 0;
   switch (p.mode) {

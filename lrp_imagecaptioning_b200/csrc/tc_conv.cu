@@ -18,6 +18,7 @@
 // The wide shallow layers of the backward pass take the vertical-halo variant in tc_conv_vh.cu instead.
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
+#include <cstdlib>
 #include <type_traits>
 
 namespace lrpcap {
@@ -32,10 +33,11 @@ struct Geom {
 };
 
 // NS = number of bf16 planes per operand: 2 -> products (0,0)(0,1)(1,0); 3 -> additionally (0,2)(2,0)(1,1).
-template <int BN, int NS>
+// AP = number of A planes staged: NS, or 1 for the two-product backward (one fp16 message plane x [B_hi ; B_lo]).
+template <int BN, int NS, int AP = NS>
 struct Cfg {
   static constexpr int kBTileBytes = BN * 128;
-  static constexpr int kStageBytes = NS * kATileBytes + NS * kBTileBytes;
+  static constexpr int kStageBytes = AP * kATileBytes + NS * kBTileBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes;
   static_assert(kStages >= 2, "tile too large for a double-buffered shared-memory ring");
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -72,12 +74,19 @@ __device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN)
   return t;
 }
 
-template <int BN, int MODE, int NS, bool PROMO, bool F16 = false>
+// A1: two-product mode. A is ONE fp16 plane (the scaled relevance message), B two fp16 planes [hi ; lo] that sit back to
+// back in shared memory. BN <= 128: one MMA with N = 2 BN per K slice (accumulator columns [0, BN) = A*hi, [BN, 2 BN) =
+// A*lo, summed by the epilogue); BN = 256: two N = 256 MMAs into the same accumulator.
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
-  using C = Cfg<BN, NS>;
-  using ST = typename std::conditional<NS == 3, StoreSplit3,
-                                       typename std::conditional<F16, StoreSplitH, StoreSplit>::type>::type;
+  static_assert(!A1 || (NS == 2 && F16), "two-product mode: one fp16 A plane x two fp16 B planes");
+  constexpr int AP = A1 ? 1 : NS;
+  constexpr bool BCAT = A1 && BN <= 128;
+  constexpr int ACC = BCAT ? 2 * BN : BN;             // TMEM columns per accumulator buffer
+  using C = Cfg<BN, NS, AP>;
+  using ST = typename std::conditional<A1, StoreH1, typename std::conditional<NS == 3, StoreSplit3,
+                                       typename std::conditional<F16, StoreSplitH, StoreSplit>::type>::type>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -104,14 +113,14 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_k = g.taps * g.cblocks;
-  const uint32_t stage_tx = (uint32_t)NS * ((uint32_t)(g.TW * g.TH) * 128u + (uint32_t)C::kBTileBytes);
+  const uint32_t stage_tx = (uint32_t)AP * (uint32_t)(g.TW * g.TH) * 128u + (uint32_t)NS * (uint32_t)C::kBTileBytes;
 
   if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
@@ -134,11 +143,12 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
             dx = tap % 3 - 1;
           }
 #pragma unroll
-          for (int p = 0; p < NS; ++p) {
+          for (int p = 0; p < AP; ++p)
             tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], cb * kBlockK, tc.x0 + dx, tc.y0 + dy, tc.item);
-            tma_load_2d(&tm.b[p], st + NS * kATileBytes + p * C::kBTileBytes, &full_bar[s], cb * kBlockK,
+#pragma unroll
+          for (int p = 0; p < NS; ++p)
+            tma_load_2d(&tm.b[p], st + AP * kATileBytes + p * C::kBTileBytes, &full_bar[s], cb * kBlockK,
                         tap * g.Nout + tc.n0);
-          }
         }
       }
     }
@@ -146,6 +156,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       constexpr uint32_t idesc = make_idesc(128, BN, F16);
+      constexpr uint32_t idesc_cat = make_idesc(128, BCAT ? 2 * BN : BN, F16);
       uint32_t it = 0, tl = 0;   // tl counts accumulator hand-overs: one per tile, or one per `group` k-steps (promotion)
       const int gsz = PROMO ? g.group : num_k;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -153,7 +164,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           const uint32_t buf = tl & 1u;
           mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + buf * BN;
+          const uint32_t tmem_d = tmem_base + buf * ACC;
           const int kk1 = (kk0 + gsz < num_k) ? kk0 + gsz : num_k;
           for (int kk = kk0; kk < kk1; ++kk, ++it) {
             const uint32_t s = it % C::kStages;
@@ -164,14 +175,21 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
             uint64_t da[NS], db[NS];
 #pragma unroll
             for (int p = 0; p < NS; ++p) {
-              da[p] = make_desc_sw128(sbase + p * kATileBytes);
-              db[p] = make_desc_sw128(sbase + NS * kATileBytes + p * C::kBTileBytes);
+              da[p] = make_desc_sw128(sbase + (p < AP ? p : 0) * kATileBytes);
+              db[p] = make_desc_sw128(sbase + AP * kATileBytes + p * C::kBTileBytes);
             }
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
               const uint32_t first = (kk != kk0 || k != 0) ? 1u : 0u;   // a fresh accumulator starts every group
-              if (NS == 3) {   // small terms first
+              if (A1) {
+                if (BCAT) {
+                  umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc_cat, first);   // [A*hi | A*lo]
+                } else {
+                  umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, first);
+                  umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
+                }
+              } else if (NS == 3) {   // small terms first
                 umma_bf16(tmem_d, da[1] + adv, db[1] + adv, idesc, first);
                 umma_bf16(tmem_d, da[0] + adv, db[NS - 1] + adv, idesc, 1u);
                 umma_bf16(tmem_d, da[NS - 1] + adv, db[0] + adv, idesc, 1u);
@@ -222,13 +240,35 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           const uint32_t buf = tl & 1u;
           mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
           tc_fence_after();
-          const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+          const uint32_t lane_base = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
+          // the partial accumulator comes out in batches of up to 64 columns per wait: a wait per 16 columns left the
+          // epilogue, not the tensor pipe, pacing the promoted kernels (the load -> wait latency was paid kChunks times)
+          constexpr int kBatch = BCAT ? 2 : 4;              // chunks per wait (BCAT reads two column blocks per chunk)
 #pragma unroll
-          for (int ci = 0; ci < kChunks; ++ci) {
-            float v[16];
-            tmem_ld16(lane_base + (uint32_t)((half + ci * (kEpiWarps / 4)) * 16), v);
+          for (int c0 = 0; c0 < kChunks; c0 += kBatch) {
+            uint32_t r[kBatch][16], w[BCAT ? kBatch : 1][16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[ci][i] += v[i];
+            for (int b = 0; b < kBatch; ++b) {
+              if (c0 + b < kChunks) {
+                const uint32_t col = (uint32_t)((half + (c0 + b) * (kEpiWarps / 4)) * 16);
+                tmem_ld16_issue(lane_base + col, r[b]);
+                if (BCAT) tmem_ld16_issue(lane_base + BN + col, w[b]);
+              }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+              if (c0 + b < kChunks) {
+                tmem_ld_fence16(r[b]);
+                if (BCAT) tmem_ld_fence16(w[b]);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  float v = __uint_as_float(r[b][i]);
+                  if (BCAT) v += __uint_as_float(w[b][i]);
+                  acc[c0 + b][i] += v;
+                }
+              }
+            }
           }
           tc_fence_before();
           __syncwarp();
@@ -263,10 +303,20 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         }
         mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
         tc_fence_after();
-        const uint32_t lane_base = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+        const uint32_t lane_base = tmem_base + buf * ACC + ((uint32_t)(q * 32) << 16);
+        auto ld_chunk = [&](uint32_t col, float (&v)[16]) {
+          if (BCAT) {
+            float w[16];
+            tmem_ld16x2(lane_base + col, lane_base + BN + col, v, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          } else {
+            tmem_ld16(lane_base + col, v);
+          }
+        };
         if constexpr (MODE == EPI_BWD) {
           constexpr int kStep = kEpiWarps / 4;
-          auto load_acc = [&](int c, float (&v)[16]) { tmem_ld16(lane_base + (uint32_t)((half + c * kStep) * 16), v); };
+          auto load_acc = [&](int c, float (&v)[16]) { ld_chunk((uint32_t)((half + c * kStep) * 16), v); };
           if (e.up == 2)
             epi_bwd_chunks<2, kChunks, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
           else
@@ -276,7 +326,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
             float v[16];
             __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-            tmem_ld16(lane_base + (uint32_t)(c * 16), v);
+            ld_chunk((uint32_t)(c * 16), v);
             if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
           }
         }
@@ -290,7 +340,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC);
 }
 
 }  // namespace
@@ -357,16 +407,16 @@ int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
 
 namespace {
 
-template <int BN, int MODE, int NS, bool PROMO, bool F16 = false>
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false>
 int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
-  using C = Cfg<BN, NS>;
+  using C = Cfg<BN, NS, A1 ? 1 : NS>;
   static int smem_state[kMaxDevices] = {};
-  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_kernel<BN, MODE, NS, PROMO, F16>, C::kSmemBytes, smem_state));
+  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1>, C::kSmemBytes, smem_state));
   const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv: %lld tiles out of range", tiles);
   const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
-  tc_conv_kernel<BN, MODE, NS, PROMO, F16><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
+  tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -387,15 +437,23 @@ int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaS
 
 template <int BN>
 int launch_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  if (planes == kPlanesH1x2) {   // two-product backward: one fp16 message plane x two fp16 weight planes
+    if (mode == EPI_BWD)
+      return g.group > 0 ? launch_t<BN, EPI_BWD, 2, true, true, true>(tm, g, e, stream)
+                         : launch_t<BN, EPI_BWD, 2, false, true, true>(tm, g, e, stream);
+    if (mode == EPI_RAW)
+      return g.group > 0 ? launch_t<BN, EPI_RAW, 2, true, true, true>(tm, g, e, stream)
+                         : launch_t<BN, EPI_RAW, 2, false, true, true>(tm, g, e, stream);
+    set_last_error("tc_conv: the two-product mode supports backward / raw epilogues only (mode %d)", mode);
+    return kErrUnsupported;
+  }
   if (planes == kPlanesF16x2) {   // two half planes, always promoted
-    if constexpr (BN <= 128) {
-      switch (mode) {
-        case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 2, true, true>(tm, g, e, stream);
-        case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 2, true, true>(tm, g, e, stream);
-        case EPI_RAW: return launch_t<BN, EPI_RAW, 2, true, true>(tm, g, e, stream);
-      }
+    switch (mode) {
+      case EPI_FWD_TRUE: return launch_t<BN, EPI_FWD_TRUE, 2, true, true>(tm, g, e, stream);
+      case EPI_FWD_ZACT: return launch_t<BN, EPI_FWD_ZACT, 2, true, true>(tm, g, e, stream);
+      case EPI_RAW: return launch_t<BN, EPI_RAW, 2, true, true>(tm, g, e, stream);
     }
-    set_last_error("tc_conv: half-plane operands support forward / raw epilogues with BN <= 128 only (mode %d, BN %d)", mode, BN);
+    set_last_error("tc_conv: half-plane operands support forward / raw epilogues only (mode %d)", mode);
     return kErrUnsupported;
   }
   if (planes == 3) {
@@ -439,9 +497,12 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   LRPCAP_REQUIRE(a.Nout > 0 && a.Nout % 64 == 0, kErrShape, "tc_conv: Nout=%d must be a positive multiple of 64", a.Nout);
   LRPCAP_REQUIRE(a.taps == 9 || a.taps == 1, kErrShape, "tc_conv: taps must be 1 or 9");
   LRPCAP_REQUIRE(a.n_items > 0 && a.H > 0 && a.W > 0, kErrShape, "tc_conv: empty problem");
-  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3 || a.planes == kPlanesF16x2, kErrInvalidArg,
-                 "tc_conv: planes must be 2, 3 or 4 (two half planes)");
-  const int BN = (a.planes == 2 && a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
+  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3 || a.planes == kPlanesF16x2 || a.planes == kPlanesH1x2, kErrInvalidArg,
+                 "tc_conv: planes must be 2, 3, 4 (two half planes) or 5 (two-product backward)");
+  // N = 256 for the backward modes (half the shared-memory operand bytes per MMA flop of N = 128). The forward modes
+  // (3 planes / two half planes, promoted every k-step) stay at N <= 128: with N = 256 the per-k-step accumulator drain
+  // (256 columns) outweighed the operand saving (measured: forward 15.0 -> 18.0 ms per 64 images).
+  const int BN = ((a.planes == 2 || a.planes == kPlanesH1x2) && a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
   if (tc_conv_vh_eligible(a, BN)) return tc_conv_vh_launch(a, BN, stream);   // wide shallow layers: tc_conv_vh.cu
   Geom g;
   g.H = a.H;
@@ -454,15 +515,17 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
-  g.group = a.planes != 2 ? (a.promote_every > 0 ? a.promote_every : 1) : (a.promote_every > 0 ? a.promote_every : 0);
+  g.group = (a.planes != 2 && a.planes != kPlanesH1x2) ? (a.promote_every > 0 ? a.promote_every : 1)
+                                                        : (a.promote_every > 0 ? a.promote_every : 0);
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
   Maps tm;
   const int n_planes = a.planes == 3 ? 3 : 2;
+  const int a_planes = a.planes == kPlanesH1x2 ? 1 : n_planes;
   for (int pl = 0; pl < 3; ++pl) {
     const int q = pl < n_planes ? pl : 0;   // unused third slot aliases plane 0
-    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)q * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
+    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(q < a_planes ? q : 0) * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
     LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)q * a.B_elems, a.taps * a.Nout, a.C, BN));
   }
 

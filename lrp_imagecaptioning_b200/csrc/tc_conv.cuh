@@ -53,6 +53,12 @@ struct EpiParams {
   void* out_msg = nullptr;          // split storage [items, H*up, W*up, Nout]
   int out_planar_f32 = 0;              // 1: write the message as fp32 [items][NO][H*up][W*up] (read by last_dgrad only)
   size_t out_msg_elems = 0;
+  // two-product backward (TcConvArgs::planes == kPlanesH1x2): per-item scale bookkeeping, see epilogue.cuh
+  const unsigned* mx_in = nullptr;
+  unsigned* mx_out = nullptr;
+  const int* kt_in = nullptr;
+  int* kt_out = nullptr;
+  int target_exp = 4;               // predicted maximum of the outgoing fp16 plane: 2^target_exp
 };
 
 struct TcConvArgs {
@@ -62,7 +68,8 @@ struct TcConvArgs {
   const void* B = nullptr;  // split storage [taps * Nout, C]
   size_t B_elems = 0;
   int taps = 9, Nout = 0;
-  int planes = 2;           // 4 (kPlanesF16x2): two IEEE half planes, 3 products, promoted every k-step (forward / raw only);
+  int planes = 2;           // 5 (kPlanesH1x2): A = ONE fp16 plane (scaled message), B = two fp16 planes, 2 MMA products (backward /
+                            // raw only); 4 (kPlanesF16x2): two IEEE half planes, 3 products, promoted every k-step (forward / raw only);
                             // otherwise bf16 planes of A, B and of the forward epilogue's activation tensors: 2 (hi, lo: 3 MMA
                             // products, 16-bit operands) or 3 (hi, mid, lo: 6 products, fp32-exact operands; forward only)
   int promote_every = 0;    // 2-plane only: > 0 sums partial accumulators in fp32 registers every n k-steps (64 channels

@@ -21,6 +21,7 @@
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace lrpcap {
 
@@ -34,8 +35,7 @@ constexpr int kTW = 16, kTH = 16, kTM = 2;              // CTA tile: 16 x 16 pix
 constexpr int kMW = kTW / kTM;                          // MMA tile width: 8 pixels = one 1024 B swizzle group per row
 constexpr int kPatchRows = kTH + 2;                     // 18 pixel rows of 8 pixels
 constexpr int kAPlane = kPatchRows * kMW * 128;         // 18,432 B per bf16 plane (multiple of 1024)
-constexpr int kASlot = 2 * kAPlane;
-constexpr int kNA = 4;
+constexpr int kNAMax = 6;
 constexpr int kMaxNB = 8;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -63,9 +63,15 @@ __device__ __forceinline__ VhTile vh_tile(const VhGeom& g, int tile, int BN) {
   return t;
 }
 
-template <int BN, int MODE, bool NCAT>
+// A1: two-product mode (tc_conv.cu): ONE fp16 message plane x [B_hi ; B_lo]. NCAT: a single N = 128 MMA per K slice;
+// BN = 128: two N = 128 MMAs into the same accumulator. The patch slots are half as large, so the ring is deeper.
+template <int BN, int MODE, bool NCAT, bool A1 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDev e, const int total_tiles) {
+  constexpr int AP = A1 ? 1 : 2;
+  constexpr int kASlot = AP * kAPlane;
+  constexpr int kNA = A1 ? 6 : 4;
+  using ST = typename std::conditional<A1, StoreH1, StoreSplit>::type;
   constexpr int kBPlane = BN * 128;
   constexpr int kBSlot = 2 * kBPlane;
   constexpr int ACC = NCAT ? 2 * BN : BN;               // accumulator columns per MMA tile
@@ -129,7 +135,7 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
               mbar_expect_tx(&afull[sa], (uint32_t)kASlot);
               uint8_t* ap = a_ring + sa * kASlot;
 #pragma unroll
-              for (int p = 0; p < 2; ++p)
+              for (int p = 0; p < AP; ++p)
                 tma_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], cb * kBlockK, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1,
                             tc.item);
               if (j == (JINNER ? kTM - 1 : 0)) {   // the three weight taps of this dx, used by both MMA tiles
@@ -152,8 +158,8 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_n = make_idesc(128, BN);
-      constexpr uint32_t idesc_cat = make_idesc(128, NCAT ? 2 * BN : BN);
+      constexpr uint32_t idesc_n = make_idesc(128, BN, A1);
+      constexpr uint32_t idesc_cat = make_idesc(128, NCAT ? 2 * BN : BN, A1);
       uint32_t ia = 0, ib = 0, tl = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t buf = tl & 1u;
@@ -174,13 +180,20 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
               for (int j = 0; j < kTM; ++j) {
                 const uint32_t abase = smem_u32(a_ring + ((ia + j) % kNA) * kASlot);
                 da_hi[j] = make_desc_sw128(abase + (uint32_t)dyi * 1024u);
-                da_lo[j] = make_desc_sw128(abase + kAPlane + (uint32_t)dyi * 1024u);
+                da_lo[j] = make_desc_sw128(abase + (A1 ? 0 : kAPlane) + (uint32_t)dyi * 1024u);
               }
               auto mma_slice = [&](int j, int k) {
                 const uint64_t adv = (uint64_t)(k * 2);
                 const uint32_t acc_k = (accum != 0u || dyi != 0 || k != 0) ? 1u : 0u;   // the tile's first MMA overwrites
                 const uint32_t d = tmem_d + j * ACC;
-                if (NCAT) {
+                if (A1) {
+                  if (NCAT) {
+                    umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_cat, acc_k);   // [A*hi | A*lo]
+                  } else {
+                    umma_bf16(d, da_hi[j] + adv, db_lo + adv, idesc_n, acc_k);
+                    umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_n, 1u);
+                  }
+                } else if (NCAT) {
                   umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_cat, acc_k);   // [hi*hi | hi*lo]
                   umma_bf16(d, da_lo[j] + adv, db_hi + adv, idesc_n, 1u);        // += lo*hi into the first block
                 } else {
@@ -257,16 +270,16 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
       };
       if constexpr (MODE == EPI_BWD) {
         if (e.up == 2)
-          epi_bwd_chunks<2, BN / 16, StoreSplit>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0, 16, valid, load_acc);
+          epi_bwd_chunks<2, BN / 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0, 16, valid, load_acc);
         else
-          epi_bwd_chunks<1, BN / 16, StoreSplit>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0, 16, valid, load_acc);
+          epi_bwd_chunks<1, BN / 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0, 16, valid, load_acc);
       } else {
 #pragma unroll 1
         for (int c = 0; c < BN / 16; ++c) {
           float v[16];
           __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
           load_acc(c, v);
-          if (valid) epi_apply<MODE, 16, StoreSplit>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+          if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
         }
       }
       tc_fence_before();
@@ -280,30 +293,32 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int BN, int MODE, bool NCAT>
+template <int BN, int MODE, bool NCAT, bool A1>
 int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) {
   constexpr int kBSlot = 2 * BN * 128;
+  constexpr int kASlot = (A1 ? 1 : 2) * kAPlane;
+  constexpr int kNA = A1 ? 6 : 4;
   int nb = (kSmemLimit - 1024 - 512 - kNA * kASlot) / kBSlot;
   if (nb > kMaxNB) nb = kMaxNB;
   LRPCAP_REQUIRE(nb >= 2, kErrUnsupported, "tc_conv_vh: no room for a weight ring (BN=%d)", BN);
   g.NB = nb;
   const int smem = kNA * kASlot + nb * kBSlot + 1024 + 512;
   static int smem_state[kMaxDevices] = {};
-  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_vh_kernel<BN, MODE, NCAT>, smem, smem_state));
+  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_vh_kernel<BN, MODE, NCAT, A1>, smem, smem_state));
   const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv_vh: %lld tiles out of range", tiles);
   const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-  tc_conv_vh_kernel<BN, MODE, NCAT><<<grid, kThreads, smem, stream>>>(tm, g, e, (int)tiles);
+  tc_conv_vh_kernel<BN, MODE, NCAT, A1><<<grid, kThreads, smem, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 
-template <int BN, bool NCAT>
+template <int BN, bool NCAT, bool A1>
 int launch_vh_mode(int mode, const VhMaps& tm, const VhGeom& g, const EpiDev& e, cudaStream_t stream) {
   switch (mode) {
-    case EPI_BWD: return launch_vh<BN, EPI_BWD, NCAT>(tm, g, e, stream);
-    case EPI_RAW: return launch_vh<BN, EPI_RAW, NCAT>(tm, g, e, stream);
+    case EPI_BWD: return launch_vh<BN, EPI_BWD, NCAT, A1>(tm, g, e, stream);
+    case EPI_RAW: return launch_vh<BN, EPI_RAW, NCAT, A1>(tm, g, e, stream);
   }
   set_last_error("tc_conv_vh: epilogue mode %d not instantiated", mode);
   return kErrUnsupported;
@@ -321,7 +336,7 @@ bool vh_enabled() {
 }  // namespace
 
 bool tc_conv_vh_eligible(const TcConvArgs& a, int BN) {
-  return vh_enabled() && a.taps == 9 && a.planes == 2 && a.promote_every <= 0 && (BN == 64 || BN == 128) &&
+  return vh_enabled() && a.taps == 9 && (a.planes == 2 || a.planes == kPlanesH1x2) && a.promote_every <= 0 && (BN == 64 || BN == 128) &&
          a.W % kTW == 0 && a.H % kTH == 0 && (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW);
 }
 
@@ -340,14 +355,19 @@ int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream) {
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
   VhMaps tm;
+  const bool a1 = a.planes == kPlanesH1x2;
   for (int pl = 0; pl < 2; ++pl) {
-    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)pl * a.A_elems, a.n_items, a.H, a.W, a.C, kMW, kPatchRows));
+    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(a1 ? 0 : pl) * a.A_elems, a.n_items, a.H, a.W, a.C, kMW, kPatchRows));
     LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)pl * a.B_elems, a.taps * a.Nout, a.C, BN));
   }
   EpiDev e;
   LRPCAP_TRY(make_epi_dev(a.epi, &e));
-  if (BN == 64) return launch_vh_mode<64, true>(a.epi.mode, tm, g, e, stream);
-  return launch_vh_mode<128, false>(a.epi.mode, tm, g, e, stream);
+  if (a1) {
+    if (BN == 64) return launch_vh_mode<64, true, true>(a.epi.mode, tm, g, e, stream);
+    return launch_vh_mode<128, false, true>(a.epi.mode, tm, g, e, stream);
+  }
+  if (BN == 64) return launch_vh_mode<64, true, false>(a.epi.mode, tm, g, e, stream);
+  return launch_vh_mode<128, false, false>(a.epi.mode, tm, g, e, stream);
 }
 
 }  // namespace lrpcap

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .synth import VGG16_CFG
+from .synth import VGG16_CFG, VGG19_CFG
 
 
 class RuleSpec(object):
@@ -30,19 +30,23 @@ def _as_cuda_f32(x, device):
 
 
 class ImageModel(object):
-    """VGG16 conv stack with Keras layer names; `weights` = list of 13 (kernel HWIO, bias)."""
+    """VGG16 (or VGG19) conv stack with Keras layer names; `weights` = list of 13 (16) (kernel HWIO, bias)."""
     layer_names = [c[0] for c in VGG16_CFG]
 
     def __init__(self, weights, image_hw=224, precision="bf16x3", device="cuda:0"):
-        if len(weights) != 13:
-            raise ValueError("VGG16 to block5_conv3 has 13 conv layers, got %d" % len(weights))
-        for (k, b), (name, cin, cout, _) in zip(weights, VGG16_CFG):
+        if len(weights) not in (13, 16):
+            raise ValueError("VGG16 to block5_conv3 has 13 conv layers (VGG19 to block5_conv4: 16), got %d" % len(weights))
+        self.cfg = VGG16_CFG if len(weights) == 13 else VGG19_CFG
+        self.arch = 0 if len(weights) == 13 else 1
+        self.layer_names = [c[0] for c in self.cfg]
+        for (k, b), (name, cin, cout, _) in zip(weights, self.cfg):
             if tuple(k.shape) != (3, 3, cin, cout) or tuple(b.shape) != (cout,):
                 raise ValueError("layer %s: expected kernel (3,3,%d,%d) and bias (%d,)" % (name, cin, cout, cout))
         self.weights = [(np.ascontiguousarray(k, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32))
                         for k, b in weights]
         self.image_hw = int(image_hw)
-        self.precision = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3_TC}[precision]
+        self.precision = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3_TC, "f16x2": _lib.PREC_F16X2_TC,
+                          "tc": _lib.PREC_TC_AUTO}[precision]
         self.device = torch.device(device)
         self._h = None
         self._state = None   # (rule key, n_images) of the resident forward state
@@ -54,23 +58,25 @@ class ImageModel(object):
                 raise _lib.LrpcapError(-3, "no CUDA device: lrpcap has no CPU path")
             lib = _lib.load()
             torch.cuda.set_device(self.device)
-            ks = (_lib.c_float_p * 13)(*[_lib.fptr(k) for k, _ in self.weights])
-            bs = (_lib.c_float_p * 13)(*[_lib.fptr(b) for _, b in self.weights])
+            n = len(self.weights)
+            ks = (_lib.c_float_p * n)(*[_lib.fptr(k) for k, _ in self.weights])
+            bs = (_lib.c_float_p * n)(*[_lib.fptr(b) for _, b in self.weights])
             h = _lib.c_void_p()
-            _lib.check(lib.lrpcap_encoder_create(ctypes.byref(h), ks, bs, self.image_hw, self.precision))
+            _lib.check(lib.lrpcap_encoder_create_arch(ctypes.byref(h), self.arch, ks, bs, self.image_hw, self.precision))
             self._h = h
         return self._h
 
     def set_weights(self, weights):
         """Replace the 13 (kernel, bias) pairs in place (keeps the handle's large buffers; the forward state is dropped)."""
         weights = [(np.ascontiguousarray(k, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)) for k, b in weights]
-        if len(weights) != 13 or any(k.shape != k0.shape or b.shape != b0.shape for (k, b), (k0, b0) in zip(weights, self.weights)):
-            raise ValueError("set_weights needs 13 (kernel, bias) pairs with the shapes the model was built with")
+        if len(weights) != len(self.weights) or any(k.shape != k0.shape or b.shape != b0.shape for (k, b), (k0, b0) in zip(weights, self.weights)):
+            raise ValueError("set_weights needs %d (kernel, bias) pairs with the shapes the model was built with" % len(self.weights))
         self.weights = weights
         self._state = None
         if self._h is not None:
-            ks = (_lib.c_float_p * 13)(*[_lib.fptr(k) for k, _ in self.weights])
-            bs = (_lib.c_float_p * 13)(*[_lib.fptr(b) for _, b in self.weights])
+            n = len(self.weights)
+            ks = (_lib.c_float_p * n)(*[_lib.fptr(k) for k, _ in self.weights])
+            bs = (_lib.c_float_p * n)(*[_lib.fptr(b) for _, b in self.weights])
             _lib.check(_lib.load().lrpcap_encoder_set_weights(self._h, ks, bs))
 
     def close(self):
@@ -145,10 +151,10 @@ class ImageModel(object):
         """{conv layer index: uint8 [N, H/2, W/2, C]} window position (sy*2+sx) each pooled element routes to."""
         n = self._state[1]
         out = {}
-        for l, (_, _, cout, pool) in enumerate(VGG16_CFG):
+        for l, (_, _, cout, pool) in enumerate(self.cfg):
             if not pool:
                 continue
-            ho = (self.image_hw >> sum(1 for c in VGG16_CFG[:l] if c[3])) // 2
+            ho = (self.image_hw >> sum(1 for c in self.cfg[:l] if c[3])) // 2
             a = np.empty((n, ho, ho, cout), dtype=np.uint8)
             _lib.check(_lib.load().lrpcap_encoder_debug_pool_routes(self.handle(), l, _lib.c_void_p(a.ctypes.data)))
             out[l] = a
@@ -157,10 +163,21 @@ class ImageModel(object):
     def multiplier(self, layer, branch=0):
         """Dense per-image multiplier G of conv layer `layer` (< 12), [N, H, W, C] float32, pool routing folded in."""
         n = self._state[1]
-        h = self.image_hw >> sum(1 for c in VGG16_CFG[:layer] if c[3])
-        a = np.empty((n, h, h, VGG16_CFG[layer][2]), dtype=np.float32)
+        h = self.image_hw >> sum(1 for c in self.cfg[:layer] if c[3])
+        a = np.empty((n, h, h, self.cfg[layer][2]), dtype=np.float32)
         _lib.check(_lib.load().lrpcap_encoder_debug_multiplier(self.handle(), int(layer), int(branch), _lib.fptr(a)))
         return a
+
+    def message_scales(self, cap_words=4096):
+        """Two-product backward: (max [layers+1, chunk] float32, log2 scale [layers, chunk] int32) of the last chunk."""
+        n = len(self.weights)
+        mx = np.zeros((n + 1) * cap_words, dtype=np.float32)
+        kt = np.zeros(n * cap_words, dtype=np.int32)
+        chunk = ctypes.c_int(0)
+        _lib.check(_lib.load().lrpcap_encoder_debug_message_scales(self.handle(), _lib.fptr(mx), _lib.iptr(kt), cap_words,
+                                                                   ctypes.byref(chunk)))
+        c = chunk.value
+        return mx[:(n + 1) * c].reshape(n + 1, c), kt[:n * c].reshape(n, c)
 
     def launches(self):
         return int(_lib.load().lrpcap_encoder_launches(self.handle()))

@@ -23,6 +23,11 @@ ALPHA = 1
 BETA = 0
 
 
+class _DefaultPreprocessor(object):
+    SOS_TOKEN_LABEL_ENCODED = 1
+    EOS_TOKEN_LABEL_ENCODED = 2
+
+
 class ExplainImgCaptioningAttentionModel(object):
     _decoder_kind = None
 
@@ -35,7 +40,9 @@ class ExplainImgCaptioningAttentionModel(object):
         self._image_model = model.image_model
         self._img_encoder = model.img_encoder
         self._CNN_explainer = LRPSequentialPresetA(self._image_model, epsilon=EPS, neuron_selection_mode="replace")
-        self._preprocessor = dataset_provider.caption_preprocessor
+        # the reference always gets a DatasetProvider; without one (dataset_provider=None) the tokenizer's conventional
+        # ids stand in: SOS = 1, EOS = 2 (models/preprocessors.py: the first two fitted tokens)
+        self._preprocessor = dataset_provider.caption_preprocessor if dataset_provider is not None else _DefaultPreprocessor()
         self._dataset_provider = dataset_provider
         self._max_caption_length = max_caption_length
         self._hidden_dim = model._hidden_dim

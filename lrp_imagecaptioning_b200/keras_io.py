@@ -7,14 +7,29 @@ the walk and is not a dependency of the package: without it `read_keras_hdf5` ra
 import numpy as np
 
 
+_WRAPPERS = ("external_attention_rnn_wrapper", "external_bottom_up_attention")   # models/model.py:470, 606 (+ Keras "_N" suffix)
+
+
 def _key(dataset_name):
-    """'model_weights/block1_conv1/block1_conv1/kernel:0' -> 'block1_conv1/kernel'."""
+    """HDF5 dataset path -> the container's '<layer>/<tensor>' key.
+
+    Plain layers (also nested in a sub-model): 'model_weights/vgg16/block1_conv1/kernel:0' -> 'block1_conv1/kernel'.
+    The two attention wrappers name their own tensors '<layer>_<tensor>' (models/model.py:555-570, 702-724:
+    `name="{}_Wv".format(self.name)`) and hold the wrapped LSTM's kernel / recurrent_kernel / bias (built inside the
+    wrapper's scope or under 'lstm_N/'), so Keras writes
+        'model_weights/<layer>/<layer>/<layer>_Wv:0', '.../<layer>/<layer>/kernel:0' or '.../<layer>/lstm_1/kernel:0'
+    -> '<layer>/Wv', '<layer>/kernel'."""
     parts = [p for p in dataset_name.split("/") if p]
     if len(parts) < 2:
         return None
     tensor = parts[-1]
     if tensor.endswith(":0"):
         tensor = tensor[:-2]
+    for p in parts[:-1]:
+        if p.startswith(_WRAPPERS):
+            if tensor.startswith(p + "_"):
+                tensor = tensor[len(p) + 1:]
+            return p + "/" + tensor
     return parts[-2] + "/" + tensor
 
 

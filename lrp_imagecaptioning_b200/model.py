@@ -54,7 +54,7 @@ class CaptioningModel(object):
         self.image_hw = int(image_hw)
         self.precision = precision
         self.device = device
-        self.img_encoder = "vgg16"
+        self.img_encoder = "vgg16" if len(vgg) == 13 else "vgg19"   # models/model.py:419-421 (`img_encoder`)
         self._hidden_dim = dec["hidden_dim"]
         self._embedding_dim = dec["embedding_dim"]
         self.D = dec["D"]
@@ -72,7 +72,7 @@ class CaptioningModel(object):
     # ---- weight files with Keras names
     def state_dict(self):
         out = {}
-        for (k, b), name in zip(self.vgg, ImageModel.layer_names):
+        for (k, b), name in zip(self.vgg, self.image_model.layer_names):
             out[name + "/kernel"] = k
             out[name + "/bias"] = b
         for ours, keras_name in _names(self.kind).items():
@@ -91,7 +91,7 @@ class CaptioningModel(object):
         else:
             z = np.load(path)
         vgg = []
-        for name in ImageModel.layer_names:
+        for name in self.image_model.layer_names:
             vgg.append((np.asarray(z[name + "/kernel"], dtype=np.float32), np.asarray(z[name + "/bias"], dtype=np.float32)))
         dec = dict(self.dec)
         for ours, keras_name in _names(self.kind).items():

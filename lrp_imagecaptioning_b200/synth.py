@@ -20,6 +20,15 @@ VGG16_CFG = [  # (keras name, Cin, Cout, pool_after)
     ("block5_conv1", 512, 512, False), ("block5_conv2", 512, 512, False), ("block5_conv3", 512, 512, False),
 ]
 
+VGG19_CFG = [  # keras.applications.vgg19 up to block5_conv4 (models/model.py:419-421)
+    ("block1_conv1", 3, 64, False), ("block1_conv2", 64, 64, True),
+    ("block2_conv1", 64, 128, False), ("block2_conv2", 128, 128, True),
+    ("block3_conv1", 128, 256, False), ("block3_conv2", 256, 256, False), ("block3_conv3", 256, 256, False), ("block3_conv4", 256, 256, True),
+    ("block4_conv1", 256, 512, False), ("block4_conv2", 512, 512, False), ("block4_conv3", 512, 512, False), ("block4_conv4", 512, 512, True),
+    ("block5_conv1", 512, 512, False), ("block5_conv2", 512, 512, False), ("block5_conv3", 512, 512, False), ("block5_conv4", 512, 512, False),
+]
+ENCODER_CFG = {"vgg16": VGG16_CFG, "vgg19": VGG19_CFG}
+
 CAFFE_MEAN_BGR = np.array([103.939, 116.779, 123.68], dtype=np.float32)
 
 
@@ -27,15 +36,19 @@ def rng(seed):
     return np.random.Generator(np.random.PCG64(seed))
 
 
-def vgg16_weights(seed=0, bias_std=0.01):
-    """List of 13 (kernel HWIO float32, bias float32)."""
+def vgg16_weights(seed=0, bias_std=0.01, cfg=None):
+    """List of 13 (kernel HWIO float32, bias float32); cfg=VGG19_CFG: the 16 of VGG19."""
     g = rng(seed)
     out = []
-    for _, cin, cout, _ in VGG16_CFG:
+    for _, cin, cout, _ in (cfg or VGG16_CFG):
         k = g.standard_normal((3, 3, cin, cout)).astype(np.float32) * np.float32(np.sqrt(2.0 / (9 * cin)))
         b = (g.standard_normal((cout,)) * bias_std).astype(np.float32)
         out.append((k, b))
     return out
+
+
+def vgg19_weights(seed=0, bias_std=0.01):
+    return vgg16_weights(seed, bias_std, VGG19_CFG)
 
 
 def images(n, hw=224, seed=1):

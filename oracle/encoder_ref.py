@@ -26,6 +26,11 @@ import torch
 import torch.nn.functional as Fn
 
 POOL_AFTER = (1, 3, 6, 9)   # 0-based conv indices followed by a 2x2/2 max-pool (VGG16 to block5_conv3)
+POOL_AFTER_VGG19 = (1, 3, 7, 11)   # VGG19 to block5_conv4 (16 convs)
+
+
+def _pools(weights):
+    return POOL_AFTER_VGG19 if len(weights) == 16 else POOL_AFTER
 SAFE_FACTOR = 1e-7          # keras.backend.epsilon(), SafeDivide default factor
 
 
@@ -90,7 +95,7 @@ def forward(images_nhwc, weights, n_layers=None, force=None):
         k, b = weights[l]
         xs.append(x)
         x = _relu(_conv(x, k, b), l, force)
-        if l in POOL_AFTER:
+        if l in _pools(weights):
             xs.append(x)
             x = _pool(x, l, force)
     return xs, _to_nhwc(x)
@@ -102,7 +107,7 @@ def pool_routes(images_nhwc, weights):
     out, j = {}, 0
     for l in range(len(weights)):
         j += 1
-        if l in POOL_AFTER:
+        if l in _pools(weights):
             x = xs[j]
             j += 1
             N, C, H, W = x.shape
@@ -122,7 +127,7 @@ def relu_masks(images_nhwc, weights):
     for l in range(len(weights) - 1):
         j += 1                      # xs[j] is relu(z_l): the pool's input when a pool follows, else the next conv's input
         out[l] = (xs[j] > 0).permute(0, 2, 3, 1).numpy()
-        if l in POOL_AFTER:
+        if l in _pools(weights):
             j += 1
     return out
 
@@ -201,7 +206,7 @@ def analyze(method, images_nhwc, R_head_nhwc, weights, epsilon=1e-7, alpha=None,
         j = len(xs) - 1
         for l in range(len(weights) - 1, -1, -1):
             k, b = weights[l]
-            if l in POOL_AFTER:
+            if l in _pools(weights):
                 R = _grad(lambda v: _pool(v, l, force), xs[j], R)
                 j -= 1
             if method == "guided_backprop":
@@ -227,7 +232,7 @@ def analyze(method, images_nhwc, R_head_nhwc, weights, epsilon=1e-7, alpha=None,
     j = len(xs) - 1
     for l in range(len(weights) - 1, -1, -1):
         k, b = weights[l]
-        if l in POOL_AFTER:
+        if l in _pools(weights):
             R = _grad(lambda v: _pool(v, l, force), xs[j], R)
             j -= 1
         x = xs[j]

@@ -7,7 +7,8 @@ from tests.util import assert_parity, topk_features
 
 pytestmark = pytest.mark.gpu
 
-SMALL = dict(V=60, H=64, E=64, D=96, L=16, T=6, N=3)
+SMALL = dict(V=60, H=64, E=64, D=96, L=16, T=6, N=3)     # D % 64 != 0: the unfused fp64 / per-GEMM forward
+FUSED = dict(V=60, H=64, E=64, D=64, L=16, T=6, N=3)     # every dimension a multiple of 64: the fused forward (decoder_fused.cuh)
 FULL = dict(V=10000, H=512, E=512, D=512, L=196, T=20, N=2)   # BASELINE.json sizes: V = 10 000, 20 words
 
 
@@ -20,11 +21,11 @@ def _setup(kind, cfg, seed=11):
 
 
 @pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
-@pytest.mark.parametrize("size", ["small", "full"])
+@pytest.mark.parametrize("size", ["small", "fused", "full"])
 def test_decoder_lrp_matches_oracle(kind, size):
     from lrp_imagecaptioning_b200.decoder import DecoderEngine
     from oracle.decoder_ref import DecoderRef
-    cfg = SMALL if size == "small" else FULL
+    cfg = {"small": SMALL, "fused": FUSED, "full": FULL}[size]
     dec, F, cap = _setup(kind, cfg)
     eng = DecoderEngine(dec)
     eng.forward(F, cap)
@@ -81,9 +82,11 @@ def test_decoder_gradient_matches_oracle(kind, size):
 
 
 @pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
-def test_greedy_caption_is_oracle_argmax(kind):
+@pytest.mark.parametrize("cfgname", ["small", "fused"])
+def test_greedy_caption_is_oracle_argmax(kind, cfgname):
     from lrp_imagecaptioning_b200.decoder import DecoderEngine
     from oracle.decoder_ref import DecoderRef
+    SMALL = {"small": globals()["SMALL"], "fused": FUSED}[cfgname]
     dec, F, _ = _setup(kind, SMALL, seed=21)
     eng = DecoderEngine(dec)
     cap = eng.forward(F, T=SMALL["T"], greedy=True, eos=2)
@@ -121,13 +124,15 @@ def test_ragged_word_list_and_order_independence():
 
 
 @pytest.mark.parametrize("kind", ["adaptive", "gridtd"])
-def test_greedy_forward_graph_replay_is_identical(kind, monkeypatch):
+@pytest.mark.parametrize("cfgname", ["small", "fused"])
+def test_greedy_forward_graph_replay_is_identical(kind, cfgname, monkeypatch):
     """The greedy forward is captured into a CUDA graph on a repeated configuration and replayed afterwards: eager,
     captured and replayed calls must give the same captions and the same relevance, also for new features, and the
     same as a decoder that never uses a graph."""
     import torch
     from lrp_imagecaptioning_b200 import synth
     from lrp_imagecaptioning_b200.decoder import DecoderEngine
+    SMALL = {"small": globals()["SMALL"], "fused": FUSED}[cfgname]
     dec, F, _ = _setup(kind, SMALL, seed=31)
     F2 = synth.features(SMALL["N"], L=SMALL["L"], D=SMALL["D"], seed=99)
     wi = np.array([0, 1, 2, 2], dtype=np.int32)

@@ -11,8 +11,10 @@ the oracle pinned to the decisions the CUDA forward took (oracle Forced: same ar
 through lrpcap_encoder_debug_pool_routes / _multiplier) EVERY image agrees to <= 1e-3.  So each case asserts, per image:
   * against the pinned oracle: abs-max-relative error and relative L2 <= tol, conservation sum <= 1e-4, same top-k cells;
   * against the oracle as-is: the same bounds whenever no decision differs, and otherwise a bounded blob (FLIP_TOL);
-and reports the number of differing decisions.  tol = 1e-3, except the Z rule (R / z without stabiliser amplifies the
-1e-6 forward rounding without bound as z -> 0; 3e-3; not a north-star rule).
+and reports the number of differing decisions.  tol = 1e-3, except two rules outside the north-star set, 3e-3: the Z rule
+(R / z without stabiliser amplifies the 1e-6 forward rounding without bound as z -> 0) and epsilon-IgnoreBias (its
+stabiliser sign(z_nobias) * eps flips sign at z_nobias = 0 while the bias keeps the activation, the numerator, alive: a
+third kind of discrete decision, seen once in 20 images even in the exact-fp32 mode).
 """
 import numpy as np
 import pytest
@@ -24,7 +26,7 @@ pytestmark = pytest.mark.gpu
 FLIP_TOL = 8e-2
 SUM_TOL = 1e-4
 MASK_RULES = ("z", "gradient", "ixg", "guided")     # rules whose multipliers are ReLU masks: discontinuous at z = 0
-TOL = {"z": 3e-3}
+TOL = {"z": 3e-3, "eps_ib": 3e-3}
 
 RULES = {
     # name: (oracle method, oracle kwargs, analyzer name, analyzer kwargs)
@@ -67,7 +69,7 @@ def _decisions(m, x, W, rule):
         flips += (routes[l] != own[l]).reshape(n, -1).sum(axis=1)
     masks = None
     if rule in MASK_RULES:
-        masks = {l: m.multiplier(l) != 0 for l in range(12)}
+        masks = {l: m.multiplier(l) != 0 for l in range(len(W) - 1)}
         own_m = ER.relu_masks(x, W)
         for l in masks:
             mine = masks[l]
@@ -145,6 +147,33 @@ def test_relevance_matches_oracle_small(hw, rule, precision):
     ref_p = ER.analyze(om, x[idx], R, W, force=force, **okw)
     assert got.shape == ref.shape == (n, hw, hw, 3)
     _assert_pinned(got, ref_p, ref, flips, "%s hw=%d %s" % (rule, hw, precision), rule, head=R, hw=hw, precision=precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16x2"])
+@pytest.mark.parametrize("rule", ["eps", "presetA", "a2b1", "gradient"])
+def test_vgg19_relevance_matches_oracle(rule, precision):
+    """The reference's other VGG encoder (models/model.py:419-421: `img_encoder='vgg19'`, cut at block5_conv4): 16 convs,
+    pools after 2/2/4/4, same kernels, same 14 x 14 x 512 head."""
+    from lrp_imagecaptioning_b200 import synth
+    from lrp_imagecaptioning_b200.encoder import ImageModel
+    from lrp_imagecaptioning_b200.analyzers import create_analyzer
+    from oracle import encoder_ref as ER
+    if precision == "f16x2" and rule in ("eps", "gradient"):
+        pytest.skip("the two-product backward is offered for the same-sign rules (DESIGN.md section 5)")
+    n, hw = 3, 64
+    idx = np.arange(n, dtype=np.int32)
+    W = synth.vgg19_weights(0, bias_std=0.01)
+    x = synth.images(n, hw, 1)
+    m = ImageModel(W, image_hw=hw, precision=precision)
+    F, R = _head(m, x, idx, 2)
+    assert F.shape == (n, hw // 16, hw // 16, 512)
+    assert_parity(F, ER.features(x, W), "vgg19 features %s" % precision, rel_tol=1e-4, sum_tol=None)
+    om, okw, an, akw = RULES[rule]
+    got = create_analyzer(an, m, **akw).analyze_batch(x, idx, R).cpu().numpy()
+    force, flips = _decisions(m, x, W, rule)
+    ref = ER.analyze(om, x[idx], R, W, **okw)
+    ref_p = ER.analyze(om, x[idx], R, W, force=force, **okw)
+    _assert_pinned(got, ref_p, ref, flips, "vgg19 %s %s" % (rule, precision), rule, head=R, hw=hw, precision=precision)
 
 
 def test_words_of_one_image_share_the_forward_state():

@@ -139,9 +139,22 @@ def test_keras_hdf5_reader_renames_datasets(monkeypatch, tmp_path):
     for (k, b), name in zip(vgg, ImageModel.layer_names):                      # VGG16 nested as a sub-model
         store["model_weights/vgg16/%s/kernel:0" % name] = k
         store["model_weights/vgg16/%s/bias:0" % name] = b
-    for ours, keras_name in _names("gridtd").items():
-        layer, tensor = keras_name.split("/")
-        store["model_weights/%s/%s/%s:0" % (layer, layer, tensor)] = np.asarray(dec[ours])
+    # dataset names as Keras writes them for the reference's layers -- hard-coded from the reference's add_weight calls
+    # (models/model.py:702-724: name='{}_W_va'.format(self.name) ...; the wrapped LSTM's tensors sit under the wrapper)
+    GL = "external_bottom_up_attention_adaptive_1"
+    real = {
+        "image_features_w": "image_features/image_features/kernel:0", "image_features_b": "image_features/image_features/bias:0",
+        "global_w": "global_img_feature/global_img_feature/kernel:0", "global_b": "global_img_feature/global_img_feature/bias:0",
+        "embedding": "embedding_1/embedding_1/embeddings:0", "output_w": "output/output/kernel:0", "output_b": "output/output/bias:0",
+        "lang_wi": GL + "/" + GL + "/kernel:0", "lang_wh": GL + "/" + GL + "/recurrent_kernel:0", "lang_b": GL + "/lstm_1/bias:0",
+        "td_wi": GL + "/" + GL + "/" + GL + "_top_down_lstm_weight_i:0", "td_wh": GL + "/" + GL + "/" + GL + "_top_down_lstm_weight_h:0",
+        "td_b": GL + "/" + GL + "/" + GL + "_top_down_lstm_weight_bias:0",
+        "W_va": GL + "/" + GL + "/" + GL + "_W_va:0", "W_ha": GL + "/" + GL + "/" + GL + "_W_ha:0", "W_a": GL + "/" + GL + "/" + GL + "_W_a:0",
+        "W_x": GL + "/" + GL + "/" + GL + "_W_x:0", "W_h": GL + "/" + GL + "/" + GL + "_W_h:0", "W_s": GL + "/" + GL + "/" + GL + "_W_s:0",
+    }
+    assert sorted(real) == sorted(_names("gridtd"))
+    for ours, ds in real.items():
+        store["model_weights/" + ds] = np.asarray(dec[ours])
 
     class FakeFile(object):
         def __init__(self, path, mode="r"):
@@ -158,6 +171,9 @@ def test_keras_hdf5_reader_renames_datasets(monkeypatch, tmp_path):
     w = keras_io.read_keras_hdf5("keras_model.hdf5")
     assert "block3_conv2/kernel" in w and "embedding_1/embeddings" in w and all(v.dtype == np.float32 for v in w.values())
     assert keras_io._key("model_weights/output/output/bias:0") == "output/bias"
+    AL = "external_attention_rnn_wrapper_local_attention_v3_1"
+    assert keras_io._key("model_weights/%s/%s/%s_Wv:0" % (AL, AL, AL)) == AL + "/Wv"
+    assert keras_io._key("%s/lstm_2/recurrent_kernel:0" % AL) == AL + "/recurrent_kernel"
     # round trip through the container: hdf5 path -> same tensors as the synthetic source
     m = CaptioningModel("gridtd", synth.vgg16_weights(9), synth.decoder_weights("gridtd", V=50, H=64, E=64, D=512, seed=8),
                         image_hw=32)

@@ -118,8 +118,15 @@ def trunc():
                                          torch.from_numpy(B.reshape(3, 3, C, 64)).double().permute(3, 2, 0, 1), padding=1)
         ref = ref.permute(0, 2, 3, 1).numpy()
         row = {"what": "trunc", "C": C, "K": 9 * C}
-        for name, prec in (("fp32_simt", 0), ("bf16x2_nopromote", 1), ("bf16x3planes_promoted", 2), ("f16x2_promoted", 3)):
+        for name, prec in (("fp32_simt", 0), ("bf16x2_nopromote", 1), ("bf16x3planes_promoted", 2), ("f16x2_promoted", 3),
+                           ("h1x2_two_product_nopromote", 4)):
             out = _lib.debug_conv(prec, A, B, 9).astype(np.float64)
+            if prec == 4:    # the A operand is one fp16 plane by construction: compare against the contraction of that operand
+                A16 = A.astype(np.float16).astype(np.float32)
+                r16 = torch.nn.functional.conv2d(torch.from_numpy(A16).double().permute(0, 3, 1, 2),
+                                                 torch.from_numpy(B.reshape(3, 3, C, 64)).double().permute(3, 2, 0, 1), padding=1)
+                rel16 = (out - r16.permute(0, 2, 3, 1).numpy()) / ref
+                row[name + "_vs_fp16_operand"] = {"mean_rel": float(rel16[:, 4:12, 4:12].mean())}
             rel = (out - ref) / ref
             row[name] = {"mean_rel": float(rel[:, 4:12, 4:12].mean()), "rms_rel": float(np.sqrt((rel[:, 4:12, 4:12] ** 2).mean()))}
         emit(row)
@@ -135,4 +142,5 @@ if __name__ == "__main__":
     if "sums" in what:
         sums(hw, n, (rules.split(",") if rules else ["zplus", "a2b1", "presetA"]), [0, 8, 2])
     if "flips" in what:
-        flips(hw, n, (rules.split(",") if rules else ["eps", "presetA", "a2b1", "z", "gradient", "guided"]))
+        flips(hw, n, (rules.split(",") if rules else ["eps", "presetA", "a2b1", "z", "gradient", "guided"]),
+              precision=arg("--precision", "bf16x3"))

@@ -76,6 +76,9 @@ int lrpcap_encoder_create_arch(lrpcap_encoder_t** out, int arch, const float* co
  * per-image state: what `LRPInferenceLayer*` needs between fine-tuning steps (train.py:569-577), where the reference
  * explains the model that is being trained; the large state and message buffers are kept. Synchronises the device. */
 int lrpcap_encoder_set_weights(lrpcap_encoder_t* enc, const float* const* h_kernels_hwio, const float* const* h_biases);
+/* The same from DEVICE tensors (arrays of device pointers, same layouts): the fine-tuning step keeps the trained
+ * parameters on the device, so the explained model follows them without a host round trip. */
+int lrpcap_encoder_set_weights_device(lrpcap_encoder_t* enc, const float* const* d_kernels_hwio, const float* const* d_biases);
 int lrpcap_encoder_destroy(lrpcap_encoder_t* enc);
 
 /* Replaces `_image_model.predict(img)` (explainers.py:375, 1097) and the forward half of
@@ -136,15 +139,22 @@ typedef struct lrpcap_decoder_weights {
 /* keras_logits != 0: grid-TD logits = (h2 + c_hat) W_o + b as in the Keras model (models/model.py:816);
  * 0 (default): h2 W_o + b as in the reference explainer (explainers.py:1154). */
 int lrpcap_decoder_create(lrpcap_decoder_t** out, const lrpcap_decoder_weights_t* w, int sos_token, int keras_logits);
+/* Replaces the weights of an existing handle from DEVICE fp32 tensors (the struct's pointers are device memory, same
+ * layouts and dimensions as at creation): every derived layout is recomputed in place on the device, the forward state is
+ * dropped.  What the LRP-inference fine-tuning step needs between optimizer steps (train.py:569-577). */
+int lrpcap_decoder_set_weights_device(lrpcap_decoder_t* dec, const lrpcap_decoder_weights_t* d_w);
 int lrpcap_decoder_destroy(lrpcap_decoder_t* dec);
 
 /* Replaces `_forward_beam_search(X, caption)` (explainers.py:370-436, 690-778, 1092-1178, 1344-1450) for a batch:
  * teacher-forced decoder forward over T steps storing every intermediate the relevance pass reads.
  * d_features: [n_images, L, D]; h_captions: [n_images, T] tokenizer ids (model index = id - 1).
- * greedy != 0: h_captions is an OUTPUT -- token t is the arg-max of step t's logits. eos_token >= 1: that tokenizer id is
- * excluded from the arg-max (every caption then has exactly T words); eos_token <= 0: plain arg-max. Captions are never
- * truncated at EOS: every image has T positions, and a caller that wants the reference's "stop at EOS" restricts the word
- * list it passes to lrpcap_decoder_relevance itself. */
+ * greedy == 1: h_captions is an OUTPUT -- token t is the arg-max of step t's logits and is fed back as the next input.
+ * greedy == 2 ("predict"): h_captions holds the teacher tokens on input (fed as at greedy == 0) and the arg-max of every
+ * step's logits on output -- `argmax(model.predict(...))` of the fine-tuning loop (train.py:570, models/model.py:1661);
+ * the handle then holds no explainable state (run a greedy == 0 forward on the predicted caption next).
+ * eos_token >= 1: that tokenizer id is excluded from the arg-max (every caption then has exactly T words); eos_token <= 0:
+ * plain arg-max. Captions are never truncated at EOS: every image has T positions, and a caller that wants the reference's
+ * "stop at EOS" restricts the word list it passes to lrpcap_decoder_relevance itself. */
 int lrpcap_decoder_forward(lrpcap_decoder_t* dec, const float* d_features, int n_images, int L, int* h_captions, int T,
                            int greedy, int eos_token, void* stream);
 

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "lrpcap_encoder_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), ctypes.c_int, ctypes.c_int]),
     "lrpcap_encoder_create_arch": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.c_int, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p), ctypes.c_int, ctypes.c_int]),
     "lrpcap_encoder_set_weights": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_float_p), ctypes.POINTER(c_float_p)]),
+    "lrpcap_encoder_set_weights_device": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
     "lrpcap_encoder_destroy": (ctypes.c_int, [c_void_p]),
     "lrpcap_encoder_forward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int, c_void_p]),
     "lrpcap_encoder_features": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
@@ -53,6 +54,7 @@ PROTOTYPES = {
     "lrpcap_encoder_profile": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "lrpcap_encoder_profile_read": (ctypes.c_int, [c_void_p, c_double_p]),
     "lrpcap_decoder_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(DecoderWeights), ctypes.c_int, ctypes.c_int]),
+    "lrpcap_decoder_set_weights_device": (ctypes.c_int, [c_void_p, ctypes.POINTER(DecoderWeights)]),
     "lrpcap_decoder_destroy": (ctypes.c_int, [c_void_p]),
     "lrpcap_decoder_forward": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p]),
     "lrpcap_decoder_relevance": (ctypes.c_int, [c_void_p, c_int_p, c_int_p, ctypes.c_int, c_void_p, c_double_p, c_float_p, c_void_p]),

@@ -47,6 +47,11 @@ int lrpcap_encoder_set_weights(lrpcap_encoder_t* enc, const float* const* h_kern
   return enc->impl->set_weights(h_kernels_hwio, h_biases);
 }
 
+int lrpcap_encoder_set_weights_device(lrpcap_encoder_t* enc, const float* const* d_kernels_hwio, const float* const* d_biases) {
+  LRPCAP_REQUIRE(enc && enc->impl, kErrInvalidArg, "encoder_set_weights_device: null handle");
+  return enc->impl->set_weights_device(d_kernels_hwio, d_biases);
+}
+
 int lrpcap_encoder_destroy(lrpcap_encoder_t* enc) {
   if (!enc) return kOk;
   delete enc->impl;

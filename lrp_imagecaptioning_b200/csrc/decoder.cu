@@ -27,65 +27,88 @@ Decoder::~Decoder() {
                     &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &ctx_, &s_, &chat_, &alpha_, &beta_, &XH1_, &XH2_,
                     &Z_, &hp_, &sg_, &sp_, &e_, &hc_, &d_wimg_, &d_wt_, &d_order_, &Rh1_, &Rh2_, &Rh2n_, &Rc1_, &Rc2_,
                     &Rchat_, &Rctx_, &Rglob_, &rword_, &U_, &Y_, &Q_, &UV_, &YF_, &ra_, &UVs_, &YF32_, &gemm_ws_, &As_, &C32_, &As3_,
-                    &Axh_, &Ahs_, &Axh2_, &Ahc_, &C1_, &C2_, &C3_, &C4_, &Vf32_};
+                    &Axh_, &Ahs_, &Axh2_, &Ahc_, &C1_, &C2_, &C3_, &C4_, &Vf32_, &pred_, &F32_};
   for (DevBuf* b : bufs) b->release();
 }
 
-int Decoder::upload(const float* h, size_t n, double** out) {
-  LRPCAP_REQUIRE(h != nullptr, kErrInvalidArg, "decoder_create: missing weight tensor");
-  std::vector<double> tmp(n);
-  for (size_t i = 0; i < n; ++i) tmp[i] = (double)h[i];
+// ---- weight derivation. Every derived tensor (fp64 copies, transposes, [x ; h] stacks, gate slices, bf16 planes) is
+// produced on the device from fp32 source tensors that are already there: staged from the host by create(), or the
+// caller's own device tensors in set_weights_device() (fine-tuning: the explained model changes every step, and a host
+// round trip of ~30 M parameters plus their re-layout on one core was most of that step).
+namespace {
+// out (fp64 [R][ncols], or transposed [ncols][R]) = rows of a [ra, cols] stacked over rows of b [rb, cols], columns [col0, col0 + ncols)
+__global__ void w_cat_slice_kernel(const float* __restrict__ a, int ra, const float* __restrict__ b, int rb, int cols,
+                                   int col0, int ncols, int transpose, double* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = ra + rb;
+  if (i >= (size_t)R * ncols) return;
+  int r, c;
+  if (transpose) { c = (int)(i / R); r = (int)(i - (size_t)c * R); }
+  else { r = (int)(i / ncols); c = (int)(i - (size_t)r * ncols); }
+  const float* src = (r < ra) ? a + (size_t)r * cols : b + (size_t)(r - ra) * cols;
+  out[i] = (double)src[col0 + c];
+}
+// the same selection as two bf16 planes [R][ncols] (hi, then lo at + R * ncols)
+__global__ void w_cat_slice_split_kernel(const float* __restrict__ a, int ra, const float* __restrict__ b, int rb, int cols,
+                                         int col0, int ncols, __nv_bfloat16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = ra + rb;
+  const size_t n = (size_t)R * ncols;
+  if (i >= n) return;
+  const int r = (int)(i / ncols), c = (int)(i - (size_t)r * ncols);
+  const float* src = (r < ra) ? a + (size_t)r * cols : b + (size_t)(r - ra) * cols;
+  __nv_bfloat16 hi, lo;
+  split_bf16(src[col0 + c], hi, lo);
+  out[i] = hi;
+  out[n + i] = lo;
+}
+}  // namespace
+
+// A device allocation that survives set_weights_device(): the first derivation allocates, later ones walk the same list.
+int Decoder::slot(size_t bytes, void** out) {
+  if (rederive_) {
+    LRPCAP_REQUIRE(slot_cursor_ < owned_.size() && owned_bytes_[slot_cursor_] == bytes, kErrState,
+                   "decoder_set_weights_device: derived-tensor list changed (slot %zu)", slot_cursor_);
+    *out = owned_[slot_cursor_++];
+    return kOk;
+  }
   void* p = nullptr;
-  LRPCAP_CUDA(cudaMalloc(&p, n * sizeof(double)));
+  LRPCAP_CUDA(cudaMalloc(&p, bytes));
   owned_.push_back(p);
-  LRPCAP_CUDA(cudaMemcpy(p, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  *out = reinterpret_cast<double*>(p);
+  owned_bytes_.push_back(bytes);
+  *out = p;
   return kOk;
 }
 
-int Decoder::upload_t(const float* h, int rows, int cols, double** out) {
-  LRPCAP_REQUIRE(h != nullptr, kErrInvalidArg, "decoder_create: missing weight tensor");
-  std::vector<float> t((size_t)rows * cols);
-  for (int r = 0; r < rows; ++r)
-    for (int c = 0; c < cols; ++c) t[(size_t)c * rows + r] = h[(size_t)r * cols + c];
-  return upload(t.data(), t.size(), out);
+int Decoder::upload(const float* d, size_t n, double** out) {
+  return upload_cat(d, (int)n, nullptr, 0, 1, 0, 1, false, out);
+}
+
+int Decoder::upload_t(const float* d, int rows, int cols, double** out) {
+  return upload_cat(d, rows, nullptr, 0, cols, 0, cols, true, out);
 }
 
 // rows of a [ra, cols] stacked over rows of b [rb, cols], column slice [col0, col0+ncols); optionally transposed.
 int Decoder::upload_cat(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, bool transpose,
                         double** out) {
-  LRPCAP_REQUIRE(a && b, kErrInvalidArg, "decoder_create: missing weight tensor");
-  const int R = ra + rb;
-  std::vector<float> t((size_t)R * ncols);
-  for (int r = 0; r < R; ++r) {
-    const float* src = (r < ra) ? a + (size_t)r * cols : b + (size_t)(r - ra) * cols;
-    for (int c = 0; c < ncols; ++c) {
-      if (transpose) t[(size_t)c * R + r] = src[col0 + c];
-      else t[(size_t)r * ncols + c] = src[col0 + c];
-    }
-  }
-  return upload(t.data(), t.size(), out);
+  LRPCAP_REQUIRE(a && (b || rb == 0), kErrInvalidArg, "decoder: missing weight tensor");
+  const size_t n = (size_t)(ra + rb) * ncols;
+  void* p = nullptr;
+  LRPCAP_TRY(slot(n * sizeof(double), &p));
+  w_cat_slice_kernel<<<nblk(n, 256), 256>>>(a, ra, b, rb, cols, col0, ncols, transpose ? 1 : 0, reinterpret_cast<double*>(p));
+  LRPCAP_CUDA(cudaGetLastError());
+  *out = reinterpret_cast<double*>(p);
+  return kOk;
 }
 
 // rows of a stacked over rows of b, column slice -> split-bf16 [rows][ncols] (hi plane then lo plane)
 int Decoder::upload_split(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, void** out) {
-  LRPCAP_REQUIRE(a && b, kErrInvalidArg, "decoder_create: missing weight tensor");
-  const int R = ra + rb;
-  const size_t n = (size_t)R * ncols;
-  std::vector<__nv_bfloat16> sp(2 * n);
-  for (int r = 0; r < R; ++r) {
-    const float* src = (r < ra) ? a + (size_t)r * cols : b + (size_t)(r - ra) * cols;
-    for (int c = 0; c < ncols; ++c) {
-      const float v = src[col0 + c];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      sp[(size_t)r * ncols + c] = hi;
-      sp[n + (size_t)r * ncols + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    }
-  }
+  LRPCAP_REQUIRE(a && (b || rb == 0), kErrInvalidArg, "decoder: missing weight tensor");
+  const size_t n = (size_t)(ra + rb) * ncols;
   void* p = nullptr;
-  LRPCAP_CUDA(cudaMalloc(&p, 2 * n * sizeof(__nv_bfloat16)));
-  owned_.push_back(p);
-  LRPCAP_CUDA(cudaMemcpy(p, sp.data(), 2 * n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  LRPCAP_TRY(slot(2 * n * sizeof(__nv_bfloat16), &p));
+  w_cat_slice_split_kernel<<<nblk(n, 256), 256>>>(a, ra, b, rb, cols, col0, ncols, reinterpret_cast<__nv_bfloat16*>(p));
+  LRPCAP_CUDA(cudaGetLastError());
   *out = p;
   return kOk;
 }
@@ -127,11 +150,9 @@ int Decoder::gemm_tc_direct(int M, int K, size_t nA, const void* Bsplit, int N, 
 int Decoder::split3_weights(const double* d_Wt, int N, int K, int* Npad, void** out) {
   const int np = (N + 63) / 64 * 64;
   void* p = nullptr;
-  LRPCAP_CUDA(cudaMalloc(&p, (size_t)3 * np * K * sizeof(__nv_bfloat16)));
-  owned_.push_back(p);
+  LRPCAP_TRY(slot((size_t)3 * np * K * sizeof(__nv_bfloat16), &p));
   f64_rows_to_split3_kernel<<<nblk((size_t)np * K, 256), 256>>>(d_Wt, K, N, K, np, reinterpret_cast<__nv_bfloat16*>(p));
   LRPCAP_CUDA(cudaGetLastError());
-  LRPCAP_CUDA(cudaDeviceSynchronize());
   *Npad = np;
   *out = p;
   return kOk;
@@ -179,117 +200,172 @@ int Decoder::create(Decoder** out, const lrpcap_decoder_weights* w, int sos_toke
   Decoder* d = new Decoder();
   d->kind_ = w->kind; d->V_ = w->V; d->H_ = w->H; d->E_ = w->E; d->D_ = w->D;
   d->sos_ = sos_token; d->keras_logits_ = keras_logits;
-  const int V = w->V, H = w->H, E = w->E, D = w->D;
-  auto fail = [&](int st) { delete d; return st; };
-  int st;
-#define UP(expr) if ((st = (expr)) != kOk) return fail(st)
-  UP(d->upload(w->image_features_w, (size_t)D * H, &d->Wif_));
-  UP(d->upload(w->image_features_b, H, &d->bif_));
-  UP(d->upload_t(w->image_features_w, D, H, &d->WifT_));
-  UP(d->upload(w->global_w, (size_t)D * E, &d->Wgf_));
-  UP(d->upload(w->global_b, E, &d->bgf_));
-  UP(d->upload_t(w->global_w, D, E, &d->WgfT_));
-  UP(d->upload(w->embedding, (size_t)V * E, &d->Emb_));
-  UP(d->upload(w->output_w, (size_t)H * V, &d->Wo_));
-  UP(d->upload_t(w->output_w, H, V, &d->WoT_));
-  UP(d->upload(w->output_b, V, &d->bo_));
-  if (w->kind == LRPCAP_DECODER_ADAPTIVE) {
-    d->Kin1_ = 2 * E + H;
-    UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat1_));
-    UP(d->upload(w->lstm_b, 4 * H, &d->b1_));
-    UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, true, &d->Wgate1T_));
-    UP(d->upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, true, &d->Wcat1T_));
-    UP(d->upload(w->Wv, (size_t)H * H, &d->Wp_));
-    UP(d->upload(w->Wg, (size_t)H * H, &d->Whp_));
-    UP(d->upload_cat(w->Wx, 2 * E, w->Wh, H, H, 0, H, false, &d->Wsx_));
-    UP(d->upload(w->Ws, (size_t)H * H, &d->Wss_));
-    UP(d->upload(w->Vatt, H, &d->Va_));
+  if (const char* gv = getenv("LRPCAP_DECODER_GRAPH")) d->graph_enabled_ = gv[0] != '0';
+  // stage the host tensors on the device as they are (fp32, Keras layouts); every derived layout is built there
+  std::vector<WField> fl = d->fields();
+  size_t total = 0;
+  for (const WField& f : fl) total += (f.n + 3) / 4 * 4;
+  DevBuf stage;
+  lrpcap_decoder_weights wd = *w;
+  int st = stage.ensure(total * sizeof(float));
+  size_t off = 0;
+  for (size_t k = 0; st == kOk && k < fl.size(); ++k) {
+    const float* src = w->*(fl[k].p);
+    if (!src) {
+      set_last_error("decoder_create: weight tensor %zu missing", k);
+      st = kErrInvalidArg;
+      break;
+    }
+    float* dst = stage.as<float>() + off;
+    if (cudaMemcpy(dst, src, fl[k].n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_last_error("decoder_create: host -> device copy failed");
+      st = kErrCuda;
+      break;
+    }
+    wd.*(fl[k].p) = dst;
+    off += (fl[k].n + 3) / 4 * 4;
+  }
+  if (st == kOk) st = d->derive(&wd);
+  if (st == kOk && cudaDeviceSynchronize() != cudaSuccess) {
+    set_last_error("decoder_create: weight derivation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    st = kErrCuda;
+  }
+  stage.release();
+  if (st != kOk) {
+    delete d;
+    return st;
+  }
+  *out = d;
+  return kOk;
+}
+
+// The weight tensors a decoder of this kind reads, with their element counts (include/lrpcap.h: lrpcap_decoder_weights_t).
+std::vector<Decoder::WField> Decoder::fields() const {
+  const size_t V = V_, H = H_, E = E_, D = D_;
+  typedef lrpcap_decoder_weights W;
+  std::vector<WField> f = {{&W::image_features_w, D * H}, {&W::image_features_b, H}, {&W::global_w, D * E}, {&W::global_b, E},
+                           {&W::embedding, V * E}, {&W::output_w, H * V}, {&W::output_b, V}};
+  if (kind_ == LRPCAP_DECODER_ADAPTIVE) {
+    const WField a[] = {{&W::lstm_wi, 2 * E * 4 * H}, {&W::lstm_wh, H * 4 * H}, {&W::lstm_b, 4 * H}, {&W::Wv, H * H}, {&W::Wg, H * H},
+                        {&W::Wx, 2 * E * H}, {&W::Wh, H * H}, {&W::Ws, H * H}, {&W::Vatt, H}};
+    f.insert(f.end(), a, a + 9);
   } else {
-    d->Kin1_ = 2 * H + 2 * E;
-    d->Kin2_ = 3 * H;
-    UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat1_));
-    UP(d->upload(w->td_b, 4 * H, &d->b1_));
-    UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, true, &d->Wgate1T_));
-    UP(d->upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, true, &d->Wcat1T_));
-    UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, false, &d->Wcat2_));
-    UP(d->upload(w->lang_b, 4 * H, &d->b2_));
-    UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, true, &d->Wgate2T_));
-    UP(d->upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, true, &d->Wcat2T_));
-    UP(d->upload(w->W_va, (size_t)H * H, &d->Wp_));
-    UP(d->upload(w->W_ha, (size_t)H * H, &d->Whp_));
-    UP(d->upload_cat(w->W_x, H + 2 * E, w->W_h, H, H, 0, H, false, &d->Wsx_));
-    UP(d->upload(w->W_s, (size_t)H * H, &d->Wss_));
-    UP(d->upload(w->W_a, H, &d->Va_));
+    const WField g[] = {{&W::lang_wi, 2 * H * 4 * H}, {&W::lang_wh, H * 4 * H}, {&W::lang_b, 4 * H}, {&W::td_wi, (H + 2 * E) * 4 * H},
+                        {&W::td_wh, H * 4 * H}, {&W::td_b, 4 * H}, {&W::W_va, H * H}, {&W::W_ha, H * H}, {&W::W_a, H},
+                        {&W::W_x, (H + 2 * E) * H}, {&W::W_h, H * H}, {&W::W_s, H * H}};
+    f.insert(f.end(), g, g + 12);
+  }
+  return f;
+}
+
+// Replaces the weights in place from DEVICE fp32 tensors (same layouts as lrpcap_decoder_create): every derived tensor is
+// recomputed into the allocation it already has, so graphs and buffers stay valid; the forward state is dropped.
+int Decoder::set_weights_device(const lrpcap_decoder_weights* wd) {
+  LRPCAP_REQUIRE(wd != nullptr, kErrInvalidArg, "decoder_set_weights_device: null argument");
+  LRPCAP_REQUIRE(wd->kind == kind_ && wd->V == V_ && wd->H == H_ && wd->E == E_ && wd->D == D_, kErrShape,
+                 "decoder_set_weights_device: kind / dimensions differ from the handle's");
+  for (const WField& f : fields())
+    LRPCAP_REQUIRE(wd->*(f.p) != nullptr, kErrInvalidArg, "decoder_set_weights_device: a weight tensor is missing");
+  LRPCAP_CUDA(cudaDeviceSynchronize());   // nothing may still read the old values
+  rederive_ = true;
+  slot_cursor_ = 0;
+  const int st = derive(wd);
+  rederive_ = false;
+  LRPCAP_TRY(st);
+  LRPCAP_CUDA(cudaDeviceSynchronize());
+  N_ = 0;
+  return kOk;
+}
+
+// Builds every derived weight layout from device fp32 tensors `w` (pointers are device memory).
+int Decoder::derive(const lrpcap_decoder_weights* w) {
+  const int V = V_, H = H_, E = E_, D = D_;
+  LRPCAP_TRY(upload(w->image_features_w, (size_t)D * H, &Wif_));
+  LRPCAP_TRY(upload(w->image_features_b, H, &bif_));
+  LRPCAP_TRY(upload_t(w->image_features_w, D, H, &WifT_));
+  LRPCAP_TRY(upload(w->global_w, (size_t)D * E, &Wgf_));
+  LRPCAP_TRY(upload(w->global_b, E, &bgf_));
+  LRPCAP_TRY(upload_t(w->global_w, D, E, &WgfT_));
+  LRPCAP_TRY(upload(w->embedding, (size_t)V * E, &Emb_));
+  LRPCAP_TRY(upload(w->output_w, (size_t)H * V, &Wo_));
+  LRPCAP_TRY(upload_t(w->output_w, H, V, &WoT_));
+  LRPCAP_TRY(upload(w->output_b, V, &bo_));
+  if (w->kind == LRPCAP_DECODER_ADAPTIVE) {
+    Kin1_ = 2 * E + H;
+    LRPCAP_TRY(upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, false, &Wcat1_));
+    LRPCAP_TRY(upload(w->lstm_b, 4 * H, &b1_));
+    LRPCAP_TRY(upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, true, &Wgate1T_));
+    LRPCAP_TRY(upload_cat(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, true, &Wcat1T_));
+    LRPCAP_TRY(upload(w->Wv, (size_t)H * H, &Wp_));
+    LRPCAP_TRY(upload(w->Wg, (size_t)H * H, &Whp_));
+    LRPCAP_TRY(upload_cat(w->Wx, 2 * E, w->Wh, H, H, 0, H, false, &Wsx_));
+    LRPCAP_TRY(upload(w->Ws, (size_t)H * H, &Wss_));
+    LRPCAP_TRY(upload(w->Vatt, H, &Va_));
+  } else {
+    Kin1_ = 2 * H + 2 * E;
+    Kin2_ = 3 * H;
+    LRPCAP_TRY(upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, false, &Wcat1_));
+    LRPCAP_TRY(upload(w->td_b, 4 * H, &b1_));
+    LRPCAP_TRY(upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, true, &Wgate1T_));
+    LRPCAP_TRY(upload_cat(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, true, &Wcat1T_));
+    LRPCAP_TRY(upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, false, &Wcat2_));
+    LRPCAP_TRY(upload(w->lang_b, 4 * H, &b2_));
+    LRPCAP_TRY(upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, true, &Wgate2T_));
+    LRPCAP_TRY(upload_cat(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, true, &Wcat2T_));
+    LRPCAP_TRY(upload(w->W_va, (size_t)H * H, &Wp_));
+    LRPCAP_TRY(upload(w->W_ha, (size_t)H * H, &Whp_));
+    LRPCAP_TRY(upload_cat(w->W_x, H + 2 * E, w->W_h, H, H, 0, H, false, &Wsx_));
+    LRPCAP_TRY(upload(w->W_s, (size_t)H * H, &Wss_));
+    LRPCAP_TRY(upload(w->W_a, H, &Va_));
   }
   if (H % 64 == 0 && E % 64 == 0 && !getenv("LRPCAP_DECODER_FP64_GEMM")) {
     if (w->kind == LRPCAP_DECODER_ADAPTIVE) {
-      UP(d->upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, &d->Wgate1TC_));
-      UP(d->upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, &d->WcatB1TC_));
+      LRPCAP_TRY(upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 2 * H, H, &Wgate1TC_));
+      LRPCAP_TRY(upload_split(w->lstm_wi, 2 * E, w->lstm_wh, H, 4 * H, 0, 4 * H, &WcatB1TC_));
     } else {
-      UP(d->upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, &d->WcatB1TC_));
-      UP(d->upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, &d->WcatB2TC_));
-      UP(d->upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, &d->Wgate1TC_));
-      UP(d->upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, &d->Wgate2TC_));
+      LRPCAP_TRY(upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 0, 4 * H, &WcatB1TC_));
+      LRPCAP_TRY(upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 0, 4 * H, &WcatB2TC_));
+      LRPCAP_TRY(upload_split(w->td_wi, H + 2 * E, w->td_wh, H, 4 * H, 2 * H, H, &Wgate1TC_));
+      LRPCAP_TRY(upload_split(w->lang_wi, 2 * H, w->lang_wh, H, 4 * H, 2 * H, H, &Wgate2TC_));
     }
   }
   if (H % 64 == 0 && D % 64 == 0 && !getenv("LRPCAP_DECODER_FP64_GEMM")) {
     // B operand of the [words*L, H] x [H, D] relevance GEMM: B[d][h] = W_if[d][h] -- the Keras (D, H) layout as is
-    const size_t n = (size_t)D * H;
-    std::vector<__nv_bfloat16> sp(2 * n);
-    for (size_t i = 0; i < n; ++i) {
-      const float v = w->image_features_w[i];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      sp[i] = hi;
-      sp[n + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
-    }
-    void* p = nullptr;
-    if (cudaMalloc(&p, 2 * n * sizeof(__nv_bfloat16)) != cudaSuccess ||
-        cudaMemcpy(p, sp.data(), 2 * n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice) != cudaSuccess) {
-      set_last_error("decoder_create: device allocation failed");
-      return fail(kErrCuda);
-    }
-    d->owned_.push_back(p);
-    d->WifTC_ = p;
-    d->tc_features_ = true;
+    LRPCAP_TRY(upload_split(w->image_features_w, D, nullptr, 0, H, 0, H, &WifTC_));
+    tc_features_ = true;
   }
-  if (const char* gv = getenv("LRPCAP_DECODER_GRAPH")) d->graph_enabled_ = gv[0] != '0';
   {
     const char* v = getenv("LRPCAP_DECODER_TC_FWD");
     const bool want = v ? (v[0] != '0') : true;   // LRPCAP_DECODER_TC_FWD=0: all forward GEMMs in fp64
-    if (want && H % 64 == 0 && d->Kin1_ % 64 == 0 && (w->kind == LRPCAP_DECODER_ADAPTIVE || d->Kin2_ % 64 == 0)) {
-      UP(d->split3_weights(d->Wcat1T_, 4 * H, d->Kin1_, &d->G4pad_, &d->Wcat1TC3_));
-      if (w->kind == LRPCAP_DECODER_GRIDTD) UP(d->split3_weights(d->Wcat2T_, 4 * H, d->Kin2_, &d->G4pad_, &d->Wcat2TC3_));
-      UP(d->split3_weights(d->WoT_, V, H, &d->Vpad_, &d->WoTC3_));
-      d->tc_forward_ = true;
+    if (want && H % 64 == 0 && Kin1_ % 64 == 0 && (w->kind == LRPCAP_DECODER_ADAPTIVE || Kin2_ % 64 == 0)) {
+      LRPCAP_TRY(split3_weights(Wcat1T_, 4 * H, Kin1_, &G4pad_, &Wcat1TC3_));
+      if (w->kind == LRPCAP_DECODER_GRIDTD) LRPCAP_TRY(split3_weights(Wcat2T_, 4 * H, Kin2_, &G4pad_, &Wcat2TC3_));
+      LRPCAP_TRY(split3_weights(WoT_, V, H, &Vpad_, &WoTC3_));
+      tc_forward_ = true;
       const char* fv = getenv("LRPCAP_DECODER_FUSED");
       if (!(fv && fv[0] == '0') && D % 64 == 0) {
         // rows [W_cat1^T ; W_sx^T] (gates | sentinel gate) and [W_hp^T ; W_ss^T] as single B operands
         const bool ad = w->kind == LRPCAP_DECODER_ADAPTIVE;
-        const int K1 = d->Kin1_;
+        const int K1 = Kin1_;
         double *sxT = nullptr, *hpT = nullptr, *ssT = nullptr, *pT = nullptr, *cat = nullptr;
-        UP(d->upload_cat(ad ? w->Wx : w->W_x, K1 - H, ad ? w->Wh : w->W_h, H, H, 0, H, true, &sxT));
-        UP(d->upload_t(ad ? w->Wg : w->W_ha, H, H, &hpT));
-        UP(d->upload_t(ad ? w->Ws : w->W_s, H, H, &ssT));
-        UP(d->upload_t(ad ? w->Wv : w->W_va, H, H, &pT));
-        if (cudaMalloc(&cat, (size_t)5 * H * K1 * sizeof(double)) != cudaSuccess) {
-          set_last_error("decoder_create: device allocation failed");
-          return fail(kErrCuda);
-        }
-        d->owned_.push_back(cat);
-        cudaMemcpy(cat, d->Wcat1T_, (size_t)4 * H * K1 * sizeof(double), cudaMemcpyDeviceToDevice);
-        cudaMemcpy(cat + (size_t)4 * H * K1, sxT, (size_t)H * K1 * sizeof(double), cudaMemcpyDeviceToDevice);
-        UP(d->split3_weights(cat, 5 * H, K1, &d->Npad1_, &d->W1cat3_));
-        cudaMemcpy(cat, hpT, (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice);
-        cudaMemcpy(cat + (size_t)H * H, ssT, (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice);
-        UP(d->split3_weights(cat, 2 * H, H, &d->Npad2_, &d->W2cat3_));
-        UP(d->split3_weights(d->WifT_, H, D, &d->Hpad_, &d->WifTC3_));
-        UP(d->split3_weights(pT, H, H, &d->Hpad_, &d->WpTC3_));
-        d->fused_ = true;
+        LRPCAP_TRY(upload_cat(ad ? w->Wx : w->W_x, K1 - H, ad ? w->Wh : w->W_h, H, H, 0, H, true, &sxT));
+        LRPCAP_TRY(upload_t(ad ? w->Wg : w->W_ha, H, H, &hpT));
+        LRPCAP_TRY(upload_t(ad ? w->Ws : w->W_s, H, H, &ssT));
+        LRPCAP_TRY(upload_t(ad ? w->Wv : w->W_va, H, H, &pT));
+        void* catp = nullptr;
+        LRPCAP_TRY(slot((size_t)5 * H * K1 * sizeof(double), &catp));
+        cat = reinterpret_cast<double*>(catp);
+        LRPCAP_CUDA(cudaMemcpy(cat, Wcat1T_, (size_t)4 * H * K1 * sizeof(double), cudaMemcpyDeviceToDevice));
+        LRPCAP_CUDA(cudaMemcpy(cat + (size_t)4 * H * K1, sxT, (size_t)H * K1 * sizeof(double), cudaMemcpyDeviceToDevice));
+        LRPCAP_TRY(split3_weights(cat, 5 * H, K1, &Npad1_, &W1cat3_));
+        LRPCAP_CUDA(cudaMemcpy(cat, hpT, (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice));
+        LRPCAP_CUDA(cudaMemcpy(cat + (size_t)H * H, ssT, (size_t)H * H * sizeof(double), cudaMemcpyDeviceToDevice));
+        LRPCAP_TRY(split3_weights(cat, 2 * H, H, &Npad2_, &W2cat3_));
+        LRPCAP_TRY(split3_weights(pT, H, H, &Hpad_, &WpTC3_));
+        fused_ = true;
       }
     }
   }
-#undef UP
-  *out = d;
   return kOk;
 }
 
@@ -325,7 +401,12 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   LRPCAP_REQUIRE(d_features && h_captions && N > 0 && L > 0 && T > 0, kErrInvalidArg, "decoder_forward: bad argument");
   const int H = H_, E = E_, D = D_, V = V_;
   const bool td = kind_ == LRPCAP_DECODER_GRIDTD;
-  if (!greedy)
+  LRPCAP_REQUIRE(greedy >= 0 && greedy <= 2, kErrInvalidArg, "decoder_forward: greedy must be 0, 1 or 2");
+  const bool predict = greedy == 2;   // teacher-forced inputs, arg-max outputs (what `model.predict` + argmax gives, train.py:570)
+  // grid-TD: the Keras model's logits are (h2 + c_hat) W_o + b (models/model.py:816), the explainer's h2 W_o + b (quirk B1);
+  // a prediction is the Keras model's by definition
+  const int add_chat = (predict || keras_logits_) ? 1 : 0;
+  if (greedy != 1)
     for (int i = 0; i < N * T; ++i)
       LRPCAP_REQUIRE(h_captions[i] >= 1 && h_captions[i] <= V, kErrInvalidArg,
                      "decoder_forward: token id %d at %d outside [1,%d]", h_captions[i], i, V);
@@ -374,9 +455,12 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
     LRPCAP_TRY(C32_.ensure(mp * Hpad_ * sizeof(float)));
   }
   if (greedy) LRPCAP_TRY(logits_.ensure((size_t)N * V * 8));
-  else LRPCAP_CUDA(cudaMemcpyAsync(tok_.p, h_captions, (size_t)N * T * sizeof(int), cudaMemcpyHostToDevice, s));
+  if (predict) LRPCAP_TRY(pred_.ensure((size_t)N * T * sizeof(int)));
+  if (greedy != 1) LRPCAP_CUDA(cudaMemcpyAsync(tok_.p, h_captions, (size_t)N * T * sizeof(int), cudaMemcpyHostToDevice, s));
 
   // the caller's feature tensor may move between calls: it is converted outside the (pointer-baking) graph
+  LRPCAP_TRY(F32_.ensure(NL * D * sizeof(float)));
+  LRPCAP_CUDA(cudaMemcpyAsync(F32_.p, d_features, NL * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
   f32_to_f64_kernel<<<nblk(NL * D, 256), 256, 0, s>>>(d_features, F_.as<double>(), NL * D);
   ++launches_;
   // everything else the forward enqueues on the stream (memsets + ~25 small launches per step)
@@ -388,8 +472,10 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   LRPCAP_CUDA(cudaMemsetAsync(beta_.p, 0, (size_t)N * (T + 1) * 8, s));
   double *F = F_.as<double>(), *Vp = Vp_.as<double>(), *P = P_.as<double>(), *Vf = UV_.as<double>();
   // image_features / global_img_feature heads (explainers.py:375-388); F was filled from d_features by the caller part
-  if (fused) LRPCAP_TRY(gemm_tc3(F, D, (int)NL, D, WifTC3_, Hpad_, H, bif_, Vp, H, s));
-  else LRPCAP_TRY(gemm(F, D, Wif_, H, Vp, H, (int)NL, H, D, bif_, s));
+  // Vp stays an fp64 GEMM rounded to float32: its sign is a ReLU decision (gradient decoder: d_V masked where Vf <= 0) and
+  // the reference's float32 value is reproduced bit for bit this way; P = Vf W_p only enters tanh(P + hp) and may take the
+  // tensor-core path
+  LRPCAP_TRY(gemm(F, D, Wif_, H, Vp, H, (int)NL, H, D, bif_, s));
   round_f32_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, NL * H);   // rows are float32 results in the reference
   relu_copy_kernel<<<nblk(NL * H, 256), 256, 0, s>>>(Vp, Vf, NL * H);
   if (fused) {
@@ -409,6 +495,7 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   launches_ += 4;
 
   int* tok = tok_.as<int>();
+  int* tok_out = predict ? pred_.as<int>() : tok;   // greedy feeds its arg-max back; predict keeps the teacher tokens as inputs
   for (int i = 0; fused && i < T; ++i) {   // fused step: 9 launches (grid-TD, greedy); see decoder_fused.cuh
     __nv_bfloat16 *Axh = Axh_.as<__nv_bfloat16>(), *Ahs = Ahs_.as<__nv_bfloat16>(), *Ahc = Ahc_.as<__nv_bfloat16>();
     __nv_bfloat16* Axh2 = td ? Axh2_.as<__nv_bfloat16>() : nullptr;
@@ -430,12 +517,12 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
       LRPCAP_TRY(tc3(Axh2, Mpad, Kin2_, Wcat2TC3_, G4pad_, C3_.as<float>(), s));
       fwd_lstm_kernel<<<N, 256, 0, s>>>(C3_.as<float>(), G4pad_, b2_, h2_.as<double>(), c2_.as<double>(), zg2_.as<double>(),
                                         ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(), nullptr,
-                                        nullptr, 0, N, chat_.as<double>(), hc_.as<double>(), Ahc, nAhc, keras_logits_, i, T, H);
+                                        nullptr, 0, N, chat_.as<double>(), hc_.as<double>(), Ahc, nAhc, add_chat, i, T, H);
       ++launches_;
     }
     if (greedy) {
       LRPCAP_TRY(tc3(Ahc, Mpad, H, WoTC3_, Vpad_, C4_.as<float>(), s));
-      fwd_argmax_kernel<<<N, 256, 0, s>>>(C4_.as<float>(), Vpad_, bo_, V, eos_token >= 1 ? eos_token - 1 : -1, tok,
+      fwd_argmax_kernel<<<N, 256, 0, s>>>(C4_.as<float>(), Vpad_, bo_, V, eos_token >= 1 ? eos_token - 1 : -1, tok_out,
                                           logitk_.as<double>(), i, T);
     } else {
       logitk_kernel<<<N, 128, 0, s>>>(hc_.as<double>(), WoT_, bo_, tok, logitk_.as<double>(), i, T, H);
@@ -471,13 +558,13 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
                         Kin2_, b2_, s));
       lstm_point_kernel<<<N, 256, 0, s>>>(Z_.as<double>(), h2_.as<double>(), c2_.as<double>(), zg2_.as<double>(),
                                           ia2_.as<double>(), fa2_.as<double>(), ga2_.as<double>(), oa2_.as<double>(), i, T, H);
-      gridtd_hc_kernel<<<N, 256, 0, s>>>(h2_.as<double>(), chat_.as<double>(), hc_.as<double>(), i, T, H, keras_logits_);
+      gridtd_hc_kernel<<<N, 256, 0, s>>>(h2_.as<double>(), chat_.as<double>(), hc_.as<double>(), i, T, H, add_chat);
       launches_ += 3;
     }
     if (greedy) {
       if (tc_forward_) LRPCAP_TRY(gemm_tc3(hc_.as<double>(), H, N, H, WoTC3_, Vpad_, V, bo_, logits_.as<double>(), V, s));
       else LRPCAP_TRY(gemm(hc_.as<double>(), H, Wo_, V, logits_.as<double>(), V, N, V, H, bo_, s));
-      argmax_kernel<<<N, 256, 0, s>>>(logits_.as<double>(), V, eos_token >= 1 ? eos_token - 1 : -1, tok,
+      argmax_kernel<<<N, 256, 0, s>>>(logits_.as<double>(), V, eos_token >= 1 ? eos_token - 1 : -1, tok_out,
                                       logitk_.as<double>(), i, T);
     } else {
       logitk_kernel<<<N, 128, 0, s>>>(hc_.as<double>(), WoT_, bo_, tok, logitk_.as<double>(), i, T, H);
@@ -495,11 +582,11 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   if (greedy && graph_enabled_) {
     uint64_t key = 1469598103934665603ull;
     auto mix = [&](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
-    mix((uint64_t)N); mix((uint64_t)T); mix((uint64_t)L); mix((uint64_t)(int64_t)eos_token);
+    mix((uint64_t)N); mix((uint64_t)T); mix((uint64_t)L); mix((uint64_t)(int64_t)eos_token); mix((uint64_t)greedy);
     mix((uint64_t)(uintptr_t)s);
     DevBuf* all[] = {&F_, &Vp_, &P_, &UV_, &a_, &gp_, &tok_, &logitk_, &h1_, &c1_, &zg1_, &ia1_, &fa1_, &ga1_, &oa1_, &ctx_, &s_,
                      &chat_, &h2_, &c2_, &zg2_, &ia2_, &fa2_, &ga2_, &oa2_, &XH1_, &XH2_, &alpha_, &beta_, &Z_, &hp_, &sg_,
-                     &sp_, &e_, &hc_, &logits_, &gemm_ws_, &As3_, &C32_, &Axh_, &Ahs_, &Axh2_, &Ahc_, &C1_, &C2_, &C3_, &C4_, &Vf32_};
+                     &sp_, &e_, &hc_, &logits_, &pred_, &gemm_ws_, &As3_, &C32_, &Axh_, &Ahs_, &Axh2_, &Ahc_, &C1_, &C2_, &C3_, &C4_, &Vf32_};
     for (DevBuf* b : all) mix((uint64_t)(uintptr_t)b->p);
     // the legacy default stream cannot be captured: graphs run on a private stream ordered after / before it by events
     cudaStream_t gs = s;
@@ -553,10 +640,12 @@ int Decoder::forward(const float* d_features, int N, int L, int* h_captions, int
   }
   if (!done) LRPCAP_TRY(issue(s));
   if (greedy) {
-    LRPCAP_CUDA(cudaMemcpyAsync(h_captions, tok_.p, (size_t)N * T * sizeof(int), cudaMemcpyDeviceToHost, s));
+    LRPCAP_CUDA(cudaMemcpyAsync(h_captions, predict ? pred_.p : tok_.p, (size_t)N * T * sizeof(int), cudaMemcpyDeviceToHost, s));
     LRPCAP_CUDA(cudaStreamSynchronize(s));
   }
-  N_ = N; T_ = T; L_ = L;
+  // predict mode: the stored state belongs to the teacher tokens while logit_k holds the arg-max logits -- not a state to
+  // explain from; the caller runs a teacher-forced forward on the predicted caption next (models/model.py:1661-1672)
+  N_ = predict ? 0 : N; T_ = T; L_ = L;
   return kOk;
 }
 
@@ -753,23 +842,59 @@ int Decoder::relevance(const int* h_word_img, const int* h_word_t, int W, float*
   const int CH = std::min(W, 512);
   LRPCAP_TRY(UV_.ensure(std::max((size_t)CH, (size_t)N_) * L * H * 8));
   LRPCAP_TRY(YF_.ensure((size_t)CH * L * D * 8));
+  // direct tail: the redistribution kernels write the GEMM's bf16 planes, final_kernel reads its fp32 result
+  const int fh = (int)std::lround(std::sqrt((double)L));
+  const bool tail_direct = direct && tc_features_ && fh * fh == L;
+  const bool exact_uv = getenv("LRPCAP_DECODER_EXACT_UV") != nullptr;   // the float32-store emulation of explainers.py:1292-1299
+  if (tail_direct) {
+    LRPCAP_TRY(UVs_.ensure((size_t)CH * L * H * 4));
+    LRPCAP_TRY(YF32_.ensure((size_t)CH * L * D * 4));
+  }
   for (int p0 = 0; p0 < W; p0 += CH) {
     const int m = std::min(CH, W - p0);
+    const size_t nUV = (size_t)m * L * H;
+    __nv_bfloat16* UVs = tail_direct ? UVs_.as<__nv_bfloat16>() : nullptr;
     if (!td)
       uv_adaptive_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), ctx_.as<double>(),
-                                                    Rctx_.as<double>(), UV_.as<double>(), T, L, H);
-    else
-      if (T <= kUvMaxT) {
-        constexpr int kLG = 14;
-        uv_gridtd_rows_kernel<<<dim3((L + kLG - 1) / kLG, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
-                                                  UV_.as<double>(), T, L, H, kLG);
+                                                    Rctx_.as<double>(), UV_.as<double>(), T, L, H, UVs, nUV);
+    else if (T <= kUvMaxT) {
+      constexpr int kLG = 14;
+      if (tail_direct && !exact_uv)
+        uv_gridtd_rows_f32_kernel<<<dim3((L + kLG - 1) / kLG, m), 256, kLG * kUvMaxT * sizeof(float), s>>>(
+            wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(), T, L, H, kLG, UVs, nUV);
+      else
+        uv_gridtd_rows_kernel<<<dim3((L + kLG - 1) / kLG, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(),
+                                                                           Q_.as<double>(), UV_.as<double>(), T, L, H, kLG, UVs, nUV);
+    } else {
+      if (tail_direct) {   // rare long captions: rows in fp64, then the ordinary conversion
+        uv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
+                                                    UV_.as<double>(), T, L, H);
+        f64_to_split_kernel<<<nblk(nUV, 256), 256, 0, s>>>(UV_.as<double>(), UVs, UVs + nUV, nUV);
+        ++launches_;
       } else {
         uv_gridtd_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, Vp_.as<double>(), alpha_.as<double>(), Q_.as<double>(),
-                                                  UV_.as<double>(), T, L, H);
+                                                    UV_.as<double>(), T, L, H);
       }
-    LRPCAP_TRY(features_gemm(m, s));
-    final_kernel<<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F_.as<double>(), ra_.as<double>(),
-                                            YF_.as<double>(), d_R_head, L, D);
+    }
+    if (tail_direct) {
+      TcConvArgs a;
+      a.A = UVs_.p; a.A_elems = nUV; a.n_items = m; a.H = fh; a.W = fh; a.C = H;
+      a.B = WifTC_; a.B_elems = (size_t)D * H; a.taps = 1; a.Nout = D;
+      a.epi.mode = EPI_RAW;
+      a.epi.out_f32 = YF32_.as<float>();
+      LRPCAP_TRY(tc_conv_launch(a, s));
+      ++launches_;
+      if (F32_.p)
+        final_kernel<float, float><<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F32_.as<float>(), ra_.as<double>(),
+                                                              YF32_.as<float>(), d_R_head, L, D);
+      else
+        final_kernel<float><<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F_.as<double>(), ra_.as<double>(),
+                                                       YF32_.as<float>(), d_R_head, L, D);
+    } else {
+      LRPCAP_TRY(features_gemm(m, s));
+      final_kernel<double><<<dim3(L, m), 256, 0, s>>>(wr, p0, d_order_.as<int>(), F_.as<double>(), ra_.as<double>(),
+                                                      YF_.as<double>(), d_R_head, L, D);
+    }
     launches_ += 2;
   }
   LRPCAP_CUDA(cudaGetLastError());

@@ -26,6 +26,8 @@ class Decoder {
  public:
   ~Decoder();
   static int create(Decoder** out, const lrpcap_decoder_weights* w, int sos_token, int keras_logits);
+  // the same tensors as DEVICE fp32 pointers: re-derives every layout in place (fine-tuning), drops the forward state
+  int set_weights_device(const lrpcap_decoder_weights* d_w);
   int forward(const float* d_features, int n_images, int L, int* h_captions, int T, int greedy, int eos_token,
               cudaStream_t s);
   int relevance(const int* h_word_img, const int* h_word_t, int n_words, float* d_R_head, double* h_r_words,
@@ -42,8 +44,15 @@ class Decoder {
   int D() const { return D_; }
 
  private:
-  int upload(const float* h, size_t n, double** out);                        // fp32 host -> fp64 device
-  int upload_t(const float* h, int rows, int cols, double** out);            // transposed copy
+  struct WField {
+    const float* lrpcap_decoder_weights::*p;
+    size_t n;
+  };
+  std::vector<WField> fields() const;
+  int derive(const lrpcap_decoder_weights* d_w);                             // all derived layouts from device fp32 tensors
+  int slot(size_t bytes, void** out);                                        // allocation that set_weights_device() re-uses
+  int upload(const float* d, size_t n, double** out);                        // device fp32 -> fp64
+  int upload_t(const float* d, int rows, int cols, double** out);            // transposed copy
   int upload_cat(const float* a, int ra, const float* b, int rb, int cols, int col0, int ncols, bool transpose,
                  double** out);
   int gemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
@@ -79,9 +88,9 @@ class Decoder {
   // fused forward (decoder_fused.cuh): point-wise stages read the GEMM results in fp32 and write the next GEMM's operand
   // planes; [W_cat1 | W_sx] and [W_hp | W_ss] are single GEMMs; LRPCAP_DECODER_FUSED=0 restores the unfused sequence
   bool fused_ = false;
-  void *W1cat3_ = nullptr, *W2cat3_ = nullptr, *WifTC3_ = nullptr, *WpTC3_ = nullptr;
+  void *W1cat3_ = nullptr, *W2cat3_ = nullptr, *WpTC3_ = nullptr;
   int Npad1_ = 0, Npad2_ = 0, Hpad_ = 0;
-  DevBuf Axh_, Ahs_, Axh2_, Ahc_, C1_, C2_, C3_, C4_, Vf32_;
+  DevBuf Axh_, Ahs_, Axh2_, Ahc_, C1_, C2_, C3_, C4_, Vf32_, pred_, F32_;
   void *WcatB1TC_ = nullptr, *WcatB2TC_ = nullptr;   // [Kin, 4H] split-bf16: B operand of the gradient decoder's GEMMs
   void *Wcat1TC3_ = nullptr, *Wcat2TC3_ = nullptr, *WoTC3_ = nullptr;
   int Vpad_ = 0, G4pad_ = 0;
@@ -91,6 +100,9 @@ class Decoder {
   void* WifTC_ = nullptr;   // split-bf16 [D][H]: K-major B operand of the image_features relevance GEMM
   DevBuf UVs_, YF32_, gemm_ws_;
   std::vector<void*> owned_;
+  std::vector<size_t> owned_bytes_;
+  bool rederive_ = false;
+  size_t slot_cursor_ = 0;
   // weights (fp64, device)
   double *Wif_ = nullptr, *bif_ = nullptr, *WifT_ = nullptr, *Wgf_ = nullptr, *bgf_ = nullptr, *WgfT_ = nullptr;
   double *Emb_ = nullptr, *Wo_ = nullptr, *WoT_ = nullptr, *bo_ = nullptr;

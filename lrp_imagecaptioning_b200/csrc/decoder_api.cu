@@ -16,6 +16,11 @@ int lrpcap_decoder_create(lrpcap_decoder_t** out, const lrpcap_decoder_weights_t
   return kOk;
 }
 
+int lrpcap_decoder_set_weights_device(lrpcap_decoder_t* dec, const lrpcap_decoder_weights_t* d_w) {
+  LRPCAP_REQUIRE(dec && dec->impl, kErrInvalidArg, "decoder_set_weights_device: null handle");
+  return dec->impl->set_weights_device(d_w);
+}
+
 int lrpcap_decoder_destroy(lrpcap_decoder_t* dec) {
   if (!dec) return kOk;
   delete dec->impl;

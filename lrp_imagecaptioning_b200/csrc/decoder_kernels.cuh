@@ -511,16 +511,26 @@ __global__ void ra_kernel(WordRef w, const double* __restrict__ Ya, const double
 // adaptive: UV[p,l,:] = float32(Vf_l * alpha_t[l] * R_ctx / stab(ctx_t)) / stab(Vp_l)     (explainers.py:648-659)
 __global__ void uv_adaptive_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
                                    const double* __restrict__ ctx, const double* __restrict__ Rctx,
-                                   double* __restrict__ UV, int T, int L, int H) {
+                                   double* __restrict__ UV, int T, int L, int H, __nv_bfloat16* __restrict__ UVs = nullptr,
+                                   size_t nUVs = 0) {
+  // UVs != null: the rows go straight to the two bf16 planes (hi at UVs, lo at UVs + nUVs) of the image_features GEMM
   const int p = p0 + blockIdx.y, l = blockIdx.x;
   const int n = w.img[p], t = w.t[p];
   const double al = alpha[((size_t)n * (T + 1) + t) * L + l];
   const size_t st = ((size_t)n * (T + 1) + t) * H;
   const double* vp = Vp + ((size_t)n * L + l) * H;
-  double* o = UV + ((size_t)blockIdx.y * L + l) * H;
+  const size_t o0 = ((size_t)blockIdx.y * L + l) * H;
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
     const double rv = f32r(fmax(vp[j], 0.0) * al * Rctx[(size_t)p * H + j] / stabd(ctx[st + j]));
-    o[j] = rv / stabd(vp[j]);
+    const double u = rv / stabd(vp[j]);
+    if (UVs) {
+      __nv_bfloat16 hi, lo;
+      split_bf16((float)u, hi, lo);
+      UVs[o0 + j] = hi;
+      UVs[nUVs + o0 + j] = lo;
+    } else {
+      UV[o0 + j] = u;
+    }
   }
 }
 // grid-TD: r_V accumulates over every step <= t in a float32 buffer (explainers.py:1292-1299)
@@ -545,7 +555,8 @@ __global__ void uv_gridtd_kernel(WordRef w, int p0, const double* __restrict__ V
 constexpr int kUvMaxT = 24;   // the switch below enumerates steps 23 .. 0
 __global__ void __launch_bounds__(256, 3)
 uv_gridtd_rows_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
-                      const double* __restrict__ Q, double* __restrict__ UV, int T, int L, int H, int LG) {
+                      const double* __restrict__ Q, double* __restrict__ UV, int T, int L, int H, int LG,
+                      __nv_bfloat16* __restrict__ UVs = nullptr, size_t nUVs = 0) {
   const int p = p0 + blockIdx.y;
   const int n = w.img[p], t = w.t[p];
   const int l0 = blockIdx.x * LG, l1 = (l0 + LG < L) ? l0 + LG : L;
@@ -569,22 +580,72 @@ uv_gridtd_rows_kernel(WordRef w, int p0, const double* __restrict__ Vp, const do
         default: break;
       }
 #undef LRPCAP_UV_STEP
-      UV[((size_t)blockIdx.y * L + l) * H + j] = (double)acc / stabd(v);
+      const double u = (double)acc / stabd(v);
+      const size_t o = ((size_t)blockIdx.y * L + l) * H + j;
+      if (UVs) {
+        __nv_bfloat16 hi, lo;
+        split_bf16((float)u, hi, lo);
+        UVs[o] = hi;
+        UVs[nUVs + o] = lo;
+      } else {
+        UV[o] = u;
+      }
     }
   }
 }
+// The same redistribution in float32 arithmetic: r_V[l] = Vf_l * sum_i alpha_{i+1}[l] * Q_i accumulated with fp32 FMAs
+// (the reference accumulates fp64 products into a float32 buffer; both carry ~1e-7 of rounding, six times less work on the
+// fp64 / conversion pipes: 840 -> ~100 us per 512 words).  Always writes the GEMM's bf16 planes.
+__global__ void __launch_bounds__(256, 3)
+uv_gridtd_rows_f32_kernel(WordRef w, int p0, const double* __restrict__ Vp, const double* __restrict__ alpha,
+                          const double* __restrict__ Q, int T, int L, int H, int LG, __nv_bfloat16* __restrict__ UVs,
+                          size_t nUVs) {
+  const int p = p0 + blockIdx.y;
+  const int n = w.img[p], t = w.t[p];
+  const int l0 = blockIdx.x * LG, l1 = (l0 + LG < L) ? l0 + LG : L;
+  extern __shared__ float al_s[];                      // [LG][kUvMaxT]: alpha_{i+1}[l] of this block's locations
+  for (int k = threadIdx.x; k < (l1 - l0) * kUvMaxT; k += blockDim.x) {
+    const int ll = k / kUvMaxT, i = k - ll * kUvMaxT;
+    al_s[k] = i < t ? (float)alpha[((size_t)n * (T + 1) + i + 1) * L + l0 + ll] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    float q[kUvMaxT];
+#pragma unroll
+    for (int i = 0; i < kUvMaxT; ++i) q[i] = (i < t) ? (float)Q[((size_t)p * T + i) * H + j] : 0.f;
+    for (int l = l0; l < l1; ++l) {
+      const double v = Vp[((size_t)n * L + l) * H + j];
+      const float vf = (float)fmax(v, 0.0);
+      const float* al = al_s + (l - l0) * kUvMaxT;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = kUvMaxT - 1; i >= 0; --i) acc = fmaf(vf * al[i], q[i], acc);   // steps beyond t contribute exact zeros
+      const float u = (float)((double)acc / stabd(v));
+      const size_t o = ((size_t)blockIdx.y * L + l) * H + j;
+      __nv_bfloat16 hi, lo;
+      split_bf16(u, hi, lo);
+      UVs[o] = hi;
+      UVs[nUVs + o] = lo;
+    }
+  }
+}
+
 // R_F[word, l, d] = float32( float32(F/L * ra) + F * YF )      (explainers.py:641-659)
-__global__ void final_kernel(WordRef w, int p0, const int* __restrict__ order, const double* __restrict__ F,
-                             const double* __restrict__ ra, const double* __restrict__ YF, float* __restrict__ out, int L,
+// YT = float: YF is the tensor-core GEMM's fp32 result as is (no fp32 -> fp64 pass in between).
+// FT = float: the caller's float32 features as they came in (the fp64 copy F holds exactly those values).
+template <typename YT, typename FT = double>
+__global__ void final_kernel(WordRef w, int p0, const int* __restrict__ order, const FT* __restrict__ F,
+                             const double* __restrict__ ra, const YT* __restrict__ YF, float* __restrict__ out, int L,
                              int D) {
   const int p = p0 + blockIdx.y, l = blockIdx.x;
   const int n = w.img[p];
-  const double* f = F + ((size_t)n * L + l) * D;
-  const double* yf = YF + ((size_t)blockIdx.y * L + l) * D;
+  const FT* f = F + ((size_t)n * L + l) * D;
+  const YT* yf = YF + ((size_t)blockIdx.y * L + l) * D;
   float* o = out + ((size_t)order[p] * L + l) * D;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float first = (float)(f[d] / L * ra[(size_t)p * D + d]);
-    o[d] = (float)((double)first + f[d] * yf[d]);
+    const double fv = (double)f[d];
+    const float first = (float)(fv / L * ra[(size_t)p * D + d]);
+    o[d] = (float)((double)first + fv * (double)yf[d]);
   }
 }
 

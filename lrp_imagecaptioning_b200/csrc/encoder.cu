@@ -157,6 +157,55 @@ int Encoder::set_weights(const float* const* kernels_hwio, const float* const* b
   return kOk;
 }
 
+namespace {
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, unsigned* __restrict__ out) {
+  unsigned best = 0u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    best = max(best, __float_as_uint(w[i]) & 0x7fffffffu);
+  best = __reduce_max_sync(0xffffffffu, best);
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+}  // namespace
+
+// As set_weights, from DEVICE tensors (fine-tuning keeps the trained parameters on the device: no host round trip).
+int Encoder::set_weights_device(const float* const* d_kernels_hwio, const float* const* d_biases) {
+  LRPCAP_REQUIRE(d_kernels_hwio && d_biases, kErrInvalidArg, "encoder_set_weights_device: null argument");
+  for (int l = 0; l < nl_; ++l)
+    LRPCAP_REQUIRE(d_kernels_hwio[l] && d_biases[l], kErrInvalidArg, "encoder_set_weights_device: layer %d weights missing", l);
+  LRPCAP_CUDA(cudaDeviceSynchronize());   // nothing may still read the old layouts
+  DevBuf mx;
+  LRPCAP_TRY(mx.ensure(kMaxLayers * sizeof(unsigned)));
+  LRPCAP_CUDA(cudaMemset(mx.p, 0, kMaxLayers * sizeof(unsigned)));
+  for (int l = 0; l < nl_; ++l) {
+    Layer& L = L_[l];
+    const size_t nw = (size_t)9 * L.cin * L.cout;
+    LRPCAP_CUDA(cudaMemcpy(L.w_hwio, d_kernels_hwio[l], nw * sizeof(float), cudaMemcpyDeviceToDevice));
+    LRPCAP_CUDA(cudaMemcpy(L.bias, d_biases[l], L.cout * sizeof(float), cudaMemcpyDeviceToDevice));
+    absmax_kernel<<<64, 256>>>(L.w_hwio, nw, mx.as<unsigned>() + l);
+    for (auto& f : L.prepared)
+      for (auto& p : f)
+        if (p) { cudaFree(p); p = nullptr; }
+    for (auto& p : L.dual)
+      if (p) { cudaFree(p); p = nullptr; }
+  }
+  LRPCAP_CUDA(cudaGetLastError());
+  float** small[] = {&w0_pm_, &w0_mp_, &w0_last_a_, &w0_last_b_};
+  for (float** p : small)
+    if (*p) { cudaFree(*p); *p = nullptr; }
+  float hmax[kMaxLayers];
+  LRPCAP_CUDA(cudaMemcpy(hmax, mx.p, kMaxLayers * sizeof(float), cudaMemcpyDeviceToHost));
+  mx.release();
+  for (int l = 0; l < nl_; ++l) {
+    int ex = 0;
+    if (hmax[l] > 0.f && std::isfinite(hmax[l])) std::frexp(hmax[l], &ex);
+    L_[l].wpow = 13 - ex;
+  }
+  w0_host_.resize((size_t)9 * 3 * 64);
+  LRPCAP_CUDA(cudaMemcpy(w0_host_.data(), L_[0].w_hwio, w0_host_.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  n_images_ = 0;
+  return kOk;
+}
+
 int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
   Layer& L = L_[l];
   if (!L.prepared[fmt][sign]) {

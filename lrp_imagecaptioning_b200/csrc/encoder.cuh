@@ -55,6 +55,7 @@ class Encoder {
   // Replaces the 13 kernels / biases in place (fine-tuning: the explained model changes every step); keeps every large
   // state / message buffer, drops the prepared weight layouts and the per-image state.
   int set_weights(const float* const* kernels_hwio, const float* const* biases);
+  int set_weights_device(const float* const* d_kernels_hwio, const float* const* d_biases);   // the same from device tensors
   // images: device fp32 [n, hw, hw, 3] (already preprocessed). Builds features + per-image rule state.
   int forward(const float* d_images, int n_images, const EncoderRule& rule, cudaStream_t s);
   const float* features() const { return F_.as<float>(); }   // device fp32 [n, hw/16, hw/16, 512]

@@ -43,6 +43,43 @@ class DecoderEngine(object):
             self._h = h
         return self._h
 
+    def set_weights_device(self, tensors):
+        """In-place weight replacement from CUDA float32 tensors: `tensors` maps the weight names of synth.decoder_weights
+        ('image_features_w', ..., 'V' for the attention vector) to contiguous tensors of the handle's shapes."""
+        names = _SHARED + (_ADAPTIVE if self.kind == "adaptive" else _GRIDTD)
+        w = _lib.DecoderWeights()
+        w.kind = _lib.DECODER_ADAPTIVE if self.kind == "adaptive" else _lib.DECODER_GRIDTD
+        w.V, w.H, w.E, w.D = self.V, self.H, self.E, self.D
+        keep = []
+        for k in names + (("Vatt",) if self.kind == "adaptive" else ()):
+            t = tensors["V" if k == "Vatt" else k]
+            ref = self._w[k]
+            if tuple(t.shape) != ref.shape or t.dtype != torch.float32 or not t.is_cuda:
+                raise ValueError("set_weights_device: %s must be a float32 CUDA tensor of shape %s" % (k, ref.shape))
+            t = t.contiguous()
+            keep.append(t)
+            setattr(w, k, ctypes.cast(t.data_ptr(), _lib.c_float_p))
+        _lib.check(_lib.load().lrpcap_decoder_set_weights_device(self.handle(), ctypes.byref(w)))
+        self.N = 0
+
+    def predict(self, features, captions, eos=-1):
+        """Teacher-forced forward that returns the arg-max token of every step ([N, T] int32) -- `argmax(model.predict)` of
+        the LRP-inference loop.  `captions[n, i]` is the token fed at step i + 1 (SOS is fed at step 0).  The handle holds
+        no explainable state afterwards: run `forward(features, captions=predicted)` next."""
+        f = features
+        if isinstance(f, np.ndarray):
+            f = torch.from_numpy(np.ascontiguousarray(f, dtype=np.float32))
+        f = f.to(self.device).contiguous().float()
+        N = f.shape[0]
+        f = f.reshape(N, -1, f.shape[-1])
+        cap = np.ascontiguousarray(np.asarray(captions), dtype=np.int32).copy()
+        if cap.ndim != 2 or cap.shape[0] != N:
+            raise ValueError("captions must be [N, T]")
+        _lib.check(_lib.load().lrpcap_decoder_forward(self.handle(), _lib.c_void_p(f.data_ptr()), N, f.shape[1], _lib.iptr(cap),
+                                                      cap.shape[1], 2, int(eos), self._stream()))
+        self.N = 0
+        return cap
+
     def close(self):
         if self._h is not None:
             _lib.load().lrpcap_decoder_destroy(self._h)

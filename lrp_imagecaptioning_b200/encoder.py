@@ -79,6 +79,20 @@ class ImageModel(object):
             bs = (_lib.c_float_p * n)(*[_lib.fptr(b) for _, b in self.weights])
             _lib.check(_lib.load().lrpcap_encoder_set_weights(self._h, ks, bs))
 
+    def set_weights_device(self, kernels_hwio, biases):
+        """In-place weight replacement from CUDA tensors (lists of contiguous float32 tensors, HWIO kernels): no host round
+        trip.  `self.weights` (the host copy) is NOT refreshed -- call `sync_host_weights` if it is needed."""
+        if len(kernels_hwio) != len(self.weights) or len(biases) != len(self.weights):
+            raise ValueError("set_weights_device needs %d kernels and biases" % len(self.weights))
+        for k, b, (k0, b0) in zip(kernels_hwio, biases, self.weights):
+            if tuple(k.shape) != k0.shape or tuple(b.shape) != b0.shape or k.dtype != torch.float32 or not k.is_cuda or not k.is_contiguous():
+                raise ValueError("set_weights_device: contiguous float32 CUDA tensors with the model's shapes are required")
+        n = len(self.weights)
+        ks = (_lib.c_void_p * n)(*[k.data_ptr() for k in kernels_hwio])
+        bs = (_lib.c_void_p * n)(*[b.contiguous().data_ptr() for b in biases])
+        self._state = None
+        _lib.check(_lib.load().lrpcap_encoder_set_weights_device(self.handle(), ks, bs))
+
     def close(self):
         if self._h is not None:
             _lib.load().lrpcap_encoder_destroy(self._h)

@@ -87,6 +87,23 @@ class _LRPInferenceLayer(object):
                                                           _lib.fptr(out), stream))
         return out.astype(np.float64)
 
+    def sparse_weights(self, images, caption_encoded, features_ready=False):
+        """The non-trivial entries of `call`'s result for an already known predicted caption [B, T] (tokenizer ids):
+        (sample, position - 1, vocabulary column, score) arrays -- everything else of the (B, T, V) weight is 1.
+        features_ready: the engine's encoder already holds the forward state of `images` (same rule)."""
+        caption_encoded = np.ascontiguousarray(caption_encoded, dtype=np.int32)
+        wi, wt = self.word_list(caption_encoded)
+        if not len(wi):
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z, np.zeros(0, dtype=np.float64)
+        eng = self._engine
+        if not features_ready:
+            eng.image_model.forward(images, eng.rule)
+        eng.decoder.forward(eng.image_model.features(), captions=caption_encoded)
+        sc = self.scores(eng.explain_words(wi, wt))
+        col = caption_encoded[wi, wt - 1].astype(np.int64)          # quirk B10: column = tokenizer id, not id - 1
+        return wi.astype(np.int64), (wt - 1).astype(np.int64), col, sc
+
     def call(self, inputs):
         assert len(inputs) == 3
         _, img_inputs, y_preds = inputs
@@ -147,6 +164,16 @@ class CaptionerTorch(torch.nn.Module):
         model.vgg = vgg
         model.image_model.set_weights(vgg)
         return model
+
+    def sync_engine(self, engine):
+        """Device-to-device: the engine's encoder and decoder handles take the current parameters in place
+        (lrpcap_encoder_set_weights_device / lrpcap_decoder_set_weights_device); nothing goes through the host.
+        The host copies `model.vgg` / `model.dec` are left as they were (use export_into for those)."""
+        with torch.no_grad():
+            ks = [w.detach().permute(2, 3, 1, 0).contiguous() for w in self.conv_w]
+            bs = [b.detach().contiguous() for b in self.conv_b]
+            engine.image_model.set_weights_device(ks, bs)
+            engine.decoder.set_weights_device({k: p.detach() for k, p in self.dec.items()})
 
     def features(self, images_nhwc):
         x = images_nhwc.permute(0, 3, 1, 2)
@@ -214,11 +241,45 @@ def lrp_inference_loss(logits, lrp_weight, y_true):
     return 0.5 * ce(lg) + 0.5 * ce(lg * w)
 
 
+def lrp_inference_loss_sparse(logits, b_idx, t_idx, col, score, target):
+    """The same loss with the weight given by its non-trivial entries (w = 1 everywhere else) and the target as class
+    indices [B, T] (model index = tokenizer id - 1): no dense (B, T, V) weight / one-hot tensors."""
+    weighted = logits.clone()
+    if b_idx.numel():
+        weighted[b_idx, t_idx, col] = logits[b_idx, t_idx, col] * (1.0 + score)
+    V = logits.shape[-1]
+    tgt = target[:, :-1].reshape(-1)
+    ce = lambda z: Fn.cross_entropy(z[:, :-1].reshape(-1, V), tgt)   # noqa: E731
+    return 0.5 * ce(logits) + 0.5 * ce(weighted)
+
+
+def allreduce_mean_(params, dist_module=None):
+    """In place: every parameter's .grad becomes the mean over the ranks of the process group (one flattened all-reduce,
+    NCCL over NVLink on the GPU box).  Returns the flattened reduced gradient; no-op (returns the local flat gradient)
+    without an initialised multi-rank group."""
+    import torch.distributed as dist
+    dist = dist_module or dist
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat)
+        flat /= dist.get_world_size()
+        off = 0
+        for p in params:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+    return flat
+
+
 class LRPInferenceTrainer(object):
-    """One fine-tuning step = predict -> LRP weights for the predicted words -> train on [y, y] (train.py:569-577)."""
+    """One fine-tuning step = predict -> LRP weights for the predicted words -> train on [y, y] (train.py:569-577).
+
+    Everything stays on the device: the engine's handles follow the trained parameters through
+    `CaptionerTorch.sync_engine` (device-to-device), the prediction is the engine's own teacher-forced forward in
+    arg-max mode (no second VGG16 pass, no (B, T, V) host copy), the per-word scores enter the loss as a sparse update of
+    the logits, and the one collective is the NCCL all-reduce of the flattened gradient."""
 
     def __init__(self, model, dataset_provider, lrp_inference_mode="mean", learning_rate=1e-4, clipvalue=None,
-                 stop_words=DEFAULT_STOP_WORDS):
+                 stop_words=DEFAULT_STOP_WORDS, tf32=True):
         self.model = model
         self.provider = dataset_provider
         self.mode = lrp_inference_mode
@@ -226,37 +287,50 @@ class LRPInferenceTrainer(object):
         self.net = CaptionerTorch(model)
         self.clipvalue = clipvalue if clipvalue is not None else (0.01 if model.kind == "adaptive" else 0.1)
         self.opt = torch.optim.Adam(self.net.parameters(), lr=learning_rate, eps=1e-7)
-        self.layer_cls = LRPInferenceLayerAdaptive if model.kind == "adaptive" else LRPInferenceLayergridTD
+        layer_cls = LRPInferenceLayerAdaptive if model.kind == "adaptive" else LRPInferenceLayergridTD
+        self.layer = layer_cls(model, dataset_provider, model._hidden_dim, model._embedding_dim, model.L, model.D,
+                               model.img_encoder, lrp_inference_mode, stop_words=stop_words, overflow="skip")
+        if tf32:   # the differentiable pass is plain PyTorch; TF32 is what TF/Keras use on this class of GPU
+            torch.backends.cudnn.allow_tf32 = True
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.explained_words = 0          # words explained in the last step
         self.explained_words_total = 0
+        self.last_gradient = None         # flattened (all-reduced, unclipped) gradient of the last step, when keep_gradient
 
-    def step(self, captions_in, images, y_true):
-        """captions_in [B, T] int (tokenizer ids), images [B, hw, hw, 3], y_true [B, T, V] one-hot. Returns the loss."""
-        import torch.distributed as dist
+    def predict(self, captions_in, images):
+        """Predicted caption [B, T] (tokenizer ids) = argmax of the teacher-forced logits + 1, on the engine; leaves the
+        encoder's forward state of `images` in place for the explanation."""
+        eng = self.layer._engine
+        cap_in = np.asarray(captions_in)
+        teacher = np.concatenate([cap_in[:, 1:], cap_in[:, -1:]], axis=1).astype(np.int32)   # input of step i+1 = teacher[:, i]
+        eng.image_model.forward(images, eng.rule)
+        return eng.decoder.predict(eng.image_model.features(), teacher)
+
+    def step(self, captions_in, images, y_true, keep_gradient=False):
+        """captions_in [B, T] int (tokenizer ids fed at each step, SOS first), images [B, hw, hw, 3], y_true [B, T, V]
+        one-hot or [B, T] class indices (model index = tokenizer id - 1). Returns the loss."""
         dev = next(self.net.parameters()).device
         tok = torch.as_tensor(np.asarray(captions_in), device=dev).long()
-        img = torch.as_tensor(np.asarray(images, dtype=np.float32), device=dev)
-        y = torch.as_tensor(np.asarray(y_true, dtype=np.float32), device=dev)
-        with torch.no_grad():
-            y_pred = self.net(tok, img).cpu().numpy()
-        layer = self.layer_cls(self.model, self.provider, self.model._hidden_dim, self.model._embedding_dim, self.model.L,
-                               self.model.D, self.model.img_encoder, self.mode, stop_words=self.stop_words, overflow="skip")
-        w = layer.call([captions_in, images, y_pred])
-        self.explained_words = int(len(layer.word_list((np.argmax(y_pred, axis=-1) + 1).astype(np.int32))[0]))
+        img = images if torch.is_tensor(images) else torch.as_tensor(np.asarray(images, dtype=np.float32))
+        img = img.to(dev)
+        y = torch.as_tensor(np.asarray(y_true), device=dev)
+        target = y.long() if y.dim() == 2 else y.argmax(dim=-1)
+        self.net.sync_engine(self.layer._engine)                      # the engine explains the model being trained
+        pred = self.predict(captions_in, img)
+        b_idx, t_idx, col, sc = self.layer.sparse_weights(img, pred, features_ready=True)
+        V = self.model._vocab_size
+        keep = col < V                                                # quirk B10 overflow: such a word stays unweighted
+        self.explained_words = int(len(b_idx))
         self.explained_words_total += self.explained_words
-        w = torch.as_tensor(w, dtype=torch.float32, device=dev)
+        tb = lambda a, dt: torch.as_tensor(np.asarray(a)[keep], dtype=dt, device=dev)   # noqa: E731
         self.opt.zero_grad(set_to_none=True)
-        loss = lrp_inference_loss(self.net(tok, img), w, y)
+        loss = lrp_inference_loss_sparse(self.net(tok, img), tb(b_idx, torch.long), tb(t_idx, torch.long), tb(col, torch.long),
+                                         tb(sc, torch.float32), target)
         loss.backward()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in self.net.parameters()])
-            dist.all_reduce(flat)                     # NCCL over NVLink: the one collective of the fine-tune step
-            flat /= dist.get_world_size()
-            off = 0
-            for p in self.net.parameters():
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
-        torch.nn.utils.clip_grad_value_(self.net.parameters(), self.clipvalue)
+        params = [p for p in self.net.parameters()]
+        flat = allreduce_mean_(params)                # NCCL over NVLink: the one collective of the fine-tune step
+        if keep_gradient:
+            self.last_gradient = flat
+        torch.nn.utils.clip_grad_value_(params, self.clipvalue)
         self.opt.step()
-        self.net.export_into(self.model)            # the next step explains with the updated weights
         return float(loss.item())

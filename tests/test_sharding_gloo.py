@@ -55,3 +55,34 @@ def test_uneven_shards():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, 29534, 5, ret), nprocs=2, join=True)
     assert np.array_equal(ret["gathered"], ret["single"])
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lrp_imagecaptioning_b200.lrp_inference import allreduce_mean_
+    g = torch.Generator().manual_seed(100 + rank)
+    params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7))]
+    local = [torch.randn(p.shape, generator=g) for p in params]
+    for p, l in zip(params, local):
+        p.grad = l.clone()
+    flat = allreduce_mean_(params)
+    ret["local%d" % rank] = [l.numpy() for l in local]
+    ret["reduced%d" % rank] = [p.grad.numpy().copy() for p in params]
+    ret["flat%d" % rank] = flat.numpy().copy()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_is_the_mean_of_the_per_rank_gradients():
+    """The fine-tune step's one collective (lrp_inference.allreduce_mean_, train.py:569-577 on N GPUs): after it every rank
+    holds (sum of the per-rank gradients) / world, parameter by parameter."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, 29535, ret), nprocs=2, join=True)
+    for k in range(2):
+        want = (ret["local0"][k] + ret["local1"][k]) / 2.0
+        for r in range(2):
+            assert np.allclose(ret["reduced%d" % r][k], want, rtol=0, atol=1e-7)
+    assert np.array_equal(ret["flat0"], ret["flat1"])
+    assert np.allclose(ret["flat0"], np.concatenate([((ret["local0"][k] + ret["local1"][k]) / 2.0).reshape(-1) for k in range(2)]), atol=1e-7)

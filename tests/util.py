@@ -67,6 +67,27 @@ def topk_cells(R, k=10, cell=16):
     return [int(i) for i in order[:min(k, order.size)]]
 
 
+def cell_sums(R, cell=16):
+    R = _f64(R)
+    H, W = R.shape[0], R.shape[1]
+    return R.reshape(H // cell, cell, W // cell, cell, -1).sum(axis=(1, 3, 4)).reshape(-1)
+
+
+def same_topk(got, ref, k=10, cell=16, tol=REL_TOL, sums=None):
+    """"Identical top-k relevant grid regions" up to ties inside the stated tolerance: the two rankings must agree rank
+    by rank, except where the reference's own scores of the two cells involved differ by less than tol * max|score| (a
+    difference the per-pixel tolerance itself allows to go either way).  sums: callable giving the per-cell scores."""
+    f = sums or (lambda a: cell_sums(a, cell))
+    g, r = f(got), f(ref)
+    og = np.argsort(-g, kind="stable")[:min(k, g.size)]
+    orf = np.argsort(-r, kind="stable")[:min(k, r.size)]
+    scale = np.max(np.abs(r))
+    for a, b in zip(og, orf):
+        if a != b and abs(r[a] - r[b]) > tol * scale:
+            return False
+    return True
+
+
 def topk_features(R, k=10):
     """Top-k grid cells of a feature-level relevance map R [L, D] or [h, w, D] (summed over D)."""
     g = _f64(R).sum(axis=-1).reshape(-1)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblrpcap.so")
+LIB_PATH = os.environ.get("LRPCAP_LIB") or os.path.join(_HERE, "liblrpcap.so")   # LRPCAP_LIB: e.g. the bounds-checking debug build
 
 OK = 0
 PREC_FP32_SIMT, PREC_BF16X3_TC, PREC_F16X2_TC, PREC_TC_AUTO = 0, 1, 2, 3

@@ -36,7 +36,14 @@ def _stamp(paths):
     return h.hexdigest()
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, debug=False):
+    """debug=True: -DLRPCAP_DEBUG_BOUNDS (every epilogue address checked against its tensor's logical size, violation =
+    printf + trap) into liblrpcap_dbg.so; select it at run time with LRPCAP_LIB=<path> (tools/run_bounds_check.py)."""
+    global OBJ, LIB, NVCC_FLAGS
+    if debug:
+        OBJ = os.path.join(CSRC, "build_dbg")
+        LIB = os.path.join(HERE, "liblrpcap_dbg.so")
+        NVCC_FLAGS = NVCC_FLAGS + ["-DLRPCAP_DEBUG_BOUNDS"]
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "lrpcap.h")]
     stamp = _stamp(deps)
@@ -68,4 +75,4 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

@@ -510,6 +510,8 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
       ep.rule_bias = rule.bias;
       ep.g_up = L.pool_after ? 2 : 1;
       if (gmode != G_NONE) { ep.G = Gl; ep.Mseed = Ml; }
+      ep.g_elems = (size_t)m * oe;
+      ep.aux_elems = (size_t)m * oe;
       LRPCAP_TRY(conv(l, false, WS_ALL, X, X_elems, m, ep, s));
 
       if (ab || zpf) {
@@ -521,6 +523,8 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
         ez.x_act_elems = (size_t)m * oe;
         ez.G = Gl;
         ez.Mseed = Ml;
+        ez.g_elems = (size_t)m * oe;
+        ez.aux_elems = (size_t)m * oe;
         ez.g_up = L.pool_after ? 2 : 1;
         if (l == 0 && ab) {
           LRPCAP_TRY(posneg_.ensure((size_t)m * hw_ * hw_ * 6 * sizeof(float)));
@@ -656,6 +660,7 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       ep.up = L_[l - 1].pool_after ? 2 : 1;
       ep.Gin = ep.up == 2 ? Gc_[l - 1].as<float>() : G_[l - 1].as<float>();
       ep.Gidx = ep.up == 2 ? Gi_[l - 1].as<unsigned>() : nullptr;
+      ep.g_elems = (size_t)n_images_ * layer_out_elems(l - 1) / (ep.up == 2 ? 4 : 1);
       ep.relu_acc = guided ? 1 : 0;
       ep.out_msg = msg_[cur ^ 1].p;
       ep.Gin2 = inh ? (ep.up == 2 ? Gc2_[l - 1].as<float>() : G2_[l - 1].as<float>()) : nullptr;

@@ -40,7 +40,25 @@ struct EpiDev {
   const int* kt_in;        // [items] log2 of the incoming message's scale
   int* kt_out;             // [items] log2 of the outgoing message's scale (every tile of an item writes the same value)
   int target_exp;          // the predicted maximum of the outgoing plane is 2^target_exp
+  size_t g_elems;          // LRPCAP_DEBUG_BOUNDS: floats behind G / Gin (one multiplier tensor), 0 = unknown
+  size_t aux_elems;        // LRPCAP_DEBUG_BOUNDS: floats behind out_f32 / Mseed, 0 = unknown
 };
+
+// Debug build (python -m lrp_imagecaptioning_b200.build --debug -> liblrpcap_dbg.so, run by tools/run_bounds_check.py):
+// every epilogue address is checked against the logical size of the tensor it belongs to; a violation prints the site
+// and traps (compute-sanitizer is closed on this GPU pool).
+#ifdef LRPCAP_DEBUG_BOUNDS
+#define LRPCAP_BOUNDS(what, off, n, limit)                                                                              \
+  do {                                                                                                                  \
+    if ((limit) != 0 && (size_t)(off) + (size_t)(n) > (size_t)(limit)) {                                                \
+      printf("lrpcap bounds: %s offset %llu + %d > %llu (block %d thread %d)\n", what, (unsigned long long)(off), (int)(n),  \
+             (unsigned long long)(limit), (int)blockIdx.x, (int)threadIdx.x);                                           \
+      __trap();                                                                                                         \
+    }                                                                                                                   \
+  } while (0)
+#else
+#define LRPCAP_BOUNDS(what, off, n, limit) ((void)0)
+#endif
 
 constexpr int kMsgTargetExp = 4;   // default: predicted maximum 2^4: 2^12 of head-room against growth, 2^-28 of the maximum resolved
 // log2 of the factor that brings a plane whose maximum has float bits `mbits` to the target maximum 2^target
@@ -313,8 +331,10 @@ template <int NV, class ST>
 __device__ __forceinline__ void epi_store_msg(const EpiDev& e, size_t item_pixels, int item, size_t pix, int NO, int n,
                                               const float (&o)[NV]) {
   if (!e.out_planar_f32) {
+    LRPCAP_BOUNDS("message", ((size_t)item * item_pixels + pix) * NO + n, NV, e.out_elems);
     ST::template store<NV>(e.out, e.out_elems, ((size_t)item * item_pixels + pix) * NO + n, o);
   } else {
+    LRPCAP_BOUNDS("planar message", ((size_t)item * NO + n + NV - 1) * item_pixels + pix, 1, e.out_elems);
     // last message: fp32, fully channel-planar [item][NO][pixels] -- what the 64 -> 3 transposed conv (fp32 FMA, reads a
     // 3x3 window per channel through TMA) consumes; adjacent lanes are adjacent pixels, so the stores coalesce
     float* dst = reinterpret_cast<float*>(e.out) + ((size_t)item * NO + n) * item_pixels + pix;
@@ -388,6 +408,7 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
     unsigned gi[NB] = {};
     if (PIPE && valid) {
       const size_t o0 = gpix + (size_t)(n_first >> 4) * gplane;
+      LRPCAP_BOUNDS("multiplier", o0 * 16, 16, e.g_elems);
       load_f32<16>(G + o0 * 16, gg[0]);
       if (UP == 2) gi[0] = __ldg(e.Gidx + o0);
     }
@@ -404,11 +425,13 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
       if (PIPE) {
         if (c + 1 < NCH && valid) {
           const size_t o1 = gpix + (size_t)((n + n_step) >> 4) * gplane;
+          LRPCAP_BOUNDS("multiplier", o1 * 16, 16, e.g_elems);
           load_f32<16>(G + o1 * 16, gg[(c + 1) % NB]);
           if (UP == 2) gi[(c + 1) % NB] = __ldg(e.Gidx + o1);
         }
       } else if (valid) {
         const size_t o1 = gpix + (size_t)(n >> 4) * gplane;
+        LRPCAP_BOUNDS("multiplier", o1 * 16, 16, e.g_elems);
         load_f32<16>(G + o1 * 16, gg[0]);
         if (UP == 2) gi[0] = __ldg(e.Gidx + o1);
       }
@@ -469,8 +492,12 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
       for (int i = 0; i < NV; ++i) mx = fmaxf(mx, xo[i]);
       if (!(mx < 32768.f)) atomicOr(e.overflow, 1);
     }
+    LRPCAP_BOUNDS("activation", off, NV, e.out_elems);
     ST::template store<NV>(e.out, e.out_elems, off, xo);
-    if (e.out_f32) store_f32<NV>(e.out_f32 + off, xo);
+    if (e.out_f32) {
+      LRPCAP_BOUNDS("features", off, NV, e.aux_elems);
+      store_f32<NV>(e.out_f32 + off, xo);
+    }
     if (e.G || e.Mseed) {
       float gg[NV], mm[NV];
 #pragma unroll
@@ -489,12 +516,19 @@ __device__ __forceinline__ void epi_apply(const EpiDev& e, int H, int W, int Nou
           gg[i] = mm[i];
         }
       }
-      if (e.G) store_f32<NV>(e.G + g_offset(item, y, x, n, H, W, Nout, e.g_up), gg);
-      if (e.Mseed) store_f32<NV>(e.Mseed + off, mm);
+      if (e.G) {
+        LRPCAP_BOUNDS("multiplier store", g_offset(item, y, x, n, H, W, Nout, e.g_up), NV, e.g_elems);
+        store_f32<NV>(e.G + g_offset(item, y, x, n, H, W, Nout, e.g_up), gg);
+      }
+      if (e.Mseed) {
+        LRPCAP_BOUNDS("seed multiplier", off, NV, e.aux_elems);
+        store_f32<NV>(e.Mseed + off, mm);
+      }
     }
   } else if (MODE == EPI_FWD_ZACT) {
     const size_t off = (((size_t)item * H + y) * W + x) * Nout + n;
     float xa[NV], gg[NV], mm[NV];
+    LRPCAP_BOUNDS("activation read", off, NV, e.x_elems);
     ST::template load<NV>(e.x_act, e.x_elems, off, xa);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -542,6 +576,8 @@ inline int make_epi_dev(const EpiParams& p, EpiDev* e) {
   e->kt_in = p.kt_in;
   e->kt_out = p.kt_out;
   e->target_exp = p.target_exp;
+  e->g_elems = p.g_elems;
+  e->aux_elems = p.aux_elems;
   e->out = nullptr;
   e->out_elems = 0;
   switch (p.mode) {

@@ -59,6 +59,9 @@ struct EpiParams {
   const int* kt_in = nullptr;
   int* kt_out = nullptr;
   int target_exp = 4;               // predicted maximum of the outgoing fp16 plane: 2^target_exp
+  // logical sizes for the debug build's bounds checks (epilogue.cuh: LRPCAP_DEBUG_BOUNDS); 0 = not checked
+  size_t g_elems = 0;               // floats behind G (forward) / Gin, Gin2 (backward)
+  size_t aux_elems = 0;             // floats behind out_f32 / Mseed
 };
 
 struct TcConvArgs {

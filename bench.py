@@ -320,7 +320,12 @@ def run_ours(args, rank, local_rank, world):
 
     total_words = job.n_words * world
     value = total_words / (ms / 1000.0)
-    products = 2 if (args.precision == "f16x2" or (args.precision == "tc" and args.workload == "config3")) else 3
+    same_sign = args.workload == "config3"
+    mode = {"tc": "f16x2" if same_sign else "h1f8", "bf16x3": "bf16x3", "f16x2": "f16x2", "h1f8": "h1f8", "fp32": "fp32"}[args.precision]
+    products = 3 if mode == "bf16x3" else 2
+    how = {"bf16x3": "hi*hi + hi*lo + lo*hi, bf16 planes", "f16x2": "a*w_hi + a*w_lo, one scaled fp16 message plane",
+           "h1f8": "one kind::f16 product a16*w_hi plus one double-rate kind::f8f6f4 product [a8 | r8]*[w_lo8 ; w8] = two "
+                   "product-equivalents", "fp32": "fp32 FMA"}[mode]
     peak_tf, peak_bw, peak_src = peaks()
     tc_ms, tc_flops, tc_n = prof["tc_bwd"]
     achieved = (tc_flops / 1e12) / (tc_ms / 1e3) if tc_ms > 0 else 0.0
@@ -332,9 +337,9 @@ def run_ours(args, rank, local_rank, world):
                                 "scaled to this run's words per launch" % NCU_DRAM_MB_PER_WORD,
                 "peak_source": "%s bf16 cuBLAS (sustained)" % peak_src,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC of the transposed convs, %.2f GFLOP/word) / CUDA-event "
-                        "kernel time of one instrumented step; every algorithmic MAC is %d 16-bit tensor-core MACs (%s), "
-                        "so tensor-pipe work is %dx this figure" % (ENC_GFLOP_PER_WORD * job.flop_mul, products,
-                                                                    "hi*hi + hi*lo + lo*hi" if products == 3 else "a*w_hi + a*w_lo, fp16 message", products),
+                        "kernel time of one instrumented step; every algorithmic MAC costs %d 16-bit tensor-core MAC-equivalents (%s), "
+                        "so tensor-pipe work is %dx this figure" % (ENC_GFLOP_PER_WORD * job.flop_mul, products, how, products),
+                "backward_arithmetic": mode,
                 "products_per_mac": products,
                 "tensor_pipe_frac": products * achieved / peak_tf if peak_tf else None,
                 "kernel_ms_per_step": tc_ms, "kernel_launches_per_step": tc_n,
@@ -343,7 +348,7 @@ def run_ours(args, rank, local_rank, world):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms, "higher_is_better": True, "scaling": WORKLOADS[args.workload][2], "vs_baseline": None,
            "dtype": "f32 encoder / f64 decoder" if args.precision == "fp32" else
-                    "f32 as split 16-bit tensor-core operands (%d products backward, 3 forward on f16 planes), fp32 accumulate; f64 decoder" % products,
+                    "f32 emulated on the 16-/8-bit tensor pipe (backward: %s = %d product-equivalents per MAC; forward: 3 products on f16 planes), fp32 accumulate; f64 decoder rules" % (mode, products),
            "data": "synthetic", "config": config_dict(args, world, args.workload, job.rule_desc), "clocks": clocks,
            "gpu_launches": int(launches),
            "e2e": {"value": total_words / (ms_e2e / 1000.0), "unit": UNIT, "ms_per_step": ms_e2e,
@@ -392,8 +397,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--rule", default="presetA", choices=["presetA", "a2b1"], help="config3 only: the alpha-beta rule")
-    ap.add_argument("--precision", default="tc", choices=["tc", "bf16x3", "f16x2", "fp32"],
-                    help="tc: tensor cores, two products per MAC for the alpha-beta family, three for the other rules")
+    ap.add_argument("--precision", default="tc", choices=["tc", "bf16x3", "f16x2", "h1f8", "fp32"],
+                    help="tc: tensor cores; fp16 two-product backward for the alpha-beta family, fp16 + fp8 for the other rules")
     ap.add_argument("--chunk-words", type=int, default=320)
     ap.add_argument("--promote", type=int, default=None, help="backward accumulator promotion interval (k-steps; 0 = off, -1 = default policy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -36,8 +36,11 @@ extern "C" {
                                  * two per word and layer, against two fp16 weight planes: 2 products per MAC instead of 3
                                  * and half the message bytes; 11-bit messages (alpha-beta family: 2e-5 maps) */
 
-#define LRPCAP_PREC_TC_AUTO 3   /* tensor cores, products per rule: two for the alpha-beta family / z+ (same-sign chains),
-                                 * three for epsilon, z and the gradient family (mixed-sign chains need the 16-bit message) */
+#define LRPCAP_PREC_TC_AUTO 3   /* tensor cores, arithmetic per rule: the two-product fp16 mode for the alpha-beta family / z+
+                                 * (same-sign chains), the fp16 + fp8 mode for epsilon, z and the gradient family */
+#define LRPCAP_PREC_H1F8_TC 4   /* messages as a scaled fp16 plane + an E4M3 plane of [top bits | rounding residual], weights as
+                                 * an fp16 high plane + an E4M3 plane of [low part | high part]: one kind::f16 and one
+                                 * double-rate kind::f8f6f4 product per MAC (two product-equivalents, ~15 bits) */
 
 /* encoder rules; replaces the iNNvestigate analyzer classes constructed in
  * models/explainers.py:32,671,883,928 (LRPSequentialPresetA, Gradient, InputTimesGradient, GuidedBackprop) and
@@ -242,7 +245,7 @@ int lrpcap_encoder_debug_message_scales(lrpcap_encoder_t* enc, float* h_max, int
 /* Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
  * precision: LRPCAP_PREC_FP32_SIMT; LRPCAP_PREC_BF16X3_TC (two bf16 planes: the backward arithmetic); 2 = three bf16
  * planes, promoted; 3 = two IEEE half planes, promoted (the forward arithmetic); 4 = the two-product backward arithmetic
- * (A rounded to one fp16 plane x two fp16 weight planes).
+ * (A rounded to one fp16 plane x two fp16 weight planes); 5 = the fp16 + fp8 backward arithmetic.
  * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LRPCAP_LIB") or os.path.join(_HERE, "liblrpcap.so")   # LRPCAP_LIB: e.g. the bounds-checking debug build
 
 OK = 0
-PREC_FP32_SIMT, PREC_BF16X3_TC, PREC_F16X2_TC, PREC_TC_AUTO = 0, 1, 2, 3
+PREC_FP32_SIMT, PREC_BF16X3_TC, PREC_F16X2_TC, PREC_TC_AUTO, PREC_H1F8_TC = 0, 1, 2, 3, 4
 RULE_EPSILON, RULE_Z, RULE_ALPHA_BETA, RULE_ZPLUS_FAST, RULE_GRADIENT, RULE_INPUT_T_GRADIENT, RULE_GUIDED_BACKPROP = range(7)
 DECODER_ADAPTIVE, DECODER_GRIDTD = 0, 1
 

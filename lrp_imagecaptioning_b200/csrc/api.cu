@@ -3,6 +3,7 @@
 #include "handles.cuh"
 #include "encoder_kernels.cuh"
 #include "tc_conv.cuh"
+#include <cmath>
 #include <vector>
 
 namespace lrpcap {
@@ -163,6 +164,7 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
   const size_t nA = (size_t)items * H * W * C, nB = (size_t)taps * C * Nout, nO = (size_t)items * H * W * Nout;
   DevBuf dA, dB, dO, sA, sB;
   int st = kOk;
+  float wscale = 1.f;
   auto run = [&]() -> int {
     LRPCAP_TRY(dA.ensure(nA * 4));
     LRPCAP_TRY(dB.ensure(nB * 4));
@@ -173,15 +175,23 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
     EpiParams ep;
     ep.mode = EPI_RAW;
     ep.out_f32 = dO.as<float>();
-    if (precision == PREC_BF16X3_TC || precision == 2 || precision == 3 || precision == 4) {
+    if (precision == PREC_BF16X3_TC || precision == 2 || precision == 3 || precision == 4 || precision == 5) {
       // 2: three bf16 planes (the forward pass's arithmetic); 3: two IEEE half planes, promoted (optional forward mode);
       // 4: two-product backward arithmetic (A rounded to ONE fp16 plane x two fp16 weight planes)
-      const int planes = precision == 2 ? 3 : precision == 3 ? kPlanesF16x2 : precision == 4 ? kPlanesH1x2 : 2;
+      // 5: fp16 + fp8 backward arithmetic (fp16 plane + E4M3 [top bits | residual] plane x fp16 + E4M3 [low | high] weights)
+      const int planes = precision == 2 ? 3 : precision == 3 ? kPlanesF16x2 : precision == 4 ? kPlanesH1x2 : precision == 5 ? kPlanesH1F8 : 2;
       const int store_planes = planes == kPlanesH1x2 ? kPlanesF16x2 : planes;
       LRPCAP_TRY(sA.ensure(nA * 2 * 3));
       LRPCAP_TRY(sB.ensure(nB * 2 * 3));
       LRPCAP_TRY(f32_to_split(dA.as<float>(), sA.p, nA, 0, store_planes));
-      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps, store_planes));
+      if (planes == kPlanesH1F8) {   // the byte planes need the weights in the scaled range the encoder uses (Layer::wpow)
+        float m = 0.f;
+        for (size_t i = 0; i < nB; ++i) m = std::fmax(m, std::fabs(h_B[i]));
+        int ex = 0;
+        if (m > 0.f && std::isfinite(m)) std::frexp(m, &ex);
+        wscale = std::ldexp(1.f, 13 - ex);
+      }
+      LRPCAP_TRY(prep_weights(dB.as<float>(), sB.p, C, Nout, WF_TC_FWD, WS_ALL, 0, taps, store_planes, wscale));
       TcConvArgs a;
       a.A = sA.p; a.A_elems = nA; a.n_items = items; a.H = H; a.W = W; a.C = C;
       a.B = sB.p; a.B_elems = nB; a.taps = taps; a.Nout = Nout; a.planes = planes; a.epi = ep;
@@ -194,6 +204,8 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
     }
     LRPCAP_CUDA(cudaDeviceSynchronize());
     LRPCAP_CUDA(cudaMemcpy(h_out, dO.p, nO * 4, cudaMemcpyDeviceToHost));
+    if (wscale != 1.f)
+      for (size_t i = 0; i < nO; ++i) h_out[i] /= wscale;
     return kOk;
   };
   st = run();

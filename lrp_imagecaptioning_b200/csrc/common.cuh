@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -83,6 +84,8 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi2, uint32_t
 //      22 mantissa bits inside the half range (|v| < 65504; lo underflows gradually below |v| ~ 0.1).  Plane code 4. ----
 constexpr int kPlanesF16x2 = 4;
 constexpr int kPlanesH1x2 = 5;    // two-product backward: A one fp16 plane, B two fp16 planes
+constexpr int kPlanesH1F8 = 6;    // fp16 + fp8 backward: A = fp16 plane + E4M3 [top bits | residual] plane, B = fp16 hi plane +
+                                  // E4M3 [low part | high part] plane: one kind::f16 and one double-length kind::f8f6f4 product
 __device__ __forceinline__ void split2h(float a, float b, uint32_t& hi2, uint32_t& lo2) {
   const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
   const __half al = __float2half_rn(a - __half2float(ah)), bl = __float2half_rn(b - __half2float(bh));

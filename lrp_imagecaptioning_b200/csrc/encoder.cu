@@ -74,7 +74,7 @@ int Encoder::create(Encoder** out, const float* const* kernels_hwio, const float
   const Arch& A = kArch[arch];
   LRPCAP_REQUIRE(out && kernels_hwio && biases, kErrInvalidArg, "encoder_create: null argument");
   LRPCAP_REQUIRE(image_hw >= 16 && image_hw % 16 == 0, kErrShape, "encoder_create: image size %d must be a multiple of 16", image_hw);
-  LRPCAP_REQUIRE(precision >= PREC_FP32_SIMT && precision <= PREC_TC_AUTO, kErrInvalidArg,
+  LRPCAP_REQUIRE(precision >= PREC_FP32_SIMT && precision <= PREC_H1F8_TC, kErrInvalidArg,
                  "encoder_create: unknown precision %d", precision);
   Encoder* e = new Encoder();
   e->hw_ = image_hw;
@@ -206,6 +206,11 @@ int Encoder::set_weights_device(const float* const* d_kernels_hwio, const float*
   return kOk;
 }
 
+bool Encoder::getenv_off(const char* name) {
+  const char* v = std::getenv(name);
+  return v && v[0] == '0';
+}
+
 int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
   Layer& L = L_[l];
   if (!L.prepared[fmt][sign]) {
@@ -215,6 +220,8 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
     if (fmt == WF_TC_FWD3) LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, 3));
     else if (fmt == WF_TC_BWDH)
       LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_BWD, sign, s, 9, kPlanesF16x2, std::ldexp(1.f, L.wpow)));
+    else if (fmt == WF_TC_BWDF8)
+      LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_BWD, sign, s, 9, kPlanesH1F8, std::ldexp(1.f, L.wpow)));
     else if (fmt == WF_TC_FWDH)
       LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, kPlanesF16x2, std::ldexp(1.f, L.wpow)));
     else LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, fmt, sign, s));
@@ -226,13 +233,14 @@ int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
 
 int Encoder::get_dual_weights(int l, bool tc, void** out, cudaStream_t s) {
   Layer& L = L_[l];
-  const bool h = tc && two_product();
-  void*& slot = L.dual[tc ? (h ? 2 : 1) : 0];
+  const bool f8 = tc && fp8_mode();
+  const bool h = tc && (two_product() || f8);
+  void*& slot = L.dual[tc ? (f8 ? 3 : h ? 2 : 1) : 0];
   if (!slot) {
     LRPCAP_CUDA(cudaMalloc(&slot, (size_t)9 * L.cin * 2 * L.cout * sizeof(float)));
     const float ws = h ? std::ldexp(1.f, L.wpow) : 1.f;
     LRPCAP_TRY(prep_weights_dual(L.w_hwio, slot, L.cin, L.cout, tc ? WF_TC_BWD : WF_SIMT_BWD, WS_PLUS, rule_.alpha * ws, WS_MINUS,
-                                 -rule_.beta * ws, s, h ? 1 : 0));
+                                 -rule_.beta * ws, s, f8 ? 2 : h ? 1 : 0));
     ++launches_;
   }
   *out = slot;
@@ -249,7 +257,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
   const bool tc = split() && C % 64 == 0 && Nout % 64 == 0;
   if (!tc) LRPCAP_REQUIRE(!split() || l == 0, kErrState, "encoder: layer %d has no tensor-core shape", l);
   if (dual) LRPCAP_TRY(get_dual_weights(l, tc, &B, s));
-  else LRPCAP_TRY(get_weights(l, tc ? (backward ? (two_product() ? WF_TC_BWDH : WF_TC_BWD) : (fwd_planes_ == 3 ? WF_TC_FWD3 : fwd_planes_ == kPlanesF16x2 ? WF_TC_FWDH : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
+  else LRPCAP_TRY(get_weights(l, tc ? (backward ? (fp8_mode() ? WF_TC_BWDF8 : two_product() ? WF_TC_BWDH : WF_TC_BWD) : (fwd_planes_ == 3 ? WF_TC_FWD3 : fwd_planes_ == kPlanesF16x2 ? WF_TC_FWDH : WF_TC_FWD)) : (backward ? WF_SIMT_BWD : WF_SIMT_FWD), sign, &B, s));
   ProfRec rec{};
   if (profile_) {
     LRPCAP_CUDA(cudaEventCreate(&rec.a));
@@ -263,7 +271,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     TcConvArgs a;
     a.A = A; a.A_elems = A_elems; a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = B; a.B_elems = (size_t)9 * L.cin * L.cout * (dual ? 2 : 1); a.taps = 9; a.Nout = Nout;
-    a.planes = backward ? (two_product() ? kPlanesH1x2 : 2) : fwd_planes_;
+    a.planes = backward ? (fp8_mode() ? kPlanesH1F8 : two_product() ? kPlanesH1x2 : 2) : fwd_planes_;
     // backward: tensor-core fp32 accumulation rounds toward zero, which shrinks every output of a chain of n accumulates
     // by ~1.5e-8 n (measured, tools/diag_parity.py trunc: -1.6e-5 at K = 4608, -1e-4 over the 12 layers). A uniform 1e-4
     // scale error is inside the per-pixel tolerance of every rule, but for the same-sign chains of the alpha-beta family
@@ -277,7 +285,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     }
     a.promote_every = backward ? pe : fwd_promote_;
     a.epi = epi;
-    if (backward && two_product()) a.epi.acc_scale = std::ldexp(1.f, -L.wpow);   // the half-plane weights hold 2^wpow * w
+    if (backward && scaled_messages()) a.epi.acc_scale = std::ldexp(1.f, -L.wpow);   // the fp16 weight planes hold 2^wpow * w
     if (!backward && fwd_planes_ == kPlanesF16x2) {
       a.epi.acc_scale = std::ldexp(1.f, -L.wpow);
       a.epi.overflow = d_overflow_;
@@ -287,7 +295,7 @@ int Encoder::conv(int l, bool backward, int sign, const void* A, size_t A_elems,
     SimtConvArgs a;
     a.A = reinterpret_cast<const float*>(A); a.n_items = n_items; a.H = L.hw; a.W = L.hw; a.C = C;
     a.B = reinterpret_cast<const float*>(B); a.taps = 9; a.Nout = Nout;
-    LRPCAP_REQUIRE(!(backward && two_product()), kErrState, "encoder: layer %d backward has no tensor-core shape", l);
+    LRPCAP_REQUIRE(!(backward && scaled_messages()), kErrState, "encoder: layer %d backward has no tensor-core shape", l);
     a.out_planes = split() ? (backward ? 2 : fwd_planes_) : 0;
     a.epi = epi;
     if (!backward && split() && fwd_planes_ == kPlanesF16x2) a.epi.overflow = d_overflow_;
@@ -629,7 +637,7 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
     if (ab) LRPCAP_TRY(get_weights(0, WF_SIMT_BWD, WS_MINUS, &Wb, s));
   }
   const int mul = inh ? 2 : 1;
-  const bool tp = two_product();
+  const bool tp = scaled_messages();
   if (tp) LRPCAP_TRY(scale_.ensure((size_t)(2 * kLayers + 1) * CW * sizeof(unsigned)));
   unsigned* mxb = scale_.as<unsigned>();   // [layers + 1][CW]: row l = stored max of message l, last row = the seed's true max
   int* ktb = reinterpret_cast<int*>(mxb + (size_t)(kLayers + 1) * CW);   // [layers][CW]: log2 scale of message l
@@ -646,7 +654,8 @@ int Encoder::relevance(const int* h_img_index, const float* d_R_head, int n_word
       LRPCAP_CUDA(cudaMemsetAsync(mxb, 0, (size_t)(kLayers + 1) * CW * sizeof(unsigned), s));
       LRPCAP_TRY(seed_message_scaled(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr,
                                      idx, msg_[cur].p, m, fh * fh, 512, guided ? 1 : 0, mxb + (size_t)kLayers * CW,
-                                     mxb + (size_t)(kLayers - 1) * CW, ktb + (size_t)(kLayers - 1) * CW, msg_target_exp_, s));
+                                     mxb + (size_t)(kLayers - 1) * CW, ktb + (size_t)(kLayers - 1) * CW, msg_target_exp_, s,
+                                     fp8_mode() ? 1 : 0));
       ++launches_;
     } else {
       LRPCAP_TRY(seed_message(d_R_head + (size_t)w0 * head_elems, Mseed_.as<float>(), inh ? Mseed2_.as<float>() : nullptr, idx,

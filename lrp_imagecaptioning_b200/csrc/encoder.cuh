@@ -16,7 +16,7 @@
 
 namespace lrpcap {
 
-enum Precision : int { PREC_FP32_SIMT = 0, PREC_BF16X3_TC = 1, PREC_F16X2_TC = 2, PREC_TC_AUTO = 3 };
+enum Precision : int { PREC_FP32_SIMT = 0, PREC_BF16X3_TC = 1, PREC_F16X2_TC = 2, PREC_TC_AUTO = 3, PREC_H1F8_TC = 4 };
 
 enum RuleKind : int {
   RULE_EPSILON = 0,       // LRPEpsilon            (relevance_analyzer.py:531-552)
@@ -107,9 +107,9 @@ class Encoder {
     bool pool_after;
     float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
     float* bias = nullptr;    // device fp32 [cout]
-    void* prepared[7][3] = {};  // [WeightFormat][WeightSign]
+    void* prepared[8][3] = {};  // [WeightFormat][WeightSign]
     int wpow = 0;             // half-plane forward: weights are stored as 2^wpow * w (keeps the low plane out of the subnormals)
-    void* dual[3] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC, half-plane TC} backward layouts
+    void* dual[4] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC, half-plane TC, fp16 + fp8 TC} backward layouts
   };
   int get_weights(int l, int fmt, int sign, void** out, cudaStream_t s);
   int conv(int l, bool backward, int sign, const void* A, size_t A_elems, int n_items, const struct EpiParams& epi,
@@ -125,6 +125,16 @@ class Encoder {
     return precision_ == PREC_F16X2_TC ||
            (precision_ == PREC_TC_AUTO && (rule_.kind == RULE_ALPHA_BETA || rule_.kind == RULE_ZPLUS_FAST));
   }
+  // fp16 + fp8 backward (epilogue.cuh: StoreH1F8): the scaled fp16 message plus an E4M3 plane of [its top bits | its
+  // rounding residual] against the weights' fp16 high plane plus an E4M3 plane of [their low part | their high part]: one
+  // kind::f16 and one double-rate kind::f8f6f4 product = two product-equivalents with ~15 bits. Used on the layers the
+  // generic kernel runs (the wide shallow ones keep their vertical-halo kernel's format); PREC_TC_AUTO picks it for the
+  // mixed-sign rules, whose 1e-3 tolerance the plain two-product mode's 11-bit message does not leave room for.
+  bool fp8_mode() const {
+    return precision_ == PREC_H1F8_TC || (precision_ == PREC_TC_AUTO && !two_product() && !getenv_off("LRPCAP_H1F8"));
+  }
+  static bool getenv_off(const char* name);
+  bool scaled_messages() const { return two_product() || fp8_mode(); }   // fp16 message planes with per-word scales
   // storage planes of forward activations in tensor-core mode (fp32 otherwise). The per-image forward decides ReLU signs
   // and pool arg-max and forms x/stab(z); 16-bit operands there cost 1e-2-level map errors, so its
   // operands carry >= 22 bits: two IEEE half planes (default, 3 MMA products; falls back for good when an activation

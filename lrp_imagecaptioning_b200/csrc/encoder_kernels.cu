@@ -35,6 +35,15 @@ __global__ void prep_weights_kernel(const float* __restrict__ w, float* __restri
   if (sign == WS_MINUS) v = v < 0.f ? v : 0.f;
   if (fmt == WF_SIMT_FWD || fmt == WF_SIMT_BWD) {
     out_f32[idx] = v;
+  } else if (planes == kPlanesH1F8) {    // fp16 high plane [total] + byte plane [total / 64][128] = [e4m3(low part) | e4m3(2^-kResShift * w)]
+    __half* oh = reinterpret_cast<__half*>(out_hi);
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out_hi) + total * 2;
+    v *= scale;
+    const __half h = __float2half_rn(v);
+    oh[idx] = h;
+    const size_t b = (idx >> 6) * 128 + (idx & 63);      // the K axis (innermost, a multiple of 64) in 64-element blocks
+    o8[b] = (uint8_t)__nv_cvt_float_to_fp8(v - __half2float(h), __NV_SATFINITE, __NV_E4M3);
+    o8[b + 64] = (uint8_t)__nv_cvt_float_to_fp8(v * (1.f / (float)(1 << kResShift)), __NV_SATFINITE, __NV_E4M3);
   } else if (planes == kPlanesF16x2) {   // two half planes of scale * w (scale = 2^k keeps the low plane normal)
     __half* oh = reinterpret_cast<__half*>(out_hi);
     v *= scale;
@@ -71,6 +80,14 @@ __global__ void prep_weights_dual_kernel(const float* __restrict__ w, float* __r
   v *= second ? scale_b : scale_a;
   if (fmt == WF_SIMT_BWD) {
     out_f32[idx] = v;
+  } else if (half_planes == 2) {   // fp16 + fp8 layout (see prep_weights_kernel)
+    __half* oh = reinterpret_cast<__half*>(out_hi);
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(out_hi) + total * 2;
+    const __half h = __float2half_rn(v);
+    oh[idx] = h;
+    const size_t b = (idx >> 6) * 128 + (idx & 63);
+    o8[b] = (uint8_t)__nv_cvt_float_to_fp8(v - __half2float(h), __NV_SATFINITE, __NV_E4M3);
+    o8[b + 64] = (uint8_t)__nv_cvt_float_to_fp8(v * (1.f / (float)(1 << kResShift)), __NV_SATFINITE, __NV_E4M3);
   } else if (half_planes) {
     __half* oh = reinterpret_cast<__half*>(out_hi);
     const __half h = __float2half_rn(v);
@@ -353,6 +370,16 @@ __global__ void f32_to_split_kernel(const float* __restrict__ in, __nv_bfloat16*
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   float v = in[idx];
+  if (planes == kPlanesH1F8) {   // debug operand: unscaled value in the fp16 + fp8 message layout
+    __half* oh = reinterpret_cast<__half*>(hi);
+    uint8_t* o8 = reinterpret_cast<uint8_t*>(hi) + n * 2;
+    const __half h = __float2half_rn(v);
+    oh[idx] = h;
+    const size_t b = (idx >> 6) * 128 + (idx & 63);
+    o8[b] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h), __NV_SATFINITE, __NV_E4M3);
+    o8[b + 64] = (uint8_t)__nv_cvt_float_to_fp8((v - __half2float(h)) * (float)(1 << kResShift), __NV_SATFINITE, __NV_E4M3);
+    return;
+  }
   if (planes == kPlanesF16x2) {
     __half* oh = reinterpret_cast<__half*>(hi);
     const __half h = __float2half_rn(v);
@@ -430,7 +457,8 @@ int seed_message(const float* R, const float* M, const float* M2, const int* img
 }
 
 int seed_message_scaled(const float* R, const float* M, const float* M2, const int* img_index, void* msg, int items, int pix,
-                        int C, int relu, unsigned* mx_true, unsigned* mx_out, int* kt_out, int target_exp, cudaStream_t s) {
+                        int C, int relu, unsigned* mx_true, unsigned* mx_out, int* kt_out, int target_exp, cudaStream_t s,
+                        int fp8_planes) {
   const size_t per_item = (size_t)pix * C;
   LRPCAP_REQUIRE(per_item % 8 == 0 && C % 8 == 0, kErrShape, "seed_message_scaled: item size must be a multiple of 8");
   int bpi = (int)((per_item / 4 + 255) / 256);
@@ -438,8 +466,13 @@ int seed_message_scaled(const float* R, const float* M, const float* M2, const i
   seed_max_kernel<<<dim3((unsigned)bpi, (unsigned)items), 256, 0, s>>>(R, M, M2, img_index, mx_true, per_item, relu);
   LRPCAP_CUDA(cudaGetLastError());
   const size_t total8 = (size_t)items * per_item / 8;
-  seed_kernel<StoreH1><<<grid_for(total8, 256), 256, 0, s>>>(R, M, M2, img_index, msg, 0, items, per_item, C, relu, mx_true,
-                                                             mx_out, kt_out, target_exp);
+  const size_t msg_elems = (size_t)items * per_item * (M2 ? 2 : 1);
+  if (fp8_planes)
+    seed_kernel<StoreH1F8><<<grid_for(total8, 256), 256, 0, s>>>(R, M, M2, img_index, msg, msg_elems, items, per_item, C, relu,
+                                                                 mx_true, mx_out, kt_out, target_exp);
+  else
+    seed_kernel<StoreH1><<<grid_for(total8, 256), 256, 0, s>>>(R, M, M2, img_index, msg, 0, items, per_item, C, relu, mx_true,
+                                                               mx_out, kt_out, target_exp);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }

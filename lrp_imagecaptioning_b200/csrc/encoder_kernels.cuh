@@ -12,6 +12,7 @@ enum WeightFormat : int {
   WF_TC_FWD3 = 4,   // as WF_TC_FWD with three bf16 planes (fp32-exact forward operands)
   WF_TC_FWDH = 5,   // as WF_TC_FWD with two IEEE half planes of 2^k * w (Layer::wpow): the default forward operands
   WF_TC_BWDH = 6,   // as WF_TC_BWD with two IEEE half planes of 2^k * w: B operand of the two-product backward
+  WF_TC_BWDF8 = 7,  // as WF_TC_BWD in the fp16 + fp8 layout (high fp16 plane + E4M3 [low | high] byte plane) of 2^k * w
 };
 enum WeightSign : int { WS_ALL = 0, WS_PLUS = 1, WS_MINUS = 2 };
 
@@ -24,7 +25,8 @@ int prep_weights(const float* w_hwio, void* out, int cin, int cout, int fmt, int
 // Backward weights of the alpha-beta rule with beta != 0, stacked along K (2*cout input channels):
 //   k <  cout : scale_a * sign_a(W)      k >= cout : scale_b * sign_b(W)
 // fmt: WF_SIMT_BWD -> fp32 [tap'][2*cout][cin]; WF_TC_BWD -> split-bf16 [tap'][cin][2*cout].
-// half_planes != 0 (WF_TC_BWD only): two IEEE half planes instead of two bf16 planes (fold 2^wpow into the scales).
+// half_planes (WF_TC_BWD only): 1 = two IEEE half planes instead of two bf16 planes (fold 2^wpow into the scales);
+// 2 = the fp16 + fp8 layout.
 int prep_weights_dual(const float* w_hwio, void* out, int cin, int cout, int fmt, int sign_a, float scale_a, int sign_b,
                       float scale_b, cudaStream_t s, int half_planes = 0);
 
@@ -44,7 +46,8 @@ int seed_message(const float* R, const float* M, const float* M2, const int* img
 // Two-product backward: the seed as ONE fp16 plane scaled by a power of two per item. mx_true [items] must be zero on
 // entry (receives max |value| per item); mx_out [items] receives the stored plane's maximum, kt_out [items] log2(scale).
 int seed_message_scaled(const float* R, const float* M, const float* M2, const int* img_index, void* msg, int items, int pix,
-                        int C, int relu, unsigned* mx_true, unsigned* mx_out, int* kt_out, int target_exp, cudaStream_t s);
+                        int C, int relu, unsigned* mx_true, unsigned* mx_out, int* kt_out, int target_exp, cudaStream_t s,
+                        int fp8_planes = 0);   // fp8_planes: the fp16 + fp8 layout (epilogue.cuh: StoreH1F8) instead of one fp16 plane
 
 // Last transposed conv (64 -> 3 channels) + input re-weighting:
 //   c_a = Wa^T (*) s,  c_b = Wb^T (*) s (only if Wb != null)

@@ -238,6 +238,55 @@ struct StoreH1 {
   }
 };
 
+// fp16 + fp8 message (kPlanesH1F8): the scaled value v is stored as a16 = half(v) in the fp16 plane, and in the byte plane
+// (at base + 2 * elems bytes, 128 bytes per 64-channel block) as [e4m3(a16) (64 B) | e4m3((v - a16) * 2^kResShift) (64 B)]:
+// the top four bits of the message (pairs with the weights' low part) and its rounding residual (pairs with the weights'
+// high part).  a16 * w_hi runs as one kind::f16 product, [a8 | r8] * [w_lo8 ; w_8] as one double-length kind::f8f6f4
+// product at twice the rate: two product-equivalents for ~15 bits (tools/sim_h1f8.py: 1e-5 per layer vs 2e-4 of the plain
+// two-product mode and 4e-6 of the three-product mode).
+constexpr int kResShift = 13;
+struct StoreH1F8 {
+  static constexpr bool kScaled = true;
+  template <int NV>
+  static __device__ __forceinline__ void store(void* base, size_t elems, size_t off, const float (&v)[NV]) {
+    static_assert(NV == 16 || NV == 8, "fp16 + fp8 storage moves 8 or 16 elements per vector");
+    __half* p16 = reinterpret_cast<__half*>(base) + off;
+    uint8_t* p8 = reinterpret_cast<uint8_t*>(base) + elems * 2 + (off >> 6) * 128 + (off & 63);
+    uint32_t u[NV / 2];
+    uint16_t a8[NV / 2], r8[NV / 2];
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+      const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+      const __half2 h = __floats2half2_rn(a, b);
+      u[i] = *reinterpret_cast<const uint32_t*>(&h);
+      const float2 hf = __half22float2(h);
+      a8[i] = __nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E4M3);
+      r8[i] = __nv_cvt_float2_to_fp8x2(make_float2((a - hf.x) * (float)(1 << kResShift), (b - hf.y) * (float)(1 << kResShift)),
+                                       __NV_SATFINITE, __NV_E4M3);
+    }
+    if constexpr (NV == 16) {
+      uint32_t w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = u[i];
+      stg256(p16, w);
+      *reinterpret_cast<uint4*>(p8) = make_uint4(a8[0] | ((uint32_t)a8[1] << 16), a8[2] | ((uint32_t)a8[3] << 16),
+                                                 a8[4] | ((uint32_t)a8[5] << 16), a8[6] | ((uint32_t)a8[7] << 16));
+      *reinterpret_cast<uint4*>(p8 + 64) = make_uint4(r8[0] | ((uint32_t)r8[1] << 16), r8[2] | ((uint32_t)r8[3] << 16),
+                                                      r8[4] | ((uint32_t)r8[5] << 16), r8[6] | ((uint32_t)r8[7] << 16));
+    } else {
+      *reinterpret_cast<uint4*>(p16) = make_uint4(u[0], u[1], u[2], u[3]);
+      *reinterpret_cast<uint2*>(p8) = make_uint2(a8[0] | ((uint32_t)a8[1] << 16), a8[2] | ((uint32_t)a8[3] << 16));
+      *reinterpret_cast<uint2*>(p8 + 64) = make_uint2(r8[0] | ((uint32_t)r8[1] << 16), r8[2] | ((uint32_t)r8[3] << 16));
+    }
+  }
+  template <int NV>
+  static __device__ __forceinline__ void load(const void* base, size_t, size_t off, float (&v)[NV]) {
+    const __half* p = reinterpret_cast<const __half*>(base) + off;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __half2float(p[i]);
+  }
+};
+
 struct StoreSplit3 {
   static constexpr bool kScaled = false;
   template <int NV>

@@ -77,16 +77,20 @@ __device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN)
 // A1: two-product mode. A is ONE fp16 plane (the scaled relevance message), B two fp16 planes [hi ; lo] that sit back to
 // back in shared memory. BN <= 128: one MMA with N = 2 BN per K slice (accumulator columns [0, BN) = A*hi, [BN, 2 BN) =
 // A*lo, summed by the epilogue); BN = 256: two N = 256 MMAs into the same accumulator.
-template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false>
+// F8: fp16 + fp8 mode (epilogue.cuh: StoreH1F8). Plane 0 of A and B are fp16 (message, high weight part), plane 1 are E4M3
+// byte planes of the same tile size (128 bytes per row = [top bits | residual] of the message, [low part | high part] of
+// the weights): per k-step four kind::f16 MMAs (K = 16) and four kind::f8f6f4 MMAs (K = 32) into one accumulator.
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false, bool F8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
   static_assert(!A1 || (NS == 2 && F16), "two-product mode: one fp16 A plane x two fp16 B planes");
+  static_assert(!F8 || (NS == 2 && F16 && !A1), "fp16 + fp8 mode: one fp16 and one byte plane per operand");
   constexpr int AP = A1 ? 1 : NS;
   constexpr bool BCAT = A1 && BN <= 128;
   constexpr int ACC = BCAT ? 2 * BN : BN;             // TMEM columns per accumulator buffer
   using C = Cfg<BN, NS, AP>;
-  using ST = typename std::conditional<A1, StoreH1, typename std::conditional<NS == 3, StoreSplit3,
-                                       typename std::conditional<F16, StoreSplitH, StoreSplit>::type>::type>::type;
+  using ST = typename std::conditional<F8, StoreH1F8, typename std::conditional<A1, StoreH1, typename std::conditional<NS == 3, StoreSplit3,
+                                       typename std::conditional<F16, StoreSplitH, StoreSplit>::type>::type>::type>::type;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -143,12 +147,13 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
             dx = tap % 3 - 1;
           }
 #pragma unroll
-          for (int p = 0; p < AP; ++p)
-            tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], cb * kBlockK, tc.x0 + dx, tc.y0 + dy, tc.item);
+          for (int p = 0; p < AP; ++p)   // byte planes (F8, plane 1) count their innermost coordinate in bytes: 128 per block
+            tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], cb * ((F8 && p == 1) ? 128 : kBlockK), tc.x0 + dx,
+                        tc.y0 + dy, tc.item);
 #pragma unroll
           for (int p = 0; p < NS; ++p)
-            tma_load_2d(&tm.b[p], st + AP * kATileBytes + p * C::kBTileBytes, &full_bar[s], cb * kBlockK,
-                        tap * g.Nout + tc.n0);
+            tma_load_2d(&tm.b[p], st + AP * kATileBytes + p * C::kBTileBytes, &full_bar[s],
+                        cb * ((F8 && p == 1) ? 128 : kBlockK), tap * g.Nout + tc.n0);
         }
       }
     }
@@ -182,7 +187,10 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
             for (int k = 0; k < kBlockK / 16; ++k) {
               const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
               const uint32_t first = (kk != kk0 || k != 0) ? 1u : 0u;   // a fresh accumulator starts every group
-              if (A1) {
+              if (F8) {   // fp16 slice k, then the byte planes' 32-byte slice k (together: every product of the k-step once)
+                umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, first);
+                umma_f8(tmem_d, da[1] + adv, db[1] + adv, idesc, 1u);
+              } else if (A1) {
                 if (BCAT) {
                   umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc_cat, first);   // [A*hi | A*lo]
                 } else {
@@ -376,6 +384,34 @@ int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, in
   return kOk;
 }
 
+int make_map_act_u8(CUtensorMap* m, const void* base, int n_items, int H, int W, int Cb, int TW, int TH) {
+  EncodeTiledFn fn = get_encode_fn();
+  LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)Cb, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_items};
+  cuuint64_t strides[3] = {(cuuint64_t)Cb, (cuuint64_t)W * Cb, (cuuint64_t)H * W * Cb};
+  cuuint32_t box[4] = {128, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LRPCAP_REQUIRE(r == CUDA_SUCCESS, kErrCuda, "cuTensorMapEncodeTiled(byte activation) failed: %d", (int)r);
+  return kOk;
+}
+
+int make_map_w_u8(CUtensorMap* m, const void* base, int rows, int Cb, int BN) {
+  EncodeTiledFn fn = get_encode_fn();
+  LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)Cb, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Cb};
+  cuuint32_t box[2] = {128, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LRPCAP_REQUIRE(r == CUDA_SUCCESS, kErrCuda, "cuTensorMapEncodeTiled(byte weights) failed: %d", (int)r);
+  return kOk;
+}
+
 int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, int W, int box_w, int box_h, int box_c) {
   EncodeTiledFn fn = get_encode_fn();
   LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
@@ -407,16 +443,16 @@ int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int BN) {
 
 namespace {
 
-template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false>
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false, bool F8 = false>
 int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   using C = Cfg<BN, NS, A1 ? 1 : NS>;
   static int smem_state[kMaxDevices] = {};
-  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1>, C::kSmemBytes, smem_state));
+  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1, F8>, C::kSmemBytes, smem_state));
   const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv: %lld tiles out of range", tiles);
   const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
-  tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
+  tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1, F8><<<grid, kThreads, C::kSmemBytes, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -437,6 +473,16 @@ int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaS
 
 template <int BN>
 int launch_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  if (planes == kPlanesH1F8) {   // fp16 + fp8 backward
+    if (mode == EPI_BWD)
+      return g.group > 0 ? launch_t<BN, EPI_BWD, 2, true, true, false, true>(tm, g, e, stream)
+                         : launch_t<BN, EPI_BWD, 2, false, true, false, true>(tm, g, e, stream);
+    if (mode == EPI_RAW)
+      return g.group > 0 ? launch_t<BN, EPI_RAW, 2, true, true, false, true>(tm, g, e, stream)
+                         : launch_t<BN, EPI_RAW, 2, false, true, false, true>(tm, g, e, stream);
+    set_last_error("tc_conv: the fp16 + fp8 mode supports backward / raw epilogues only (mode %d)", mode);
+    return kErrUnsupported;
+  }
   if (planes == kPlanesH1x2) {   // two-product backward: one fp16 message plane x two fp16 weight planes
     if (mode == EPI_BWD)
       return g.group > 0 ? launch_t<BN, EPI_BWD, 2, true, true, true>(tm, g, e, stream)
@@ -497,12 +543,13 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   LRPCAP_REQUIRE(a.Nout > 0 && a.Nout % 64 == 0, kErrShape, "tc_conv: Nout=%d must be a positive multiple of 64", a.Nout);
   LRPCAP_REQUIRE(a.taps == 9 || a.taps == 1, kErrShape, "tc_conv: taps must be 1 or 9");
   LRPCAP_REQUIRE(a.n_items > 0 && a.H > 0 && a.W > 0, kErrShape, "tc_conv: empty problem");
-  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3 || a.planes == kPlanesF16x2 || a.planes == kPlanesH1x2, kErrInvalidArg,
-                 "tc_conv: planes must be 2, 3, 4 (two half planes) or 5 (two-product backward)");
+  LRPCAP_REQUIRE(a.planes == 2 || a.planes == 3 || a.planes == kPlanesF16x2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8,
+                 kErrInvalidArg, "tc_conv: planes must be 2, 3, 4 (two half planes), 5 (two-product) or 6 (fp16 + fp8)");
   // N = 256 for the backward modes (half the shared-memory operand bytes per MMA flop of N = 128). The forward modes
   // (3 planes / two half planes, promoted every k-step) stay at N <= 128: with N = 256 the per-k-step accumulator drain
   // (256 columns) outweighed the operand saving (measured: forward 15.0 -> 18.0 ms per 64 images).
-  const int BN = ((a.planes == 2 || a.planes == kPlanesH1x2) && a.Nout % 256 == 0) ? 256 : (a.Nout % 128 == 0 ? 128 : 64);
+  const int BN = ((a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) && a.Nout % 256 == 0) ? 256
+                                                                                        : (a.Nout % 128 == 0 ? 128 : 64);
   if (tc_conv_vh_eligible(a, BN)) return tc_conv_vh_launch(a, BN, stream);   // wide shallow layers: tc_conv_vh.cu
   Geom g;
   g.H = a.H;
@@ -515,14 +562,24 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
-  g.group = (a.planes != 2 && a.planes != kPlanesH1x2) ? (a.promote_every > 0 ? a.promote_every : 1)
-                                                        : (a.promote_every > 0 ? a.promote_every : 0);
+  g.group = (a.planes != 2 && a.planes != kPlanesH1x2 && a.planes != kPlanesH1F8) ? (a.promote_every > 0 ? a.promote_every : 1)
+                                                                                   : (a.promote_every > 0 ? a.promote_every : 0);
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
   Maps tm;
   const int n_planes = a.planes == 3 ? 3 : 2;
   const int a_planes = a.planes == kPlanesH1x2 ? 1 : n_planes;
+  if (a.planes == kPlanesH1F8) {   // plane 0: fp16 [.., C]; plane 1: bytes [.., 2 C] right behind it (both 2 B per element)
+    const uint8_t* A8 = reinterpret_cast<const uint8_t*>(A0) + a.A_elems * 2;
+    const uint8_t* B8 = reinterpret_cast<const uint8_t*>(B0) + a.B_elems * 2;
+    LRPCAP_TRY(make_map_act(&tm.a[0], A0, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
+    LRPCAP_TRY(make_map_act_u8(&tm.a[1], A8, a.n_items, a.H, a.W, 2 * a.C, g.TW, g.TH));
+    LRPCAP_TRY(make_map_w(&tm.b[0], B0, a.taps * a.Nout, a.C, BN));
+    LRPCAP_TRY(make_map_w_u8(&tm.b[1], B8, a.taps * a.Nout, 2 * a.C, BN));
+    tm.a[2] = tm.a[0];
+    tm.b[2] = tm.b[0];
+  } else
   for (int pl = 0; pl < 3; ++pl) {
     const int q = pl < n_planes ? pl : 0;   // unused third slot aliases plane 0
     LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(q < a_planes ? q : 0) * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));

@@ -30,7 +30,9 @@ namespace {
 using namespace tcptx;
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kEpiWarp0 = 4;                            // warps 0..3: producer warpgroup (TMA thread, MMA thread, two idle warps)
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
+constexpr int kProducerRegs = 96, kEpilogueRegs = 200;  // setmaxnreg: the epilogue warpgroups take the producers' registers
 constexpr int kTW = 16, kTH = 16, kTM = 2;              // CTA tile: 16 x 16 pixels = kTM MMA tiles of 8 (wide) x 16
 constexpr int kMW = kTW / kTM;                          // MMA tile width: 8 pixels = one 1024 B swizzle group per row
 constexpr int kPatchRows = kTH + 2;                     // 18 pixel rows of 8 pixels
@@ -65,13 +67,17 @@ __device__ __forceinline__ VhTile vh_tile(const VhGeom& g, int tile, int BN) {
 
 // A1: two-product mode (tc_conv.cu): ONE fp16 message plane x [B_hi ; B_lo]. NCAT: a single N = 128 MMA per K slice;
 // BN = 128: two N = 128 MMAs into the same accumulator. The patch slots are half as large, so the ring is deeper.
-template <int BN, int MODE, bool NCAT, bool A1 = false>
+// F8: fp16 + fp8 mode (tc_conv.cu, epilogue.cuh: StoreH1F8): plane 0 of the patches and weight taps is fp16, plane 1 the
+// E4M3 byte plane (same tile sizes: 128 bytes per pixel and 64-channel block); per K slice one kind::f16 and one
+// kind::f8f6f4 MMA.
+template <int BN, int MODE, bool NCAT, bool A1 = false, bool F8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDev e, const int total_tiles) {
+  static_assert(!F8 || (!NCAT && !A1), "fp16 + fp8 mode: plain two-plane staging");
   constexpr int AP = A1 ? 1 : 2;
   constexpr int kASlot = AP * kAPlane;
   constexpr int kNA = A1 ? 6 : 4;
-  using ST = typename std::conditional<A1, StoreH1, StoreSplit>::type;
+  using ST = typename std::conditional<F8, StoreH1F8, typename std::conditional<A1, StoreH1, StoreSplit>::type>::type;
   constexpr int kBPlane = BN * 128;
   constexpr int kBSlot = 2 * kBPlane;
   constexpr int ACC = NCAT ? 2 * BN : BN;               // accumulator columns per MMA tile
@@ -121,6 +127,7 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer: patches and weight taps in the order the MMA thread consumes them ----------------
@@ -135,9 +142,9 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
               mbar_expect_tx(&afull[sa], (uint32_t)kASlot);
               uint8_t* ap = a_ring + sa * kASlot;
 #pragma unroll
-              for (int p = 0; p < AP; ++p)
-                tma_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], cb * kBlockK, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1,
-                            tc.item);
+              for (int p = 0; p < AP; ++p)   // byte planes (F8, plane 1) count the innermost coordinate in bytes
+                tma_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], cb * ((F8 && p == 1) ? 128 : kBlockK),
+                            tc.x0 + kMW * j + dxi - 1, tc.y0 - 1, tc.item);
               if (j == (JINNER ? kTM - 1 : 0)) {   // the three weight taps of this dx, used by both MMA tiles
                 for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
                   const uint32_t sb = ib % NB;
@@ -147,7 +154,8 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
                   const int tap = dyi * 3 + dxi;
 #pragma unroll
                   for (int p = 0; p < 2; ++p)
-                    tma_load_2d(&tm.b[p], bp + p * kBPlane, &bfull[sb], cb * kBlockK, tap * g.Nout + tc.n0);
+                    tma_load_2d(&tm.b[p], bp + p * kBPlane, &bfull[sb], cb * ((F8 && p == 1) ? 128 : kBlockK),
+                                tap * g.Nout + tc.n0);
                 }
               }
             }
@@ -158,8 +166,8 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc_n = make_idesc(128, BN, A1);
-      constexpr uint32_t idesc_cat = make_idesc(128, NCAT ? 2 * BN : BN, A1);
+      constexpr uint32_t idesc_n = make_idesc(128, BN, A1 || F8);
+      constexpr uint32_t idesc_cat = make_idesc(128, NCAT ? 2 * BN : BN, A1 || F8);
       uint32_t ia = 0, ib = 0, tl = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
         const uint32_t buf = tl & 1u;
@@ -186,7 +194,10 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
                 const uint64_t adv = (uint64_t)(k * 2);
                 const uint32_t acc_k = (accum != 0u || dyi != 0 || k != 0) ? 1u : 0u;   // the tile's first MMA overwrites
                 const uint32_t d = tmem_d + j * ACC;
-                if (A1) {
+                if (F8) {
+                  umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_n, acc_k);     // fp16 message x fp16 high weights
+                  umma_f8(d, da_lo[j] + adv, db_lo + adv, idesc_n, 1u);          // [top bits | residual] x [low | high], E4M3
+                } else if (A1) {
                   if (NCAT) {
                     umma_bf16(d, da_hi[j] + adv, db_hi + adv, idesc_cat, acc_k);   // [A*hi | A*lo]
                   } else {
@@ -234,10 +245,11 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
         umma_commit(&tfull[buf]);
       }
     }
-  } else {
-    // ---------------- epilogue: warp w owns TMEM lanes [32 (w % 4), +32) of MMA tile (w - 2) / 4 ----------------
+  } else if (warp >= kEpiWarp0) {
+    // ---------------- epilogue: warp w owns TMEM lanes [32 (w % 4), +32) of MMA tile (w - 4) / 4 ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpilogueRegs));
     const int q = warp & 3;
-    const int j = (warp - 2) >> 2;
+    const int j = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
     const int ty = r >> 3, tx = kMW * j + (r & 7);
     uint32_t tl = 0;
@@ -293,7 +305,7 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-template <int BN, int MODE, bool NCAT, bool A1>
+template <int BN, int MODE, bool NCAT, bool A1, bool F8 = false>
 int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) {
   constexpr int kBSlot = 2 * BN * 128;
   constexpr int kASlot = (A1 ? 1 : 2) * kAPlane;
@@ -304,21 +316,21 @@ int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) 
   g.NB = nb;
   const int smem = kNA * kASlot + nb * kBSlot + 1024 + 512;
   static int smem_state[kMaxDevices] = {};
-  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_vh_kernel<BN, MODE, NCAT, A1>, smem, smem_state));
+  LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_vh_kernel<BN, MODE, NCAT, A1, F8>, smem, smem_state));
   const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv_vh: %lld tiles out of range", tiles);
   const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-  tc_conv_vh_kernel<BN, MODE, NCAT, A1><<<grid, kThreads, smem, stream>>>(tm, g, e, (int)tiles);
+  tc_conv_vh_kernel<BN, MODE, NCAT, A1, F8><<<grid, kThreads, smem, stream>>>(tm, g, e, (int)tiles);
   LRPCAP_CUDA(cudaGetLastError());
   return kOk;
 }
 
-template <int BN, bool NCAT, bool A1>
+template <int BN, bool NCAT, bool A1, bool F8 = false>
 int launch_vh_mode(int mode, const VhMaps& tm, const VhGeom& g, const EpiDev& e, cudaStream_t stream) {
   switch (mode) {
-    case EPI_BWD: return launch_vh<BN, EPI_BWD, NCAT, A1>(tm, g, e, stream);
-    case EPI_RAW: return launch_vh<BN, EPI_RAW, NCAT, A1>(tm, g, e, stream);
+    case EPI_BWD: return launch_vh<BN, EPI_BWD, NCAT, A1, F8>(tm, g, e, stream);
+    case EPI_RAW: return launch_vh<BN, EPI_RAW, NCAT, A1, F8>(tm, g, e, stream);
   }
   set_last_error("tc_conv_vh: epilogue mode %d not instantiated", mode);
   return kErrUnsupported;
@@ -336,8 +348,11 @@ bool vh_enabled() {
 }  // namespace
 
 bool tc_conv_vh_eligible(const TcConvArgs& a, int BN) {
-  return vh_enabled() && a.taps == 9 && (a.planes == 2 || a.planes == kPlanesH1x2) && a.promote_every <= 0 && (BN == 64 || BN == 128) &&
-         a.W % kTW == 0 && a.H % kTH == 0 && (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW);
+  // fp16 + fp8 mode, 64 output channels from more than 64 input channels (128 -> 64 @ 112^2): the generic kernel is faster
+  // (measured 2.28 vs 2.95 ms per 320 words; without the [hi ; lo] N = 128 trick the N = 64 MMAs of this kernel starve)
+  if (a.planes == kPlanesH1F8 && BN == 64 && a.C != 64) return false;
+  return vh_enabled() && a.taps == 9 && (a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) && a.promote_every <= 0 &&
+         (BN == 64 || BN == 128) && a.W % kTW == 0 && a.H % kTH == 0 && (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW);
 }
 
 int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream) {
@@ -355,13 +370,24 @@ int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream) {
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
   VhMaps tm;
-  const bool a1 = a.planes == kPlanesH1x2;
+  const bool a1 = a.planes == kPlanesH1x2, f8 = a.planes == kPlanesH1F8;
+  if (f8) {   // plane 0: fp16 [.., C]; plane 1: bytes [.., 2 C] right behind it
+    LRPCAP_TRY(make_map_act(&tm.a[0], A0, a.n_items, a.H, a.W, a.C, kMW, kPatchRows));
+    LRPCAP_TRY(make_map_act_u8(&tm.a[1], reinterpret_cast<const uint8_t*>(A0) + a.A_elems * 2, a.n_items, a.H, a.W, 2 * a.C, kMW,
+                               kPatchRows));
+    LRPCAP_TRY(make_map_w(&tm.b[0], B0, a.taps * a.Nout, a.C, BN));
+    LRPCAP_TRY(make_map_w_u8(&tm.b[1], reinterpret_cast<const uint8_t*>(B0) + a.B_elems * 2, a.taps * a.Nout, 2 * a.C, BN));
+  } else
   for (int pl = 0; pl < 2; ++pl) {
     LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(a1 ? 0 : pl) * a.A_elems, a.n_items, a.H, a.W, a.C, kMW, kPatchRows));
     LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)pl * a.B_elems, a.taps * a.Nout, a.C, BN));
   }
   EpiDev e;
   LRPCAP_TRY(make_epi_dev(a.epi, &e));
+  if (f8) {
+    if (BN == 64) return launch_vh_mode<64, false, false, true>(a.epi.mode, tm, g, e, stream);
+    return launch_vh_mode<128, false, false, true>(a.epi.mode, tm, g, e, stream);
+  }
   if (a1) {
     if (BN == 64) return launch_vh_mode<64, true, true>(a.epi.mode, tm, g, e, stream);
     return launch_vh_mode<128, false, true>(a.epi.mode, tm, g, e, stream);

@@ -93,6 +93,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 with both operands E4M3 (format code 0 = the descriptor make_idesc(M, N, true) builds): K = 32 bytes per
+// instruction, twice the MAC rate of kind::f16, fp32 accumulation into the same TMEM accumulator.
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -176,6 +187,9 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, fl
 // 128B-swizzled, OOB zero-filled.  Weights: bf16 [rows, C] read as boxes {64 ch, box_rows}.
 int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int box_w, int box_h);
 int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int box_rows);
+// Byte tensors (E4M3 planes of the fp16 + fp8 mode): rows of `Cb` bytes, boxes of 128 bytes along the row.
+int make_map_act_u8(CUtensorMap* m, const void* base, int n_items, int H, int W, int Cb, int box_w, int box_h);
+int make_map_w_u8(CUtensorMap* m, const void* base, int rows, int Cb, int box_rows);
 // Channel-planar fp32 message [n_planes][H][W] (EpiParams::out_planar_f32) read as boxes {box_w, box_h, box_c}, OOB zero-filled.
 int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, int W, int box_w, int box_h, int box_c);
 

@@ -46,7 +46,7 @@ class ImageModel(object):
                         for k, b in weights]
         self.image_hw = int(image_hw)
         self.precision = {"fp32": _lib.PREC_FP32_SIMT, "bf16x3": _lib.PREC_BF16X3_TC, "f16x2": _lib.PREC_F16X2_TC,
-                          "tc": _lib.PREC_TC_AUTO}[precision]
+                          "tc": _lib.PREC_TC_AUTO, "h1f8": _lib.PREC_H1F8_TC}[precision]
         self.device = torch.device(device)
         self._h = None
         self._state = None   # (rule key, n_images) of the resident forward state

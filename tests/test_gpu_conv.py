@@ -30,10 +30,10 @@ GENERIC = [(1, 8, 16, 64, 64, 1), (1, 14, 14, 128, 256, 9), (3, 28, 28, 256, 256
            (1, 4, 4, 64, 128, 9), (1, 2, 2, 512, 512, 9), (5, 7, 7, 64, 64, 1), (1, 8, 16, 64, 64, 9)]
 VERTICAL_HALO = [(2, 16, 16, 64, 64, 9), (1, 16, 32, 128, 128, 9), (2, 32, 32, 64, 64, 9), (1, 32, 48, 128, 64, 9),
                  (3, 48, 32, 256, 128, 9), (150, 16, 16, 64, 64, 9), (1, 112, 112, 128, 64, 9)]
-TOL = {_lib.PREC_FP32_SIMT: 2e-6, _lib.PREC_BF16X3_TC: 3e-5, 2: 2e-6, 3: 2e-6, 4: 3e-5}
+TOL = {_lib.PREC_FP32_SIMT: 2e-6, _lib.PREC_BF16X3_TC: 3e-5, 2: 2e-6, 3: 2e-6, 4: 3e-5, 5: 1e-4}
 
 
-@pytest.mark.parametrize("prec", [_lib.PREC_FP32_SIMT, _lib.PREC_BF16X3_TC, 2, 3, 4], ids=["simt", "tc", "tc3", "f16x2", "h1x2"])
+@pytest.mark.parametrize("prec", [_lib.PREC_FP32_SIMT, _lib.PREC_BF16X3_TC, 2, 3, 4, 5], ids=["simt", "tc", "tc3", "f16x2", "h1x2", "h1f8"])
 @pytest.mark.parametrize("shape", GENERIC + VERTICAL_HALO, ids=lambda s: "x".join(map(str, s)))
 def test_conv_matches_float64(prec, shape):
     items, H, W, C, Nout, taps = shape

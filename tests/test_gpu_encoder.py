@@ -127,7 +127,7 @@ def test_features_match_oracle(hw, precision):
     assert_parity(got, ER.features(x, W), "features hw=%d %s" % (hw, precision), rel_tol=1e-4, sum_tol=None)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "tc"])
 @pytest.mark.parametrize("rule", sorted(RULES))
 @pytest.mark.parametrize("hw", [32, 64])
 def test_relevance_matches_oracle_small(hw, rule, precision):
@@ -150,7 +150,7 @@ def test_relevance_matches_oracle_small(hw, rule, precision):
     _assert_pinned(got, ref_p, ref, flips, "%s hw=%d %s" % (rule, hw, precision), rule, head=R, hw=hw, precision=precision)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16x2"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16x2", "tc"])
 @pytest.mark.parametrize("rule", ["eps", "presetA", "a2b1", "gradient"])
 def test_vgg19_relevance_matches_oracle(rule, precision):
     """The reference's other VGG encoder (models/model.py:419-421: `img_encoder='vgg19'`, cut at block5_conv4): 16 convs,
@@ -160,7 +160,7 @@ def test_vgg19_relevance_matches_oracle(rule, precision):
     from lrp_imagecaptioning_b200.analyzers import create_analyzer
     from oracle import encoder_ref as ER
     if precision == "f16x2" and rule in ("eps", "gradient"):
-        pytest.skip("the two-product backward is offered for the same-sign rules (DESIGN.md section 5)")
+        pytest.skip("the plain two-product backward is offered for the same-sign rules only (DESIGN.md section 2.3)")
     n, hw = 3, 64
     idx = np.arange(n, dtype=np.int32)
     W = synth.vgg19_weights(0, bias_std=0.01)
@@ -229,7 +229,10 @@ def test_chunking_is_invisible():
 
 @pytest.mark.parametrize("rule,precision", [("presetA", "bf16x3"), ("eps", "bf16x3"), ("presetA", "fp32"), ("eps", "fp32"),
                                             ("a2b1", "bf16x3"), ("zplus", "bf16x3"), ("z", "bf16x3"), ("gradient", "bf16x3"),
-                                            ("guided", "bf16x3"), ("ixg", "bf16x3")])
+                                            ("guided", "bf16x3"), ("ixg", "bf16x3"),
+                                            # the default arithmetic ("tc": fp16 two-product for the same-sign rules, fp16 + fp8 for the rest)
+                                            ("presetA", "tc"), ("a2b1", "tc"), ("zplus", "tc"), ("eps", "tc"), ("z", "tc"),
+                                            ("gradient", "tc"), ("guided", "tc"), ("ixg", "tc"), ("eps", "h1f8"), ("presetA", "h1f8")])
 def test_relevance_matches_oracle_224(rule, precision):
     """BASELINE.json full image size, three images: every image within tolerance of the oracle pinned to the CUDA
     forward's arg-max routes (and ReLU masks for the mask rules), identical top-10 cells, sums to 1e-4."""

@@ -4,6 +4,7 @@
 #include "encoder_kernels.cuh"
 #include "tc_conv.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace lrpcap {
@@ -195,6 +196,7 @@ int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, 
       TcConvArgs a;
       a.A = sA.p; a.A_elems = nA; a.n_items = items; a.H = H; a.W = W; a.C = C;
       a.B = sB.p; a.B_elems = nB; a.taps = taps; a.Nout = Nout; a.planes = planes; a.epi = ep;
+      if (const char* pe = std::getenv("LRPCAP_DEBUG_CONV_PROMOTE")) a.promote_every = std::atoi(pe);   // tests: promoted kernels
       LRPCAP_TRY(tc_conv_launch(a, 0));
     } else {
       SimtConvArgs a;

@@ -34,9 +34,10 @@ struct Geom {
 
 // NS = number of bf16 planes per operand: 2 -> products (0,0)(0,1)(1,0); 3 -> additionally (0,2)(2,0)(1,1).
 // AP = number of A planes staged: NS, or 1 for the two-product backward (one fp16 message plane x [B_hi ; B_lo]).
-template <int BN, int NS, int AP = NS>
+// SM2: CTA-pair mode, each CTA stages half of the B rows (the pair's MMA has N = BN).
+template <int BN, int NS, int AP = NS, bool SM2 = false>
 struct Cfg {
-  static constexpr int kBTileBytes = BN * 128;
+  static constexpr int kBTileBytes = (SM2 ? BN / 2 : BN) * 128;
   static constexpr int kStageBytes = AP * kATileBytes + NS * kBTileBytes;
   static constexpr int kStages = (200 * 1024) / kStageBytes;
   static_assert(kStages >= 2, "tile too large for a double-buffered shared-memory ring");
@@ -74,21 +75,46 @@ __device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN)
   return t;
 }
 
+// CTA-pair mode: pair-tile q covers two consecutive 128-pixel tiles (2 mp, 2 mp + 1) of one channel tile; CTA `rank` takes
+// the pixels of tile 2 mp + rank.
+__device__ __forceinline__ TileCoord tile_coord_pair(const Geom& g, int q, int BN, int rank) {
+  TileCoord t;
+  const int n_tile = q % g.n_tiles_n;
+  int m = 2 * (q / g.n_tiles_n) + rank;
+  const int tiles_per_item = g.tiles_x * g.tiles_y;
+  t.item = m / tiles_per_item;
+  m -= t.item * tiles_per_item;
+  t.x0 = (m % g.tiles_x) * g.TW;
+  t.y0 = (m / g.tiles_x) * g.TH;
+  t.n0 = n_tile * BN;
+  return t;
+}
+
 // A1: two-product mode. A is ONE fp16 plane (the scaled relevance message), B two fp16 planes [hi ; lo] that sit back to
 // back in shared memory. BN <= 128: one MMA with N = 2 BN per K slice (accumulator columns [0, BN) = A*hi, [BN, 2 BN) =
 // A*lo, summed by the epilogue); BN = 256: two N = 256 MMAs into the same accumulator.
 // F8: fp16 + fp8 mode (epilogue.cuh: StoreH1F8). Plane 0 of A and B are fp16 (message, high weight part), plane 1 are E4M3
 // byte planes of the same tile size (128 bytes per row = [top bits | residual] of the message, [low part | high part] of
 // the weights): per k-step four kind::f16 MMAs (K = 16) and four kind::f8f6f4 MMAs (K = 32) into one accumulator.
-template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false, bool F8 = false>
+// SM2: CTA-pair mode (cta_group::2, launched as clusters of two): the pair runs one M = 256 x N = BN MMA per K slice. Each
+// CTA stages its own 128 pixels of A and HALF of the B rows (the operand bytes through each SM's shared memory drop by a
+// third to a half -- the shared-memory pipe, shared by TMA writes and MMA operand reads, is what bounds the one-CTA kernel);
+// its TMEM holds the accumulator rows of its pixels, its epilogue warps drain them. TMA loads of both CTAs complete on
+// the leader's full barrier, the leader's MMA thread issues for both and its commits arrive on both CTAs' barriers.
+template <int BN, int MODE, int NS, bool PROMO, bool F16 = false, bool A1 = false, bool F8 = false, bool SM2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
   static_assert(!A1 || (NS == 2 && F16), "two-product mode: one fp16 A plane x two fp16 B planes");
   static_assert(!F8 || (NS == 2 && F16 && !A1), "fp16 + fp8 mode: one fp16 and one byte plane per operand");
+  static_assert(!SM2 || BN == 256, "CTA-pair mode: N = 256, 128 B rows per CTA");
   constexpr int AP = A1 ? 1 : NS;
   constexpr bool BCAT = A1 && BN <= 128;
   constexpr int ACC = BCAT ? 2 * BN : BN;             // TMEM columns per accumulator buffer
-  using C = Cfg<BN, NS, AP>;
+  using C = Cfg<BN, NS, AP, SM2>;
+  const uint32_t rank = SM2 ? cluster_ctarank() : 0u;   // 0 = leader
+  const int tile0 = SM2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;            // first (pair-)tile of this CTA (pair)
+  const int tile_step = SM2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto coord = [&](int tile) { return SM2 ? tile_coord_pair(g, tile, BN, (int)rank) : tile_coord(g, tile, BN); };
   using ST = typename std::conditional<F8, StoreH1F8, typename std::conditional<A1, StoreH1, typename std::conditional<NS == 3, StoreSplit3,
                                        typename std::conditional<F16, StoreSplitH, StoreSplit>::type>::type>::type>::type;
   extern __shared__ uint8_t smem_raw[];
@@ -113,11 +139,15 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(&tempty_bar[b], SM2 ? 2 * kEpiWarps : kEpiWarps);   // one arrival per epilogue warp (of both CTAs: the leader's counts)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC);
+  if (SM2) cluster_sync_all();   // both CTAs' barriers exist before any remote arrival / completion
+  if (warp == 1) {
+    if (SM2) tmem_alloc2(tmem_slot, 2 * ACC);
+    else tmem_alloc(tmem_slot, 2 * ACC);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -131,14 +161,15 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(g, tile, BN);
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+        const TileCoord tc = coord(tile);
         for (int kk = 0; kk < num_k; ++kk, ++it) {
           const uint32_t s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* st = smem + s * C::kStageBytes;
-          mbar_expect_tx(&full_bar[s], stage_tx);
+          if (!SM2) mbar_expect_tx(&full_bar[s], stage_tx);
+          else if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * stage_tx);   // the bytes of both CTAs land on the leader's barrier
           const int tap = kk / g.cblocks;
           const int cb = kk - tap * g.cblocks;
           int dy = 0, dx = 0;
@@ -147,24 +178,41 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
             dx = tap % 3 - 1;
           }
 #pragma unroll
-          for (int p = 0; p < AP; ++p)   // byte planes (F8, plane 1) count their innermost coordinate in bytes: 128 per block
-            tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], cb * ((F8 && p == 1) ? 128 : kBlockK), tc.x0 + dx,
-                        tc.y0 + dy, tc.item);
+          for (int p = 0; p < AP; ++p) {   // byte planes (F8, plane 1) count their innermost coordinate in bytes: 128 per block
+            const int c0 = cb * ((F8 && p == 1) ? 128 : kBlockK);
+            if (SM2) tma2_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], c0, tc.x0 + dx, tc.y0 + dy, tc.item);
+            else tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], c0, tc.x0 + dx, tc.y0 + dy, tc.item);
+          }
 #pragma unroll
-          for (int p = 0; p < NS; ++p)
-            tma_load_2d(&tm.b[p], st + AP * kATileBytes + p * C::kBTileBytes, &full_bar[s],
-                        cb * ((F8 && p == 1) ? 128 : kBlockK), tap * g.Nout + tc.n0);
+          for (int p = 0; p < NS; ++p) {
+            const int c0 = cb * ((F8 && p == 1) ? 128 : kBlockK);
+            uint8_t* dstb = st + AP * kATileBytes + p * C::kBTileBytes;
+            if (SM2) tma2_load_2d(&tm.b[p], dstb, &full_bar[s], c0, tap * g.Nout + tc.n0 + (int)rank * (BN / 2));
+            else tma_load_2d(&tm.b[p], dstb, &full_bar[s], c0, tap * g.Nout + tc.n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      constexpr uint32_t idesc = make_idesc(128, BN, F16);
+    if (lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (CTA-pair mode: the leader's, for both CTAs) ----------------
+      constexpr uint32_t idesc = make_idesc(SM2 ? 256 : 128, BN, F16);
+      auto mma16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (SM2) umma2_bf16(d, a, b, id, acc);
+        else umma_bf16(d, a, b, id, acc);
+      };
+      auto mma8 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (SM2) umma2_f8(d, a, b, id, acc);
+        else umma_f8(d, a, b, id, acc);
+      };
+      auto commit = [](uint64_t* bar) {
+        if (SM2) umma_commit2_mc(bar, (uint16_t)3);
+        else umma_commit(bar);
+      };
       constexpr uint32_t idesc_cat = make_idesc(128, BCAT ? 2 * BN : BN, F16);
       uint32_t it = 0, tl = 0;   // tl counts accumulator hand-overs: one per tile, or one per `group` k-steps (promotion)
       const int gsz = PROMO ? g.group : num_k;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         for (int kk0 = 0; kk0 < num_k; kk0 += gsz, ++tl) {
           const uint32_t buf = tl & 1u;
           mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -188,31 +236,31 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
               const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units inside the swizzle row
               const uint32_t first = (kk != kk0 || k != 0) ? 1u : 0u;   // a fresh accumulator starts every group
               if (F8) {   // fp16 slice k, then the byte planes' 32-byte slice k (together: every product of the k-step once)
-                umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, first);
-                umma_f8(tmem_d, da[1] + adv, db[1] + adv, idesc, 1u);
+                mma16(tmem_d, da[0] + adv, db[0] + adv, idesc, first);
+                mma8(tmem_d, da[1] + adv, db[1] + adv, idesc, 1u);
               } else if (A1) {
                 if (BCAT) {
-                  umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc_cat, first);   // [A*hi | A*lo]
+                  mma16(tmem_d, da[0] + adv, db[0] + adv, idesc_cat, first);   // [A*hi | A*lo]
                 } else {
-                  umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, first);
-                  umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
+                  mma16(tmem_d, da[0] + adv, db[1] + adv, idesc, first);
+                  mma16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
                 }
               } else if (NS == 3) {   // small terms first
-                umma_bf16(tmem_d, da[1] + adv, db[1] + adv, idesc, first);
-                umma_bf16(tmem_d, da[0] + adv, db[NS - 1] + adv, idesc, 1u);
-                umma_bf16(tmem_d, da[NS - 1] + adv, db[0] + adv, idesc, 1u);
-                umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, 1u);
-                umma_bf16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
-                umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
+                mma16(tmem_d, da[1] + adv, db[1] + adv, idesc, first);
+                mma16(tmem_d, da[0] + adv, db[NS - 1] + adv, idesc, 1u);
+                mma16(tmem_d, da[NS - 1] + adv, db[0] + adv, idesc, 1u);
+                mma16(tmem_d, da[0] + adv, db[1] + adv, idesc, 1u);
+                mma16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
+                mma16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
               } else {
-                umma_bf16(tmem_d, da[0] + adv, db[1] + adv, idesc, first);
-                umma_bf16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
-                umma_bf16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
+                mma16(tmem_d, da[0] + adv, db[1] + adv, idesc, first);
+                mma16(tmem_d, da[1] + adv, db[0] + adv, idesc, 1u);
+                mma16(tmem_d, da[0] + adv, db[0] + adv, idesc, 1u);
               }
             }
-            umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
+            commit(&empty_bar[s]);  // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
           }
-          umma_commit(&tfull_bar[buf]);  // (partial) accumulator complete
+          commit(&tfull_bar[buf]);  // (partial) accumulator complete
         }
       }
     }
@@ -227,8 +275,14 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     const bool row_ok = r < g.TW * g.TH;
     uint32_t tl = 0;
     constexpr int kChunks = BN / 16 / (kEpiWarps / 4);   // 16-column chunks owned by this warp
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(g, tile, BN);
+    auto release_acc = [&](uint32_t buf) {   // this warp has drained accumulator buffer `buf`
+      if (lane == 0) {
+        if (SM2 && rank != 0) mbar_arrive_cluster(&tempty_bar[buf], 0u);
+        else mbar_arrive(&tempty_bar[buf]);
+      }
+    };
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+      const TileCoord tc = coord(tile);
       const int y = tc.y0 + ty, x = tc.x0 + tx;
       const bool valid = row_ok && (y < g.H) && (x < g.W);
       if constexpr (PROMO) {
@@ -280,7 +334,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+          release_acc(buf);
         }
         if constexpr (MODE == EPI_BWD) {
           constexpr int kStep = kEpiWarps / 4;
@@ -301,9 +355,8 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
       } else {
         const uint32_t buf = tl & 1u;
         if (MODE == EPI_BWD && row_ok) {   // multipliers of the NEXT tile (and of the first one) -> L2, a tile period ahead
-          for (int pt = (tl == 0 ? tile : tile + (int)gridDim.x); pt <= tile + (int)gridDim.x && pt < total_tiles;
-               pt += gridDim.x) {
-            const TileCoord nt = tile_coord(g, pt, BN);
+          for (int pt = (tl == 0 ? tile : tile + tile_step); pt <= tile + tile_step && pt < total_tiles; pt += tile_step) {
+            const TileCoord nt = coord(pt);
             if (nt.y0 + ty < g.H && nt.x0 + tx < g.W)
               for (int c = half; c < BN / 16; c += kEpiWarps / 4)
                 epi_prefetch_bwd(e, g.H, g.W, g.Nout, nt.item, nt.y0 + ty, nt.x0 + tx, nt.n0 + c * 16);
@@ -340,7 +393,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        release_acc(buf);
         ++tl;
       }
     }
@@ -348,7 +401,11 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * ACC);
+  if (SM2) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer can still reach its barriers / accumulator
+  if (warp == 1) {
+    if (SM2) tmem_dealloc2(tmem_base, 2 * ACC);
+    else tmem_dealloc(tmem_base, 2 * ACC);
+  }
 }
 
 }  // namespace
@@ -457,6 +514,44 @@ int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream
   return kOk;
 }
 
+// CTA-pair launch (BN = 256 only): clusters of two CTAs, one pair per two SMs; `tm.b` boxes hold 128 rows.
+template <int MODE, int NS, bool PROMO, bool F16, bool A1, bool F8>
+int launch_pair(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  using C = Cfg<256, NS, A1 ? 1 : NS, true>;
+  auto kern = tc_conv_kernel<256, MODE, NS, PROMO, F16, A1, F8, true>;
+  static int smem_state[kMaxDevices] = {};
+  LRPCAP_CUDA(ensure_dynamic_smem(kern, C::kSmemBytes, smem_state));
+  const long long tiles_m = (long long)g.n_items * g.tiles_x * g.tiles_y;
+  const long long pair_tiles = tiles_m / 2 * g.n_tiles_n;
+  LRPCAP_REQUIRE(tiles_m % 2 == 0 && pair_tiles > 0 && pair_tiles < (1ll << 30), kErrShape, "tc_conv: %lld pixel tiles do not pair up", tiles_m);
+  const int pairs_max = device_sm_count() / 2;
+  const unsigned grid = 2u * (unsigned)(pair_tiles < pairs_max ? pair_tiles : pairs_max);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LRPCAP_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, g, e, (int)pair_tiles));
+  return kOk;
+}
+
+// -1 = not asked yet; LRPCAP_TC_2SM=0 disables the CTA-pair kernels
+bool pair_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* v = std::getenv("LRPCAP_TC_2SM");
+    on = (v && v[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 // Instantiated combinations: 2 planes -> every epilogue, BN in {64,128,256}, with and without promotion;
 // 3 bf16 planes or 2 half planes (forward / raw only, always promoted) -> BN in {64,128}.
 template <int BN, bool PROMO>
@@ -469,6 +564,24 @@ int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaS
   }
   set_last_error("tc_conv: unknown epilogue mode %d", mode);
   return kErrInvalidArg;
+}
+
+// CTA-pair dispatch for the N = 256 backward / raw launches (the caller made `tm.b` with 128-row boxes).
+int launch_pair_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
+  const bool promo = g.group > 0;
+#define LRPCAP_PAIR(MODE)                                                                                              \
+  do {                                                                                                                 \
+    if (planes == kPlanesH1F8)                                                                                         \
+      return promo ? launch_pair<MODE, 2, true, true, false, true>(tm, g, e, stream) : launch_pair<MODE, 2, false, true, false, true>(tm, g, e, stream); \
+    if (planes == kPlanesH1x2)                                                                                         \
+      return promo ? launch_pair<MODE, 2, true, true, true, false>(tm, g, e, stream) : launch_pair<MODE, 2, false, true, true, false>(tm, g, e, stream); \
+    return promo ? launch_pair<MODE, 2, true, false, false, false>(tm, g, e, stream) : launch_pair<MODE, 2, false, false, false, false>(tm, g, e, stream); \
+  } while (0)
+  if (mode == EPI_BWD) LRPCAP_PAIR(EPI_BWD);
+  if (mode == EPI_RAW) LRPCAP_PAIR(EPI_RAW);
+#undef LRPCAP_PAIR
+  set_last_error("tc_conv: the CTA-pair kernels cover backward / raw epilogues only (mode %d)", mode);
+  return kErrUnsupported;
 }
 
 template <int BN>
@@ -567,6 +680,10 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
+  // CTA pairs for the N = 256 backward launches whose pixel tiles pair up (every full chunk of the encoder chain)
+  const bool pair = BN == 256 && pair_enabled() && (a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) &&
+                    (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW) && ((long long)a.n_items * g.tiles_x * g.tiles_y) % 2 == 0;
+  const int brows = pair ? BN / 2 : BN;   // B rows staged per CTA
   Maps tm;
   const int n_planes = a.planes == 3 ? 3 : 2;
   const int a_planes = a.planes == kPlanesH1x2 ? 1 : n_planes;
@@ -575,20 +692,21 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
     const uint8_t* B8 = reinterpret_cast<const uint8_t*>(B0) + a.B_elems * 2;
     LRPCAP_TRY(make_map_act(&tm.a[0], A0, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
     LRPCAP_TRY(make_map_act_u8(&tm.a[1], A8, a.n_items, a.H, a.W, 2 * a.C, g.TW, g.TH));
-    LRPCAP_TRY(make_map_w(&tm.b[0], B0, a.taps * a.Nout, a.C, BN));
-    LRPCAP_TRY(make_map_w_u8(&tm.b[1], B8, a.taps * a.Nout, 2 * a.C, BN));
+    LRPCAP_TRY(make_map_w(&tm.b[0], B0, a.taps * a.Nout, a.C, brows));
+    LRPCAP_TRY(make_map_w_u8(&tm.b[1], B8, a.taps * a.Nout, 2 * a.C, brows));
     tm.a[2] = tm.a[0];
     tm.b[2] = tm.b[0];
   } else
   for (int pl = 0; pl < 3; ++pl) {
     const int q = pl < n_planes ? pl : 0;   // unused third slot aliases plane 0
     LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(q < a_planes ? q : 0) * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
-    LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)q * a.B_elems, a.taps * a.Nout, a.C, BN));
+    LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)q * a.B_elems, a.taps * a.Nout, a.C, brows));
   }
 
   const EpiParams& p = a.epi;
   EpiDev e;
   LRPCAP_TRY(make_epi_dev(p, &e));
+  if (pair) return launch_pair_mode(p.mode, a.planes, tm, g, e, stream);
 
   switch (BN) {
     case 256: return launch_mode<256>(p.mode, a.planes, tm, g, e, stream);

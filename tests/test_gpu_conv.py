@@ -30,6 +30,9 @@ GENERIC = [(1, 8, 16, 64, 64, 1), (1, 14, 14, 128, 256, 9), (3, 28, 28, 256, 256
            (1, 4, 4, 64, 128, 9), (1, 2, 2, 512, 512, 9), (5, 7, 7, 64, 64, 1), (1, 8, 16, 64, 64, 9)]
 VERTICAL_HALO = [(2, 16, 16, 64, 64, 9), (1, 16, 32, 128, 128, 9), (2, 32, 32, 64, 64, 9), (1, 32, 48, 128, 64, 9),
                  (3, 48, 32, 256, 128, 9), (150, 16, 16, 64, 64, 9), (1, 112, 112, 128, 64, 9)]
+# N = 256 shapes whose 128-pixel tiles pair up: the CTA-pair (cta_group::2) kernels; (40, 14, 14, ..) gives 80 pair tiles,
+# more than the 74 pairs of a B200, so some pairs run two tiles through both accumulator buffers
+PAIRS = [(4, 14, 14, 512, 512, 9), (2, 28, 28, 512, 256, 9), (40, 14, 14, 256, 512, 9), (2, 14, 14, 64, 256, 1), (1, 56, 56, 256, 256, 9)]
 TOL = {_lib.PREC_FP32_SIMT: 2e-6, _lib.PREC_BF16X3_TC: 3e-5, 2: 2e-6, 3: 2e-6, 4: 3e-5, 5: 1e-4}
 
 
@@ -59,3 +62,33 @@ def test_tap_geometry_vertical_halo():
         got = _lib.debug_conv(_lib.PREC_BF16X3_TC, A, B, 9)
         ref = ref_conv(A, B, 9)
         assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5, t
+
+
+@pytest.mark.parametrize("promote", [0, 9], ids=["plain", "promoted"])
+@pytest.mark.parametrize("prec", [_lib.PREC_BF16X3_TC, 4, 5], ids=["tc", "h1x2", "h1f8"])
+@pytest.mark.parametrize("shape", PAIRS, ids=lambda s: "x".join(map(str, s)))
+def test_cta_pair_conv_matches_the_one_cta_kernel(prec, shape, promote, monkeypatch):
+    """The cta_group::2 kernels (two CTAs share one M = 256 MMA, each staging half of the weight rows) against float64 and,
+    bit for bit, against the one-CTA kernel (LRPCAP_TC_2SM=0 is read once per process, so that arm runs in a child)."""
+    import subprocess, sys, os, tempfile
+    items, H, W, C, Nout, taps = shape
+    rng = np.random.default_rng(7)
+    A = rng.standard_normal((items, H, W, C)).astype(np.float32)
+    B = (rng.standard_normal((taps, C, Nout)) / np.sqrt(taps * C)).astype(np.float32)
+    if promote:
+        monkeypatch.setenv("LRPCAP_DEBUG_CONV_PROMOTE", str(promote))
+    got = _lib.debug_conv(prec, A, B, taps)
+    Ar = A.astype(np.float16).astype(np.float32) if prec == 4 else A
+    ref = ref_conv(Ar, B, taps).reshape(got.shape)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert np.isfinite(got).all() and err <= TOL[prec], err
+    with tempfile.TemporaryDirectory() as d:
+        np.save(os.path.join(d, "A.npy"), A); np.save(os.path.join(d, "B.npy"), B)
+        code = ("import numpy as np, sys; sys.path.insert(0, %r); from lrp_imagecaptioning_b200 import _lib; "
+                "np.save(%r, _lib.debug_conv(%d, np.load(%r), np.load(%r), %d))"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(d, "o.npy"), prec,
+                   os.path.join(d, "A.npy"), os.path.join(d, "B.npy"), taps))
+        env = dict(os.environ, LRPCAP_TC_2SM="0")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+        one = np.load(os.path.join(d, "o.npy"))
+    assert np.array_equal(one, got), np.abs(one - got).max()

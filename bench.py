@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--rule", default="presetA", choices=["presetA", "a2b1"], help="config3 only: the alpha-beta rule")
     ap.add_argument("--precision", default="tc", choices=["tc", "bf16x3", "f16x2", "h1f8", "fp32"],
-                    help="tc: tensor cores; fp16 two-product backward for the alpha-beta family, fp16 + fp8 for the other rules")
+                    help="tc: tensor cores; fp16 two-product backward for alpha1-beta0 / z+, fp16 + fp8 for the other rules")
     ap.add_argument("--chunk-words", type=int, default=320)
     ap.add_argument("--promote", type=int, default=None, help="backward accumulator promotion interval (k-steps; 0 = off, -1 = default policy)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -36,8 +36,9 @@ extern "C" {
                                  * two per word and layer, against two fp16 weight planes: 2 products per MAC instead of 3
                                  * and half the message bytes; 11-bit messages (alpha-beta family: 2e-5 maps) */
 
-#define LRPCAP_PREC_TC_AUTO 3   /* tensor cores, arithmetic per rule: the two-product fp16 mode for the alpha-beta family / z+
-                                 * (same-sign chains), the fp16 + fp8 mode for epsilon, z and the gradient family */
+#define LRPCAP_PREC_TC_AUTO 3   /* tensor cores, arithmetic per rule: the two-product fp16 mode for the positive-flow rules
+                                 * (alpha1 beta0 / z+, images of at least 128 x 128), the fp16 + fp8 mode for everything
+                                 * else (epsilon, z, gradient family, alpha-beta with beta > 0, small images) */
 #define LRPCAP_PREC_H1F8_TC 4   /* messages as a scaled fp16 plane + an E4M3 plane of [top bits | rounding residual], weights as
                                  * an fp16 high plane + an E4M3 plane of [low part | high part]: one kind::f16 and one
                                  * double-rate kind::f8f6f4 product per MAC (two product-equivalents, ~15 bits) */

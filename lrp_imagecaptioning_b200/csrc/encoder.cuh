@@ -119,17 +119,22 @@ class Encoder {
   // two-product backward (PREC_F16X2_TC): the relevance message is ONE fp16 plane scaled by a power of two per word and
   // layer, the weights two fp16 planes: 2 MMA products per algorithmic MAC instead of 3, half the message bytes; the
   // message keeps 11 bits instead of 16 (DESIGN.md section 5 for what that costs per rule)
-  // PREC_TC_AUTO: two products for the rules whose chains are same-sign sums (alpha-beta family, z+: an 11-bit message
-  // costs them 2e-4 of the map maximum), three for the mixed-sign rules (epsilon, z, gradients: 7e-4 -- too close to 1e-3)
+  // PREC_TC_AUTO. The plain two-product mode keeps an 11-bit message: per layer 2e-4 of the GROSS relevance flowing
+  // through. The tolerance is 1e-3 of the NET map, so the mode is only picked where little cancels: the purely
+  // positive-flow rules (alpha1 beta0 / z+, the reference explainers' default PresetA) on maps of at least 128 x 128 (a
+  // head of >= 64 cells: on smaller images every head cell covers the whole image, positive and negative head relevance
+  // land on the same pixels and the error relative to what is left grows by sum|R| / |sum R| -- measured 4.8e-3 at
+  // 32 x 32, profiles/r02_diag_small_images.jsonl). Everything else (epsilon, z, gradients, alpha-beta with beta > 0,
+  // small images) runs the fp16 + fp8 mode below, which carries ~15 bits.
   bool two_product() const {
-    return precision_ == PREC_F16X2_TC ||
-           (precision_ == PREC_TC_AUTO && (rule_.kind == RULE_ALPHA_BETA || rule_.kind == RULE_ZPLUS_FAST));
+    if (precision_ == PREC_F16X2_TC) return true;
+    if (precision_ != PREC_TC_AUTO || hw_ < 128) return false;
+    return rule_.kind == RULE_ZPLUS_FAST || (rule_.kind == RULE_ALPHA_BETA && rule_.beta == 0.f);
   }
   // fp16 + fp8 backward (epilogue.cuh: StoreH1F8): the scaled fp16 message plus an E4M3 plane of [its top bits | its
   // rounding residual] against the weights' fp16 high plane plus an E4M3 plane of [their low part | their high part]: one
-  // kind::f16 and one double-rate kind::f8f6f4 product = two product-equivalents with ~15 bits. Used on the layers the
-  // generic kernel runs (the wide shallow ones keep their vertical-halo kernel's format); PREC_TC_AUTO picks it for the
-  // mixed-sign rules, whose 1e-3 tolerance the plain two-product mode's 11-bit message does not leave room for.
+  // kind::f16 and one double-rate kind::f8f6f4 product = two product-equivalents with ~15 bits (error per layer 1e-5, the
+  // three-product mode's 4e-6). LRPCAP_H1F8=0 sends PREC_TC_AUTO back to three bf16 products.
   bool fp8_mode() const {
     return precision_ == PREC_H1F8_TC || (precision_ == PREC_TC_AUTO && !two_product() && !getenv_off("LRPCAP_H1F8"));
   }

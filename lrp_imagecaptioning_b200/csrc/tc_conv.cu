@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, const int total_tiles) {
   static_assert(!A1 || (NS == 2 && F16), "two-product mode: one fp16 A plane x two fp16 B planes");
   static_assert(!F8 || (NS == 2 && F16 && !A1), "fp16 + fp8 mode: one fp16 and one byte plane per operand");
-  static_assert(!SM2 || BN == 256, "CTA-pair mode: N = 256, 128 B rows per CTA");
+  static_assert(!SM2 || BN >= 128, "CTA-pair mode: N = 128 or 256, half of the B rows per CTA");
   constexpr int AP = A1 ? 1 : NS;
-  constexpr bool BCAT = A1 && BN <= 128;
+  constexpr bool BCAT = A1 && BN <= 128 && !SM2;   // pairs split the operand rows between the CTAs: no [hi ; lo] concatenation
   constexpr int ACC = BCAT ? 2 * BN : BN;             // TMEM columns per accumulator buffer
   using C = Cfg<BN, NS, AP, SM2>;
   const uint32_t rank = SM2 ? cluster_ctarank() : 0u;   // 0 = leader
@@ -514,11 +514,11 @@ int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream
   return kOk;
 }
 
-// CTA-pair launch (BN = 256 only): clusters of two CTAs, one pair per two SMs; `tm.b` boxes hold 128 rows.
-template <int MODE, int NS, bool PROMO, bool F16, bool A1, bool F8>
+// CTA-pair launch (BN = 128 / 256): clusters of two CTAs, one pair per two SMs; `tm.b` boxes hold BN / 2 rows.
+template <int BN, int MODE, int NS, bool PROMO, bool F16, bool A1, bool F8>
 int launch_pair(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
-  using C = Cfg<256, NS, A1 ? 1 : NS, true>;
-  auto kern = tc_conv_kernel<256, MODE, NS, PROMO, F16, A1, F8, true>;
+  using C = Cfg<BN, NS, A1 ? 1 : NS, true>;
+  auto kern = tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1, F8, true>;
   static int smem_state[kMaxDevices] = {};
   LRPCAP_CUDA(ensure_dynamic_smem(kern, C::kSmemBytes, smem_state));
   const long long tiles_m = (long long)g.n_items * g.tiles_x * g.tiles_y;
@@ -542,8 +542,10 @@ int launch_pair(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t str
   return kOk;
 }
 
-// -1 = not asked yet; LRPCAP_TC_2SM=0 disables the CTA-pair kernels
-bool pair_enabled() {
+}  // namespace
+
+// -1 = not asked yet; LRPCAP_TC_2SM=0 disables the CTA-pair kernels (tc_conv_vh.cu asks too)
+bool tc_pair_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* v = std::getenv("LRPCAP_TC_2SM");
@@ -551,6 +553,8 @@ bool pair_enabled() {
   }
   return on == 1;
 }
+
+namespace {
 
 // Instantiated combinations: 2 planes -> every epilogue, BN in {64,128,256}, with and without promotion;
 // 3 bf16 planes or 2 half planes (forward / raw only, always promoted) -> BN in {64,128}.
@@ -566,16 +570,17 @@ int launch_mode2(int mode, const Maps& tm, const Geom& g, const EpiDev& e, cudaS
   return kErrInvalidArg;
 }
 
-// CTA-pair dispatch for the N = 256 backward / raw launches (the caller made `tm.b` with 128-row boxes).
+// CTA-pair dispatch for the N = 128 / 256 backward / raw launches (the caller made `tm.b` with BN / 2-row boxes).
+template <int BN>
 int launch_pair_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream) {
   const bool promo = g.group > 0;
 #define LRPCAP_PAIR(MODE)                                                                                              \
   do {                                                                                                                 \
     if (planes == kPlanesH1F8)                                                                                         \
-      return promo ? launch_pair<MODE, 2, true, true, false, true>(tm, g, e, stream) : launch_pair<MODE, 2, false, true, false, true>(tm, g, e, stream); \
+      return promo ? launch_pair<BN, MODE, 2, true, true, false, true>(tm, g, e, stream) : launch_pair<BN, MODE, 2, false, true, false, true>(tm, g, e, stream); \
     if (planes == kPlanesH1x2)                                                                                         \
-      return promo ? launch_pair<MODE, 2, true, true, true, false>(tm, g, e, stream) : launch_pair<MODE, 2, false, true, true, false>(tm, g, e, stream); \
-    return promo ? launch_pair<MODE, 2, true, false, false, false>(tm, g, e, stream) : launch_pair<MODE, 2, false, false, false, false>(tm, g, e, stream); \
+      return promo ? launch_pair<BN, MODE, 2, true, true, true, false>(tm, g, e, stream) : launch_pair<BN, MODE, 2, false, true, true, false>(tm, g, e, stream); \
+    return promo ? launch_pair<BN, MODE, 2, true, false, false, false>(tm, g, e, stream) : launch_pair<BN, MODE, 2, false, false, false, false>(tm, g, e, stream); \
   } while (0)
   if (mode == EPI_BWD) LRPCAP_PAIR(EPI_BWD);
   if (mode == EPI_RAW) LRPCAP_PAIR(EPI_RAW);
@@ -680,8 +685,8 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
 
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
-  // CTA pairs for the N = 256 backward launches whose pixel tiles pair up (every full chunk of the encoder chain)
-  const bool pair = BN == 256 && pair_enabled() && (a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) &&
+  // CTA pairs for the N >= 128 backward launches whose pixel tiles pair up (every full chunk of the encoder chain)
+  const bool pair = BN >= 128 && tc_pair_enabled() && (a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) &&
                     (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW) && ((long long)a.n_items * g.tiles_x * g.tiles_y) % 2 == 0;
   const int brows = pair ? BN / 2 : BN;   // B rows staged per CTA
   Maps tm;
@@ -706,7 +711,7 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   const EpiParams& p = a.epi;
   EpiDev e;
   LRPCAP_TRY(make_epi_dev(p, &e));
-  if (pair) return launch_pair_mode(p.mode, a.planes, tm, g, e, stream);
+  if (pair) return BN == 256 ? launch_pair_mode<256>(p.mode, a.planes, tm, g, e, stream) : launch_pair_mode<128>(p.mode, a.planes, tm, g, e, stream);
 
   switch (BN) {
     case 256: return launch_mode<256>(p.mode, a.planes, tm, g, e, stream);

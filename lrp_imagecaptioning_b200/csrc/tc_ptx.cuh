@@ -270,6 +270,7 @@ int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, i
 // Vertical-halo variant of the transposed-conv kernel (tc_conv_vh.cu); returns kErrUnsupported when the shape does
 // not qualify so that the caller can fall back to the generic kernel.
 struct TcConvArgs;
+bool tc_pair_enabled();   // LRPCAP_TC_2SM=0 switches the cta_group::2 kernels off
 bool tc_conv_vh_eligible(const TcConvArgs& a, int BN);
 int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream);
 

@@ -32,7 +32,11 @@ VERTICAL_HALO = [(2, 16, 16, 64, 64, 9), (1, 16, 32, 128, 128, 9), (2, 32, 32, 6
                  (3, 48, 32, 256, 128, 9), (150, 16, 16, 64, 64, 9), (1, 112, 112, 128, 64, 9)]
 # N = 256 shapes whose 128-pixel tiles pair up: the CTA-pair (cta_group::2) kernels; (40, 14, 14, ..) gives 80 pair tiles,
 # more than the 74 pairs of a B200, so some pairs run two tiles through both accumulator buffers
-PAIRS = [(4, 14, 14, 512, 512, 9), (2, 28, 28, 512, 256, 9), (40, 14, 14, 256, 512, 9), (2, 14, 14, 64, 256, 1), (1, 56, 56, 256, 256, 9)]
+PAIRS = [(4, 14, 14, 512, 512, 9), (2, 28, 28, 512, 256, 9), (40, 14, 14, 256, 512, 9), (2, 14, 14, 64, 256, 1), (1, 56, 56, 256, 256, 9),
+         (4, 14, 14, 256, 128, 9),                                   # N = 128 generic kernel
+         # vertical-halo kernel, 16 x 16 pixel tiles in pairs (150 items: more pair tiles than CTA pairs)
+         (2, 16, 16, 64, 64, 9), (1, 16, 32, 128, 128, 9), (2, 32, 32, 64, 64, 9), (1, 32, 48, 128, 64, 9), (3, 48, 32, 256, 128, 9),
+         (150, 16, 16, 64, 64, 9), (2, 112, 112, 128, 64, 9)]
 TOL = {_lib.PREC_FP32_SIMT: 2e-6, _lib.PREC_BF16X3_TC: 3e-5, 2: 2e-6, 3: 2e-6, 4: 3e-5, 5: 1e-4}
 
 

@@ -125,7 +125,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches stay on the uniform datapath
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -158,18 +158,16 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
 
   if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp, converged: the TMA wrappers elect the issuing lane (tc_ptx.cuh)
       // ---------------- TMA producer ----------------
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;   // ring stage and phase bit
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord tc = coord(tile);
-        for (int kk = 0; kk < num_k; ++kk, ++it) {
-          const uint32_t s = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1u;
+        for (int kk = 0; kk < num_k; ++kk) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* st = smem + s * C::kStageBytes;
-          if (!SM2) mbar_expect_tx(&full_bar[s], stage_tx);
-          else if (rank == 0) mbar_expect_tx(&full_bar[s], 2u * stage_tx);   // the bytes of both CTAs land on the leader's barrier
+          if (!SM2) mbar_expect_tx_e(&full_bar[s], stage_tx);
+          else if (rank == 0) mbar_expect_tx_e(&full_bar[s], 2u * stage_tx);   // the bytes of both CTAs land on the leader's barrier
           const int tap = kk / g.cblocks;
           const int cb = kk - tap * g.cblocks;
           int dy = 0, dx = 0;
@@ -181,21 +179,26 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           for (int p = 0; p < AP; ++p) {   // byte planes (F8, plane 1) count their innermost coordinate in bytes: 128 per block
             const int c0 = cb * ((F8 && p == 1) ? 128 : kBlockK);
             if (SM2) tma2_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], c0, tc.x0 + dx, tc.y0 + dy, tc.item);
-            else tma_load_4d(&tm.a[p], st + p * kATileBytes, &full_bar[s], c0, tc.x0 + dx, tc.y0 + dy, tc.item);
+            else tma_load_4d_e(&tm.a[p], st + p * kATileBytes, &full_bar[s], c0, tc.x0 + dx, tc.y0 + dy, tc.item);
           }
 #pragma unroll
           for (int p = 0; p < NS; ++p) {
             const int c0 = cb * ((F8 && p == 1) ? 128 : kBlockK);
             uint8_t* dstb = st + AP * kATileBytes + p * C::kBTileBytes;
             if (SM2) tma2_load_2d(&tm.b[p], dstb, &full_bar[s], c0, tap * g.Nout + tc.n0 + (int)rank * (BN / 2));
-            else tma_load_2d(&tm.b[p], dstb, &full_bar[s], c0, tap * g.Nout + tc.n0);
+            else tma_load_2d_e(&tm.b[p], dstb, &full_bar[s], c0, tap * g.Nout + tc.n0);
+          }
+          if (++s == (uint32_t)C::kStages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ---------------- MMA issuer (CTA-pair mode: the leader's, for both CTAs) ----------------
+      // the whole warp runs this loop converged; the MMA / commit wrappers elect the issuing lane (tc_ptx.cuh)
       constexpr uint32_t idesc = make_idesc(SM2 ? 256 : 128, BN, F16);
       auto mma16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
         if (SM2) umma2_bf16(d, a, b, id, acc);
@@ -210,7 +213,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         else umma_commit(bar);
       };
       constexpr uint32_t idesc_cat = make_idesc(128, BCAT ? 2 * BN : BN, F16);
-      uint32_t it = 0, tl = 0;   // tl counts accumulator hand-overs: one per tile, or one per `group` k-steps (promotion)
+      uint32_t s = 0, ph = 0, tl = 0;   // tl counts accumulator hand-overs: one per tile, or one per `group` k-steps (promotion)
       const int gsz = PROMO ? g.group : num_k;
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         for (int kk0 = 0; kk0 < num_k; kk0 += gsz, ++tl) {
@@ -219,9 +222,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * ACC;
           const int kk1 = (kk0 + gsz < num_k) ? kk0 + gsz : num_k;
-          for (int kk = kk0; kk < kk1; ++kk, ++it) {
-            const uint32_t s = it % C::kStages;
-            const uint32_t ph = (it / C::kStages) & 1u;
+          for (int kk = kk0; kk < kk1; ++kk) {
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             const uint32_t sbase = smem_u32(smem + s * C::kStageBytes);
@@ -259,6 +260,10 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
               }
             }
             commit(&empty_bar[s]);  // frees this smem stage (in both CTAs of a pair) once the MMAs above have read it
+            if (++s == (uint32_t)C::kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
           commit(&tfull_bar[buf]);  // (partial) accumulator complete
         }

@@ -42,7 +42,7 @@ constexpr int kMaxNB = 8;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct VhGeom {
-  int H, W, tiles_x, tiles_y, cblocks, Nout, n_items, n_tiles_n, NA, NB;   // NA / NB: patch / weight-tap ring slots
+  int H, W, tiles_x, tiles_y, cblocks, Nout, n_items, n_tiles_n, NA, NB, tile_major;   // NA / NB: patch / weight-tap ring slots
 };
 struct VhMaps {
   CUtensorMap a[2];
@@ -116,7 +116,7 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: the role branches stay on the uniform datapath
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -147,49 +147,55 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool tile_major = NB >= 4;   // MMA order inside a group (see above)
+  const bool tile_major = g.tile_major != 0;   // MMA order inside a group (see above)
 
   if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
-    if (lane == 0) {
+    {   // the whole warp, converged: the TMA wrappers elect the issuing lane (tc_ptx.cuh)
       // ---------------- TMA producer: patches and weight taps in the order the MMA thread waits for them ----------------
-      uint32_t ia = 0, ib = 0;
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;   // ring slot and phase bit, advanced by hand (NA / NB are run-time values)
       for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const VhTile tc = coord(tile);
         for (int cb = 0; cb < g.cblocks; ++cb) {
           for (int dxi = 0; dxi < 3; ++dxi) {
-            for (int j = 0; j < kTM; ++j, ++ia) {
-              const uint32_t sa = ia % NA;
-              mbar_wait(&aempty[sa], ((ia / NA) & 1u) ^ 1u);
-              if (!SM2) mbar_expect_tx(&afull[sa], (uint32_t)kASlot);
-              else if (rank == 0) mbar_expect_tx(&afull[sa], 2u * (uint32_t)kASlot);   // both CTAs' bytes land on the leader's barrier
+            for (int j = 0; j < kTM; ++j) {
+              mbar_wait(&aempty[sa], pha ^ 1u);
+              if (!SM2) mbar_expect_tx_e(&afull[sa], (uint32_t)kASlot);
+              else if (rank == 0) mbar_expect_tx_e(&afull[sa], 2u * (uint32_t)kASlot);   // both CTAs' bytes land on the leader's barrier
               uint8_t* ap = a_ring + sa * kASlot;
 #pragma unroll
               for (int p = 0; p < AP; ++p) {   // byte planes (F8, plane 1) count the innermost coordinate in bytes
                 const int c0 = cb * ((F8 && p == 1) ? 128 : kBlockK);
                 if (SM2) tma2_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], c0, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1, tc.item);
-                else tma_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], c0, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1, tc.item);
+                else tma_load_4d_e(&tm.a[p], ap + p * kAPlane, &afull[sa], c0, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1, tc.item);
               }
               if (j == (tile_major ? 0 : kTM - 1)) {   // the three weight taps of this dx, used by both MMA tiles
-                for (int dyi = 0; dyi < 3; ++dyi, ++ib) {
-                  const uint32_t sb = ib % NB;
-                  mbar_wait(&bempty[sb], ((ib / NB) & 1u) ^ 1u);
-                  if (!SM2) mbar_expect_tx(&bfull[sb], (uint32_t)kBSlot);
-                  else if (rank == 0) mbar_expect_tx(&bfull[sb], 2u * (uint32_t)kBSlot);
+                for (int dyi = 0; dyi < 3; ++dyi) {
+                  mbar_wait(&bempty[sb], phb ^ 1u);
+                  if (!SM2) mbar_expect_tx_e(&bfull[sb], (uint32_t)kBSlot);
+                  else if (rank == 0) mbar_expect_tx_e(&bfull[sb], 2u * (uint32_t)kBSlot);
                   uint8_t* bp = b_ring + sb * kBSlot;
                   const int tap = dyi * 3 + dxi;
 #pragma unroll
                   for (int p = 0; p < 2; ++p) {
                     const int c0 = cb * ((F8 && p == 1) ? 128 : kBlockK);
                     if (!SM2) {
-                      tma_load_2d(&tm.b[p], bp + p * kBPlane, &bfull[sb], c0, tap * g.Nout + tc.n0);
+                      tma_load_2d_e(&tm.b[p], bp + p * kBPlane, &bfull[sb], c0, tap * g.Nout + tc.n0);
                     } else if (NCAT) {   // CTA `rank` stages plane `rank`: rows [0, BN) of the pair's N = 2 BN operand are the high plane
                       if (p == (int)rank) tma2_load_2d(&tm.b[p], bp, &bfull[sb], c0, tap * g.Nout + tc.n0);
                     } else {
                       tma2_load_2d(&tm.b[p], bp + p * kBPlane, &bfull[sb], c0, tap * g.Nout + tc.n0 + (int)rank * (BN / 2));
                     }
                   }
+                  if (++sb == (uint32_t)NB) {
+                    sb = 0;
+                    phb ^= 1u;
+                  }
                 }
+              }
+              if (++sa == (uint32_t)NA) {
+                sa = 0;
+                pha ^= 1u;
               }
             }
           }
@@ -197,8 +203,9 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ---------------- MMA issuer (pairs: the leader's, for both CTAs) ----------------
+      // the whole warp runs this loop converged; the MMA / commit wrappers elect the issuing lane (tc_ptx.cuh)
       constexpr uint32_t idesc_n = make_idesc(SM2 ? 256 : 128, BN, A1 || F8);
       constexpr uint32_t idesc_cat = make_idesc(SM2 ? 256 : 128, NCAT ? 2 * BN : BN, A1 || F8);
       auto mma16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
@@ -213,54 +220,74 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
         if (SM2) umma_commit2_mc(bar, (uint16_t)3);
         else umma_commit(bar);
       };
-      uint32_t ia = 0, ib = 0, tl = 0;
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, tl = 0;
       for (int tile = tile0; tile < total_tiles; tile += tile_step, ++tl) {
         const uint32_t buf = tl & 1u;
         mbar_wait(&tempty[buf], ((tl >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * (kTM * ACC);
         for (int cb = 0; cb < g.cblocks; ++cb) {
-          for (int dxi = 0; dxi < 3; ++dxi, ib += 3, ia += kTM) {
+          for (int dxi = 0; dxi < 3; ++dxi) {
             const uint32_t accum = (cb != 0 || dxi != 0) ? 1u : 0u;
-            // the four K slices of weight tap dyi for MMA tile j
-            auto issue = [&](int j, int dyi) {
-              const uint32_t bbase = smem_u32(b_ring + ((ib + dyi) % NB) * kBSlot);
+            uint32_t as_[kTM], ap_[kTM], bs_[3], bp_[3];   // slots and phase bits of this group's patches and taps
+#pragma unroll
+            for (int j = 0; j < kTM; ++j) {
+              as_[j] = sa;
+              ap_[j] = pha;
+              if (++sa == (uint32_t)NA) {
+                sa = 0;
+                pha ^= 1u;
+              }
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              bs_[d] = sb;
+              bp_[d] = phb;
+              if (++sb == (uint32_t)NB) {
+                sb = 0;
+                phb ^= 1u;
+              }
+            }
+            // K slice k of weight tap dyi for MMA tile j
+            auto slice = [&](int j, int dyi, int k) {
+              const uint32_t bbase = smem_u32(b_ring + bs_[dyi] * kBSlot);
               const uint64_t db_hi = make_desc_sw128(bbase);                 // NCAT: the same start, N = 2 BN rows
               const uint64_t db_lo = make_desc_sw128(bbase + kBPlane);
-              const uint32_t abase = smem_u32(a_ring + ((ia + j) % NA) * kASlot);
+              const uint32_t abase = smem_u32(a_ring + as_[j] * kASlot);
               const uint64_t da_hi = make_desc_sw128(abase + (uint32_t)dyi * 1024u);
               const uint64_t da_lo = make_desc_sw128(abase + (A1 ? 0 : kAPlane) + (uint32_t)dyi * 1024u);
               const uint32_t d = tmem_d + j * ACC;
-#pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 2);
-                const uint32_t acc_k = (accum != 0u || dyi != 0 || k != 0) ? 1u : 0u;   // the tile's first MMA overwrites
-                if (F8) {
-                  mma16(d, da_hi + adv, db_hi + adv, idesc_n, acc_k);     // fp16 message x fp16 high weights
-                  mma8(d, da_lo + adv, db_lo + adv, idesc_n, 1u);         // [top bits | residual] x [low | high], E4M3
-                } else if (A1) {
-                  if (NCAT) {
-                    mma16(d, da_hi + adv, db_hi + adv, idesc_cat, acc_k);   // [A*hi | A*lo]
-                  } else {
-                    mma16(d, da_hi + adv, db_lo + adv, idesc_n, acc_k);
-                    mma16(d, da_hi + adv, db_hi + adv, idesc_n, 1u);
-                  }
-                } else if (NCAT) {
-                  mma16(d, da_hi + adv, db_hi + adv, idesc_cat, acc_k);   // [hi*hi | hi*lo]
-                  mma16(d, da_lo + adv, db_hi + adv, idesc_n, 1u);        // += lo*hi into the first block
+              const uint64_t adv = (uint64_t)(k * 2);
+              const uint32_t acc_k = (accum != 0u || dyi != 0 || k != 0) ? 1u : 0u;   // the tile's first MMA overwrites
+              if (F8) {
+                mma16(d, da_hi + adv, db_hi + adv, idesc_n, acc_k);     // fp16 message x fp16 high weights
+                mma8(d, da_lo + adv, db_lo + adv, idesc_n, 1u);         // [top bits | residual] x [low | high], E4M3
+              } else if (A1) {
+                if (NCAT) {
+                  mma16(d, da_hi + adv, db_hi + adv, idesc_cat, acc_k);   // [A*hi | A*lo]
                 } else {
                   mma16(d, da_hi + adv, db_lo + adv, idesc_n, acc_k);
-                  mma16(d, da_lo + adv, db_hi + adv, idesc_n, 1u);
                   mma16(d, da_hi + adv, db_hi + adv, idesc_n, 1u);
                 }
+              } else if (NCAT) {
+                mma16(d, da_hi + adv, db_hi + adv, idesc_cat, acc_k);   // [hi*hi | hi*lo]
+                mma16(d, da_lo + adv, db_hi + adv, idesc_n, 1u);        // += lo*hi into the first block
+              } else {
+                mma16(d, da_hi + adv, db_lo + adv, idesc_n, acc_k);
+                mma16(d, da_lo + adv, db_hi + adv, idesc_n, 1u);
+                mma16(d, da_hi + adv, db_hi + adv, idesc_n, 1u);
               }
             };
+            auto issue = [&](int j, int dyi) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) slice(j, dyi, k);
+            };
             auto wait_a = [&](int j) {
-              mbar_wait(&afull[(ia + j) % NA], ((ia + j) / NA) & 1u);
+              mbar_wait(&afull[as_[j]], ap_[j]);
               tc_fence_after();
             };
             auto wait_b = [&](int dyi) {
-              mbar_wait(&bfull[(ib + dyi) % NB], ((ib + dyi) / NB) & 1u);
+              mbar_wait(&bfull[bs_[dyi]], bp_[dyi]);
               tc_fence_after();
             };
             if (tile_major) {
@@ -269,18 +296,26 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
                 for (int dyi = 0; dyi < 3; ++dyi) {
                   if (j == 0) wait_b(dyi);
                   issue(j, dyi);
-                  if (j == kTM - 1) commit(&bempty[(ib + dyi) % NB]);
+                  if (j == kTM - 1) commit(&bempty[bs_[dyi]]);
                 }
-                commit(&aempty[(ia + j) % NA]);
+                commit(&aempty[as_[j]]);
               }
             } else {
               for (int j = 0; j < kTM; ++j) wait_a(j);
               for (int dyi = 0; dyi < 3; ++dyi) {
                 wait_b(dyi);
-                for (int j = 0; j < kTM; ++j) issue(j, dyi);
-                commit(&bempty[(ib + dyi) % NB]);
+                if (g.cblocks == 1) {   // measured: alternating the two accumulators per K slice helps the K = 576 layer only
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k)
+#pragma unroll
+                    for (int j = 0; j < kTM; ++j) slice(j, dyi, k);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < kTM; ++j) issue(j, dyi);
+                }
+                commit(&bempty[bs_[dyi]]);
               }
-              for (int j = 0; j < kTM; ++j) commit(&aempty[(ia + j) % NA]);
+              for (int j = 0; j < kTM; ++j) commit(&aempty[as_[j]]);
             }
           }
         }
@@ -372,6 +407,8 @@ int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) 
   constexpr int kASlot = (A1 ? 1 : 2) * kAPlane;
   vh_rings(kASlot, kBSlot, &g.NA, &g.NB);
   LRPCAP_REQUIRE(g.NB >= 2, kErrUnsupported, "tc_conv_vh: no room for a weight ring (BN=%d)", BN);
+  static const int order = [] { const char* v = std::getenv("LRPCAP_VH_TILE_MAJOR"); return v ? std::atoi(v) : 0; }();
+  g.tile_major = (order != 0 && g.NB >= 4) ? 1 : 0;
   const int smem = g.NA * kASlot + g.NB * kBSlot + 1024 + 512;
   auto kern = tc_conv_vh_kernel<BN, MODE, NCAT, A1, F8, SM2>;
   static int smem_state[kMaxDevices] = {};
@@ -443,10 +480,11 @@ int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
-  g.NA = g.NB = 0;
+  g.NA = g.NB = g.tile_major = 0;
   const bool a1 = a.planes == kPlanesH1x2, f8 = a.planes == kPlanesH1F8;
   // CTA pairs when the 16 x 16 pixel tiles pair up (two-product and fp16 + fp8 modes)
-  const bool pair = tc_pair_enabled() && (a1 || f8) && ((long long)a.n_items * g.tiles_x * g.tiles_y) % 2 == 0;
+  static const bool vh_pairs = [] { const char* v = std::getenv("LRPCAP_VH_2SM"); return !(v && v[0] == '0'); }();
+  const bool pair = tc_pair_enabled() && vh_pairs && (a1 || f8) && ((long long)a.n_items * g.tiles_x * g.tiles_y) % 2 == 0;
   const bool ncat = a1 && BN == 64;
   const int brows = pair && !ncat ? BN / 2 : BN;   // weight rows per TMA box
   const __nv_bfloat16* A0 = reinterpret_cast<const __nv_bfloat16*>(a.A);

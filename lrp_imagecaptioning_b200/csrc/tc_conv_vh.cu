@@ -42,7 +42,7 @@ constexpr int kMaxNB = 8;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct VhGeom {
-  int H, W, tiles_x, tiles_y, cblocks, Nout, n_items, n_tiles_n, NA, NB, tile_major;   // NA / NB: patch / weight-tap ring slots
+  int H, W, tiles_x, tiles_y, cblocks, Nout, n_items, n_tiles_n, NA, NB;   // NA / NB: patch / weight-tap ring slots
 };
 struct VhMaps {
   CUtensorMap a[2];
@@ -74,11 +74,10 @@ __device__ __forceinline__ VhTile vh_tile(const VhGeom& g, int m, int n_tile, in
 // high plane, CTA 1 the low plane; otherwise rows [rank BN/2, +BN/2) of both planes) and the leader issues M = 256 MMAs.
 // Half-size weight slots are what lets the rings be deep enough: one CTA alone has room for only two 128-channel taps.
 //
-// MMA order inside one (channel block, dx) group, chosen by the weight ring depth:
-//   NB >= 4: MMA tile by MMA tile -- a patch slot is released as soon as ITS 3 taps x 4 slices are issued, so the patch ring
-//            is refilled per patch (the ring holds NA - 1 patches in flight instead of one group of two: the kernel was
-//            bound by the latency of that single group in flight, ncu: tensor pipe 29 % busy, nothing else saturated);
-//   NB <  4: tap by tap over both MMA tiles (each tap slot is released after its tap), patches released per group.
+// MMA order inside one (channel block, dx) group: tap by tap over both MMA tiles (each weight slot is released after its
+// tap, the two patches after the group). Issuing tile by tile with per-patch release (a deeper patch pipeline) was measured
+// and makes no difference once the issue loop runs on the uniform datapath (tc_ptx.cuh) -- before that, the ~110 cycles the
+// issuing thread spent per MMA, not the memory pipeline, were what paced this kernel (ncu: tensor pipe 29 % busy).
 template <int BN, int MODE, bool NCAT, bool A1 = false, bool F8 = false, bool SM2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDev e, const int total_tiles) {
@@ -147,7 +146,6 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool tile_major = g.tile_major != 0;   // MMA order inside a group (see above)
 
   if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
@@ -169,7 +167,7 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
                 if (SM2) tma2_load_4d(&tm.a[p], ap + p * kAPlane, &afull[sa], c0, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1, tc.item);
                 else tma_load_4d_e(&tm.a[p], ap + p * kAPlane, &afull[sa], c0, tc.x0 + kMW * j + dxi - 1, tc.y0 - 1, tc.item);
               }
-              if (j == (tile_major ? 0 : kTM - 1)) {   // the three weight taps of this dx, used by both MMA tiles
+              if (j == kTM - 1) {   // the three weight taps of this dx, used by both MMA tiles
                 for (int dyi = 0; dyi < 3; ++dyi) {
                   mbar_wait(&bempty[sb], phb ^ 1u);
                   if (!SM2) mbar_expect_tx_e(&bfull[sb], (uint32_t)kBSlot);
@@ -290,33 +288,21 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
               mbar_wait(&bfull[bs_[dyi]], bp_[dyi]);
               tc_fence_after();
             };
-            if (tile_major) {
-              for (int j = 0; j < kTM; ++j) {
-                wait_a(j);
-                for (int dyi = 0; dyi < 3; ++dyi) {
-                  if (j == 0) wait_b(dyi);
-                  issue(j, dyi);
-                  if (j == kTM - 1) commit(&bempty[bs_[dyi]]);
-                }
-                commit(&aempty[as_[j]]);
+            for (int j = 0; j < kTM; ++j) wait_a(j);
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              wait_b(dyi);
+              if (g.cblocks == 1) {   // measured: alternating the two accumulators per K slice helps the K = 576 layer only
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k)
+#pragma unroll
+                  for (int j = 0; j < kTM; ++j) slice(j, dyi, k);
+              } else {
+#pragma unroll
+                for (int j = 0; j < kTM; ++j) issue(j, dyi);
               }
-            } else {
-              for (int j = 0; j < kTM; ++j) wait_a(j);
-              for (int dyi = 0; dyi < 3; ++dyi) {
-                wait_b(dyi);
-                if (g.cblocks == 1) {   // measured: alternating the two accumulators per K slice helps the K = 576 layer only
-#pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k)
-#pragma unroll
-                    for (int j = 0; j < kTM; ++j) slice(j, dyi, k);
-                } else {
-#pragma unroll
-                  for (int j = 0; j < kTM; ++j) issue(j, dyi);
-                }
-                commit(&bempty[bs_[dyi]]);
-              }
-              for (int j = 0; j < kTM; ++j) commit(&aempty[as_[j]]);
+              commit(&bempty[bs_[dyi]]);
             }
+            for (int j = 0; j < kTM; ++j) commit(&aempty[as_[j]]);
           }
         }
         commit(&tfull[buf]);
@@ -388,8 +374,7 @@ tc_conv_vh_kernel(const __grid_constant__ VhMaps tm, const VhGeom g, const EpiDe
   }
 }
 
-// Ring depths for the shared memory one CTA has: at least 4 patch slots; weight taps get what is left, and when that is
-// 4 or more (the tile-major MMA order) further room goes to the patch ring.
+// Ring depths for the shared memory one CTA has: at least 4 patch slots, 4 weight-tap slots when they fit, the rest to patches.
 static void vh_rings(int a_slot, int b_slot, int* NA, int* NB) {
   const int room = kSmemLimit - 1024 - 512;
   int na = (room - 4 * b_slot) / a_slot;
@@ -407,8 +392,6 @@ int launch_vh(const VhMaps& tm, VhGeom g, const EpiDev& e, cudaStream_t stream) 
   constexpr int kASlot = (A1 ? 1 : 2) * kAPlane;
   vh_rings(kASlot, kBSlot, &g.NA, &g.NB);
   LRPCAP_REQUIRE(g.NB >= 2, kErrUnsupported, "tc_conv_vh: no room for a weight ring (BN=%d)", BN);
-  static const int order = [] { const char* v = std::getenv("LRPCAP_VH_TILE_MAJOR"); return v ? std::atoi(v) : 0; }();
-  g.tile_major = (order != 0 && g.NB >= 4) ? 1 : 0;
   const int smem = g.NA * kASlot + g.NB * kBSlot + 1024 + 512;
   auto kern = tc_conv_vh_kernel<BN, MODE, NCAT, A1, F8, SM2>;
   static int smem_state[kMaxDevices] = {};
@@ -464,7 +447,6 @@ bool vh_enabled() {
 }  // namespace
 
 bool tc_conv_vh_eligible(const TcConvArgs& a, int BN) {
-  if (a.planes == kPlanesH1F8 && BN == 64 && a.C != 64 && std::getenv("LRPCAP_VH_F8_WIDE") == nullptr) return false;
   return vh_enabled() && a.taps == 9 && (a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) && a.promote_every <= 0 &&
          (BN == 64 || BN == 128) && a.W % kTW == 0 && a.H % kTH == 0 && (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW);
 }
@@ -480,7 +462,7 @@ int tc_conv_vh_launch(const TcConvArgs& a, int BN, cudaStream_t stream) {
   g.Nout = a.Nout;
   g.n_items = a.n_items;
   g.n_tiles_n = a.Nout / BN;
-  g.NA = g.NB = g.tile_major = 0;
+  g.NA = g.NB = 0;
   const bool a1 = a.planes == kPlanesH1x2, f8 = a.planes == kPlanesH1F8;
   // CTA pairs when the 16 x 16 pixel tiles pair up (two-product and fp16 + fp8 modes)
   static const bool vh_pairs = [] { const char* v = std::getenv("LRPCAP_VH_2SM"); return !(v && v[0] == '0'); }();

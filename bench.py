@@ -57,14 +57,14 @@ def peaks():
 
 class ClockSampler(object):
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -73,15 +73,23 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """The timed region starts here (the sampler itself started before the warm-up steps: nvidia-smi needs ~0.3 s to come up)."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        window = "timed region"
+        rows = self.rows[self.first:]
+        if not rows:   # a timed region shorter than the sampling period: the warm-up steps ran the same kernels
+            rows, window = list(self.rows), "warm-up + timed region (timed region shorter than the 100 ms sampling period)"
+        sm = [float(r[0]) for r in rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 def rule_for(workload, rule_name):
@@ -260,11 +268,12 @@ def run_ours(args, rank, local_rank, world):
     job = Job(args, args.workload, rank, world, dev, args.rule)
     im = job.model.image_model
     sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         job.step_resident()
     torch.cuda.synchronize()
     l0 = job.eng.launches()
-    sampler.start()
+    sampler.mark()
     ms = timed(job.step_resident, args.steps, 0)          # no per-launch instrumentation inside this region
     clocks = sampler.stop()
     launches = (job.eng.launches() - l0) // max(args.steps, 1)

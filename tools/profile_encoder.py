@@ -1,5 +1,6 @@
 """Short encoder-only workload for ncu: forward of 4 images, then the relevance backward for 4 x WORDS_PER_IMAGE words
-(default 80 each = one 320-word chunk, the bench's chunk) at 224x224.
+(default 80 each = one 320-word chunk, the bench's chunk) at 224x224.  N_IMAGES=64 WORDS_PER_IMAGE=1 profiles the forward
+of a bench-sized batch.
   RULE=eps|presetA|a2b1 (default eps)   PRECISION=tc|bf16x3|f16x2 (default tc)
 `ncu -k regex:"tc_conv|last_dgrad" -s <forward launches> -c 13` captures the 12 transposed-conv launches + the last conv."""
 import os, sys
@@ -9,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lrp_imagecaptioning_b200 import synth, _lib
 from lrp_imagecaptioning_b200.encoder import ImageModel, RuleSpec
 
-n_img, per = 4, int(os.environ.get("WORDS_PER_IMAGE", "80"))
+n_img, per = int(os.environ.get("N_IMAGES", "4")), int(os.environ.get("WORDS_PER_IMAGE", "80"))
 rule = {"eps": RuleSpec(_lib.RULE_EPSILON, epsilon=0.01), "presetA": RuleSpec(_lib.RULE_ALPHA_BETA, alpha=1, beta=0, bias=True),
         "a2b1": RuleSpec(_lib.RULE_ALPHA_BETA, alpha=2, beta=1, bias=True)}[os.environ.get("RULE", "eps")]
 m = ImageModel(synth.vgg16_weights(0), image_hw=224, precision=os.environ.get("PRECISION", "tc"))

@@ -230,7 +230,7 @@ def test_chunking_is_invisible():
 @pytest.mark.parametrize("rule,precision", [("presetA", "bf16x3"), ("eps", "bf16x3"), ("presetA", "fp32"), ("eps", "fp32"),
                                             ("a2b1", "bf16x3"), ("zplus", "bf16x3"), ("z", "bf16x3"), ("gradient", "bf16x3"),
                                             ("guided", "bf16x3"), ("ixg", "bf16x3"),
-                                            # the default arithmetic ("tc": fp16 two-product for the same-sign rules, fp16 + fp8 for the rest)
+                                            # the default arithmetic ("tc": plain fp16 two-product for alpha1-beta0 / z+, fp16 + fp8 for the rest)
                                             ("presetA", "tc"), ("a2b1", "tc"), ("zplus", "tc"), ("eps", "tc"), ("z", "tc"),
                                             ("gradient", "tc"), ("guided", "tc"), ("ixg", "tc"), ("eps", "h1f8"), ("presetA", "h1f8")])
 def test_relevance_matches_oracle_224(rule, precision):

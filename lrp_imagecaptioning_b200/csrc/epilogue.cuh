@@ -461,7 +461,14 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
       load_f32<16>(G + o0 * 16, gg[0]);
       if (UP == 2) gi[0] = __ldg(e.Gidx + o0);
     }
-#pragma unroll
+    // Code size: fully unrolled, the up-sampling form is NCH x 4 sub-pixels x 16 channels of convert-and-store code (the
+    // N = 256 kernel was 227 KB of SASS) that each warp runs once per tile, so every pass came through the instruction cache
+    // cold (ncu: stall_no_inst on the epilogue's ALU instructions, tensor pipe 49 % on the three layers under a pool). The
+    // pipelined form keeps two chunks per loop body (the double-buffered multiplier registers need a static index) and
+    // loops over the sub-pixels; the promoted form indexes its register accumulator by `c` and keeps its chunks unrolled.
+    constexpr int kChunkUnroll = (UP == 2 && PIPE && NCH % 2 == 0) ? 2 : NCH;
+    constexpr int kSubUnroll = 1;   // (one iteration when UP == 1)
+#pragma unroll kChunkUnroll
     for (int c = 0; c < NCH; ++c) {
       float v[16];
       __syncwarp();   // reconverge after the predicated global accesses: the accumulator load is .sync.aligned
@@ -485,7 +492,7 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
         if (UP == 2) gi[0] = __ldg(e.Gidx + o1);
       }
       if (valid) {
-#pragma unroll
+#pragma unroll kSubUnroll
         for (int sub = 0; sub < SUBS; ++sub) {
           float o[16];
 #pragma unroll

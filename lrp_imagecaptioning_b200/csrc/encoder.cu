@@ -142,11 +142,9 @@ int Encoder::set_weights(const float* const* kernels_hwio, const float* const* b
     Layer& L = L_[l];
     LRPCAP_CUDA(cudaMemcpy(L.w_hwio, kernels_hwio[l], (size_t)9 * L.cin * L.cout * sizeof(float), cudaMemcpyHostToDevice));
     LRPCAP_CUDA(cudaMemcpy(L.bias, biases[l], L.cout * sizeof(float), cudaMemcpyHostToDevice));
-    for (auto& f : L.prepared)
-      for (auto& p : f)
-        if (p) { cudaFree(p); p = nullptr; }
-    for (auto& p : L.dual)
-      if (p) { cudaFree(p); p = nullptr; }
+    for (int f = 0; f < 8; ++f)
+      for (int sg = 0; sg < 3; ++sg) L.stale[f][sg] = L.prepared[f][sg] != nullptr;
+    for (int d = 0; d < 4; ++d) L.dual_stale[d] = L.dual[d] != nullptr;
   }
   float** small[] = {&w0_pm_, &w0_mp_, &w0_last_a_, &w0_last_b_};
   for (float** p : small)
@@ -182,11 +180,11 @@ int Encoder::set_weights_device(const float* const* d_kernels_hwio, const float*
     LRPCAP_CUDA(cudaMemcpy(L.w_hwio, d_kernels_hwio[l], nw * sizeof(float), cudaMemcpyDeviceToDevice));
     LRPCAP_CUDA(cudaMemcpy(L.bias, d_biases[l], L.cout * sizeof(float), cudaMemcpyDeviceToDevice));
     absmax_kernel<<<64, 256>>>(L.w_hwio, nw, mx.as<unsigned>() + l);
-    for (auto& f : L.prepared)
-      for (auto& p : f)
-        if (p) { cudaFree(p); p = nullptr; }
-    for (auto& p : L.dual)
-      if (p) { cudaFree(p); p = nullptr; }
+    // the derived layouts keep their allocations (cudaFree + cudaMalloc of ~40 buffers cost the fine-tune step 0.1-0.25 s
+    // of host time) and are re-laid from the new w_hwio on their next use
+    for (int f = 0; f < 8; ++f)
+      for (int sg = 0; sg < 3; ++sg) L.stale[f][sg] = L.prepared[f][sg] != nullptr;
+    for (int d = 0; d < 4; ++d) L.dual_stale[d] = L.dual[d] != nullptr;
   }
   LRPCAP_CUDA(cudaGetLastError());
   float** small[] = {&w0_pm_, &w0_mp_, &w0_last_a_, &w0_last_b_};
@@ -213,10 +211,11 @@ bool Encoder::getenv_off(const char* name) {
 
 int Encoder::get_weights(int l, int fmt, int sign, void** out, cudaStream_t s) {
   Layer& L = L_[l];
-  if (!L.prepared[fmt][sign]) {
-    void* p = nullptr;
-    LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * (fmt == WF_TC_FWD3 ? 6 : 4)));
+  if (!L.prepared[fmt][sign] || L.stale[fmt][sign]) {
+    void* p = L.prepared[fmt][sign];
+    if (!p) LRPCAP_CUDA(cudaMalloc(&p, (size_t)9 * L.cin * L.cout * (fmt == WF_TC_FWD3 ? 6 : 4)));
     L.prepared[fmt][sign] = p;
+    L.stale[fmt][sign] = false;
     if (fmt == WF_TC_FWD3) LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_FWD, sign, s, 9, 3));
     else if (fmt == WF_TC_BWDH)
       LRPCAP_TRY(prep_weights(L.w_hwio, p, L.cin, L.cout, WF_TC_BWD, sign, s, 9, kPlanesF16x2, std::ldexp(1.f, L.wpow)));
@@ -235,9 +234,11 @@ int Encoder::get_dual_weights(int l, bool tc, void** out, cudaStream_t s) {
   Layer& L = L_[l];
   const bool f8 = tc && fp8_mode();
   const bool h = tc && (two_product() || f8);
-  void*& slot = L.dual[tc ? (f8 ? 3 : h ? 2 : 1) : 0];
-  if (!slot) {
-    LRPCAP_CUDA(cudaMalloc(&slot, (size_t)9 * L.cin * 2 * L.cout * sizeof(float)));
+  const int di = tc ? (f8 ? 3 : h ? 2 : 1) : 0;
+  void*& slot = L.dual[di];
+  if (!slot || L.dual_stale[di]) {
+    if (!slot) LRPCAP_CUDA(cudaMalloc(&slot, (size_t)9 * L.cin * 2 * L.cout * sizeof(float)));
+    L.dual_stale[di] = false;
     const float ws = h ? std::ldexp(1.f, L.wpow) : 1.f;
     LRPCAP_TRY(prep_weights_dual(L.w_hwio, slot, L.cin, L.cout, tc ? WF_TC_BWD : WF_SIMT_BWD, WS_PLUS, rule_.alpha * ws, WS_MINUS,
                                  -rule_.beta * ws, s, f8 ? 2 : h ? 1 : 0));
@@ -457,8 +458,7 @@ int Encoder::forward(const float* d_images, int n, const EncoderRule& rule, cuda
     LRPCAP_TRY(Mseed2_.ensure((size_t)n * layer_out_elems(kLayers - 1) * sizeof(float)));
     if (dual_alpha_ != rule.alpha || dual_beta_ != rule.beta) {   // cached stacked weights depend on (alpha, beta)
       for (auto& L : L_)
-        for (auto& p : L.dual)
-          if (p) { cudaFree(p); p = nullptr; }
+        for (int d = 0; d < 4; ++d) L.dual_stale[d] = L.dual[d] != nullptr;
       if (w0_last_a_) { cudaFree(w0_last_a_); w0_last_a_ = nullptr; }
       if (w0_last_b_) { cudaFree(w0_last_b_); w0_last_b_ = nullptr; }
       dual_alpha_ = rule.alpha;

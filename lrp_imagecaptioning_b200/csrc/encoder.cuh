@@ -108,6 +108,8 @@ class Encoder {
     float* w_hwio = nullptr;  // device fp32 [3,3,cin,cout]
     float* bias = nullptr;    // device fp32 [cout]
     void* prepared[8][3] = {};  // [WeightFormat][WeightSign]
+    bool stale[8][3] = {};      // allocation kept, contents older than w_hwio (set_weights_device): re-laid on next use
+    bool dual_stale[4] = {};
     int wpow = 0;             // half-plane forward: weights are stored as 2^wpow * w (keeps the low plane out of the subnormals)
     void* dual[4] = {};         // beta != 0: [alpha W+ ; -beta W-] stacked along K, {fp32 SIMT, split-bf16 TC, half-plane TC, fp16 + fp8 TC} backward layouts
   };

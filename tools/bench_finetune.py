@@ -15,6 +15,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--kind", default="adaptive")
 ap.add_argument("--vocab", type=int, default=10000)
+ap.add_argument("--breakdown", action="store_true", help="also time the phases of one step (synchronising between them)")
 args = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -64,10 +65,29 @@ if world > 1:
     t = torch.tensor([dt], device="cuda:%d" % lr)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
+breakdown = None
+if args.breakdown:
+    import types
+    ph = {}
+
+    def timed(name, fn):
+        torch.cuda.synchronize(); t = time.time(); r = fn(); torch.cuda.synchronize(); ph[name] = ph.get(name, 0.0) + time.time() - t
+        return r
+    eng = tr.layer._engine
+    imgs = imgs_host.to("cuda:%d" % lr)
+    timed("sync_engine (device-to-device weights, re-derived layouts)", lambda: tr.net.sync_engine(eng))
+    pred = timed("predict (encoder forward + teacher-forced decoder)", lambda: tr.predict(tok_in, imgs))
+    sw = timed("sparse_weights (decoder + encoder relevance of every predicted word)", lambda: tr.layer.sparse_weights(imgs, pred, features_ready=True))
+    tok = torch.as_tensor(tok_in, device=imgs.device).long()
+    logits = timed("torch forward (differentiable model pass)", lambda: tr.net(tok, imgs))
+    timed("torch backward", lambda: logits.float().sum().backward())
+    breakdown = {k: round(v, 4) for k, v in ph.items()}
 if rank == 0:
     out = {"kind": args.kind, "batch_per_gpu": args.batch, "gpus": world, "vocab": args.vocab, "s_per_step": dt,
            "steps_per_s": 1.0 / dt, "explained_words_per_step_per_gpu": words / args.steps,
            "explained_words_per_s_all_gpus": world * words / args.steps / dt, "loss": loss}
+    if breakdown:
+        out["phases_s"] = breakdown
     print(json.dumps(out))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/bench_finetune.json", "w"), indent=1)

@@ -445,10 +445,10 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
   float sc = 1.f;        // SC: accumulator -> stored message (undoes the weight pre-scale, moves to the new item scale)
   unsigned tmax = 0u;    // SC: float bits of the largest |stored value| this thread wrote
   if (SC) {
-    const int kin = __ldg(e.kt_in + item);                              // the whole tile belongs to one item
+    const int kin = __ldg(e.kt_in + item);                              // per thread: `item` is in range even when !valid
     const int d = e.out_planar_f32 ? -kin : msg_rescale_exp(__ldg(e.mx_in + item), e.target_exp);
     sc = e.acc_scale * pow2i(d < -100 ? -100 : (d > 100 ? 100 : d));
-    if (e.kt_out && (threadIdx.x & 31) == 0) e.kt_out[item] = kin + d;
+    if (e.kt_out && valid) e.kt_out[item] = kin + d;   // every lane of the item writes the same value (a warp can span several items)
   }
   for (int pass = 0; pass < (e.Gin2 ? 2 : 1); ++pass) {
     const float* G = pass ? e.Gin2 : e.Gin;
@@ -512,8 +512,10 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
   }
   if (SC) {
     __syncwarp();
-    tmax = __reduce_max_sync(0xffffffffu, tmax);
-    if (e.mx_out && (threadIdx.x & 31) == 0 && tmax) atomicMax(e.mx_out + item, tmax);
+    // one atomic per item and warp: the lanes of a warp can belong to several items (multi-item tiles of tc_conv.cu)
+    const unsigned peers = __match_any_sync(0xffffffffu, item);
+    tmax = __reduce_max_sync(peers, tmax);
+    if (e.mx_out && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1) && tmax) atomicMax(e.mx_out + item, tmax);
   }
 }
 

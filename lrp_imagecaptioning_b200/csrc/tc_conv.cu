@@ -29,7 +29,7 @@ using namespace tcptx;
 constexpr int kATileBytes = 128 * 128;            // 128 rows x 128 B
 
 struct Geom {
-  int H, W, TW, TH, tiles_x, tiles_y, cblocks, taps, Nout, n_items, n_tiles_n, group;   // group: k-steps per accumulator hand-over
+  int H, W, TW, TH, TI, tiles_x, tiles_y, cblocks, taps, Nout, n_items, n_tiles_n, group;   // TI: items per tile; group: k-steps per accumulator hand-over
 };
 
 // NS = number of bf16 planes per operand: 2 -> products (0,0)(0,1)(1,0); 3 -> additionally (0,2)(2,0)(1,1).
@@ -66,9 +66,10 @@ __device__ __forceinline__ TileCoord tile_coord(const Geom& g, int tile, int BN)
   TileCoord t;
   const int n_tile = tile % g.n_tiles_n;
   int m = tile / g.n_tiles_n;
-  const int tiles_per_item = g.tiles_x * g.tiles_y;
-  t.item = m / tiles_per_item;
-  m -= t.item * tiles_per_item;
+  const int tiles_per_item = g.tiles_x * g.tiles_y;   // per group of TI items
+  const int grp = m / tiles_per_item;
+  t.item = grp * g.TI;                                // first item of the tile
+  m -= grp * tiles_per_item;
   t.x0 = (m % g.tiles_x) * g.TW;
   t.y0 = (m / g.tiles_x) * g.TH;
   t.n0 = n_tile * BN;
@@ -81,9 +82,10 @@ __device__ __forceinline__ TileCoord tile_coord_pair(const Geom& g, int q, int B
   TileCoord t;
   const int n_tile = q % g.n_tiles_n;
   int m = 2 * (q / g.n_tiles_n) + rank;
-  const int tiles_per_item = g.tiles_x * g.tiles_y;
-  t.item = m / tiles_per_item;
-  m -= t.item * tiles_per_item;
+  const int tiles_per_item = g.tiles_x * g.tiles_y;   // per group of TI items
+  const int grp = m / tiles_per_item;
+  t.item = grp * g.TI;                                // first item of the tile
+  m -= grp * tiles_per_item;
   t.x0 = (m % g.tiles_x) * g.TW;
   t.y0 = (m / g.tiles_x) * g.TH;
   t.n0 = n_tile * BN;
@@ -154,7 +156,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_k = g.taps * g.cblocks;
-  const uint32_t stage_tx = (uint32_t)AP * (uint32_t)(g.TW * g.TH) * 128u + (uint32_t)NS * (uint32_t)C::kBTileBytes;
+  const uint32_t stage_tx = (uint32_t)AP * (uint32_t)(g.TW * g.TH * g.TI) * 128u + (uint32_t)NS * (uint32_t)C::kBTileBytes;
 
   if (warp < kEpiWarp0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
   if (warp == 0) {
@@ -275,9 +277,13 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     const int q = warp & 3;
     const int half = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
-    const int ty = r / g.TW;
-    const int tx = r - ty * g.TW;
-    const bool row_ok = r < g.TW * g.TH;
+    // accumulator row r = pixel (ti, ty, tx) of the tile: TI items x TH rows x TW pixels (TI > 1 on the 14 / 28 / 56-wide maps,
+    // where one item's rows fill only 98 or 112 of the 128 MMA rows: 14 pixels x 1 row x 9 items fill 126)
+    const int ti = r / (g.TW * g.TH);
+    const int rr = r - ti * (g.TW * g.TH);
+    const int ty = rr / g.TW;
+    const int tx = rr - ty * g.TW;
+    const bool row_ok = r < g.TW * g.TH * g.TI;
     uint32_t tl = 0;
     constexpr int kChunks = BN / 16 / (kEpiWarps / 4);   // 16-column chunks owned by this warp
     auto release_acc = [&](uint32_t buf) {   // this warp has drained accumulator buffer `buf`
@@ -289,7 +295,8 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord tc = coord(tile);
       const int y = tc.y0 + ty, x = tc.x0 + tx;
-      const bool valid = row_ok && (y < g.H) && (x < g.W);
+      const bool valid = row_ok && (y < g.H) && (x < g.W) && (tc.item + ti < g.n_items);
+      const int item = (tc.item + ti < g.n_items) ? tc.item + ti : g.n_items - 1;   // clamped: per-item tables are read unguarded
       if constexpr (PROMO) {
         // promotion: sum the per-group partial accumulators in registers (IEEE fp32 adds); tensor-core accumulation
         // drops low bits on every accumulate, which over hundreds of MMAs costs ~1e-5 relative
@@ -301,7 +308,7 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         if (MODE == EPI_BWD && row_ok) {   // multipliers of this tile -> L2 while its MMAs run
           if (y < g.H && x < g.W)
             for (int c = half; c < BN / 16; c += kEpiWarps / 4)
-              epi_prefetch_bwd(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16);
+              epi_prefetch_bwd(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + c * 16);
         }
         for (int kk0 = 0; kk0 < num_k; kk0 += g.group, ++tl) {
           const uint32_t buf = tl & 1u;
@@ -348,13 +355,13 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
             for (int i = 0; i < 16; ++i) v[i] = acc[c][i];
           };
           if (e.up == 2)
-            epi_bwd_chunks<2, kChunks, ST, false>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+            epi_bwd_chunks<2, kChunks, ST, false>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
           else
-            epi_bwd_chunks<1, kChunks, ST, false>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+            epi_bwd_chunks<1, kChunks, ST, false>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
         } else if (valid) {
 #pragma unroll
           for (int ci = 0; ci < kChunks; ++ci)
-            epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + (half + ci * (kEpiWarps / 4)) * 16, acc[ci]);
+            epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + (half + ci * (kEpiWarps / 4)) * 16, acc[ci]);
         }
         __syncwarp();
       } else {
@@ -362,9 +369,9 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
         if (MODE == EPI_BWD && row_ok) {   // multipliers of the NEXT tile (and of the first one) -> L2, a tile period ahead
           for (int pt = (tl == 0 ? tile : tile + tile_step); pt <= tile + tile_step && pt < total_tiles; pt += tile_step) {
             const TileCoord nt = coord(pt);
-            if (nt.y0 + ty < g.H && nt.x0 + tx < g.W)
+            if (nt.y0 + ty < g.H && nt.x0 + tx < g.W && nt.item + ti < g.n_items)
               for (int c = half; c < BN / 16; c += kEpiWarps / 4)
-                epi_prefetch_bwd(e, g.H, g.W, g.Nout, nt.item, nt.y0 + ty, nt.x0 + tx, nt.n0 + c * 16);
+                epi_prefetch_bwd(e, g.H, g.W, g.Nout, nt.item + ti, nt.y0 + ty, nt.x0 + tx, nt.n0 + c * 16);
           }
         }
         mbar_wait(&tfull_bar[buf], (tl >> 1) & 1u);
@@ -384,16 +391,16 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           constexpr int kStep = kEpiWarps / 4;
           auto load_acc = [&](int c, float (&v)[16]) { ld_chunk((uint32_t)((half + c * kStep) * 16), v); };
           if (e.up == 2)
-            epi_bwd_chunks<2, kChunks, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+            epi_bwd_chunks<2, kChunks, ST>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
           else
-            epi_bwd_chunks<1, kChunks, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
+            epi_bwd_chunks<1, kChunks, ST>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
         } else {
 #pragma unroll 1
           for (int c = half; c < BN / 16; c += kEpiWarps / 4) {
             float v[16];
             __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
             ld_chunk((uint32_t)(c * 16), v);
-            if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, tc.item, y, x, tc.n0 + c * 16, v);
+            if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + c * 16, v);
           }
         }
         tc_fence_before();
@@ -432,12 +439,12 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int TW, int TH) {
+int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int TW, int TH, int TI) {
   EncodeTiledFn fn = get_encode_fn();
   LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_items};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TI};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -446,12 +453,12 @@ int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, in
   return kOk;
 }
 
-int make_map_act_u8(CUtensorMap* m, const void* base, int n_items, int H, int W, int Cb, int TW, int TH) {
+int make_map_act_u8(CUtensorMap* m, const void* base, int n_items, int H, int W, int Cb, int TW, int TH, int TI) {
   EncodeTiledFn fn = get_encode_fn();
   LRPCAP_REQUIRE(fn != nullptr, kErrCuda, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[4] = {(cuuint64_t)Cb, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_items};
   cuuint64_t strides[3] = {(cuuint64_t)Cb, (cuuint64_t)W * Cb, (cuuint64_t)H * W * Cb};
-  cuuint32_t box[4] = {128, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t box[4] = {128, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TI};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -510,7 +517,7 @@ int launch_t(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t stream
   using C = Cfg<BN, NS, A1 ? 1 : NS>;
   static int smem_state[kMaxDevices] = {};
   LRPCAP_CUDA(ensure_dynamic_smem(tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1, F8>, C::kSmemBytes, smem_state));
-  const long long tiles = (long long)g.n_items * g.tiles_x * g.tiles_y * g.n_tiles_n;
+  const long long tiles = (long long)ceil_div(g.n_items, g.TI) * g.tiles_x * g.tiles_y * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles > 0 && tiles < (1ll << 31), kErrShape, "tc_conv: %lld tiles out of range", tiles);
   const int num_sms = device_sm_count();
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);   // persistent: one CTA per SM
@@ -526,7 +533,7 @@ int launch_pair(const Maps& tm, const Geom& g, const EpiDev& e, cudaStream_t str
   auto kern = tc_conv_kernel<BN, MODE, NS, PROMO, F16, A1, F8, true>;
   static int smem_state[kMaxDevices] = {};
   LRPCAP_CUDA(ensure_dynamic_smem(kern, C::kSmemBytes, smem_state));
-  const long long tiles_m = (long long)g.n_items * g.tiles_x * g.tiles_y;
+  const long long tiles_m = (long long)ceil_div(g.n_items, g.TI) * g.tiles_x * g.tiles_y;
   const long long pair_tiles = tiles_m / 2 * g.n_tiles_n;
   LRPCAP_REQUIRE(tiles_m % 2 == 0 && pair_tiles > 0 && pair_tiles < (1ll << 30), kErrShape, "tc_conv: %lld pixel tiles do not pair up", tiles_m);
   const int pairs_max = device_sm_count() / 2;
@@ -641,23 +648,36 @@ int launch_mode(int mode, int planes, const Maps& tm, const Geom& g, const EpiDe
 
 }  // namespace
 
-void tc_conv_tile(int H, int W, int* TW, int* TH) {
-  if (W >= 16 && W % 16 == 0 && H >= 8) {
+// Tile of <= 128 accumulator rows: TW x TH pixels of TI consecutive items. Maps whose width is a multiple of 16 take 16 x 8;
+// other widths up to 128 take the (TW | W, TH | H, TI) with the most MMA rows in use -- the 14 / 28 / 56-wide VGG maps
+// tile as 14 x 1 x 9 items = 126 rows instead of 98 / 112 rows of one item (launches on those maps are tensor-bound).
+void tc_conv_tile(int H, int W, int n_items, int* TW, int* TH, int* TI) {
+  *TI = 1;
+  if ((W >= 16 && W % 16 == 0 && H >= 8) || W > 128) {
     *TW = 16;
     *TH = 8;
     return;
   }
-  if (W <= 128) {
-    int max_th = 128 / W;
-    if (max_th > H) max_th = H;
-    int th = max_th;
-    while (th > 1 && H % th != 0) --th;
-    *TW = W;
-    *TH = th;
-    return;
+  long long best_rows = -1;
+  int bw = W, bh = 1, bi = 1;
+  for (int tw = W; tw >= 1; --tw) {
+    if (W % tw != 0 || tw > 128) continue;
+    if (tw < 7 && tw != W) continue;             // short row segments waste TMA requests
+    for (int th = 1; th <= H && tw * th <= 128; ++th) {
+      if (H % th != 0) continue;
+      for (int ti = 1; ti <= n_items && ti <= 32 && tw * th * ti <= 128; ++ti) {
+        const long long tiles = (long long)((n_items + ti - 1) / ti) * (H / th) * (W / tw);
+        // fewest tiles wins; ties: fewer items per tile, then wider tiles (loops run wide -> narrow, 1 -> many)
+        if (best_rows < 0 || tiles < best_rows) {
+          best_rows = tiles;
+          bw = tw; bh = th; bi = ti;
+        }
+      }
+    }
   }
-  *TW = 16;
-  *TH = 8;
+  *TW = bw;
+  *TH = bh;
+  *TI = bi;
 }
 
 int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
@@ -677,9 +697,10 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   Geom g;
   g.H = a.H;
   g.W = a.W;
-  tc_conv_tile(a.H, a.W, &g.TW, &g.TH);
+  tc_conv_tile(a.H, a.W, a.n_items, &g.TW, &g.TH, &g.TI);
   g.tiles_x = ceil_div(a.W, g.TW);
   g.tiles_y = ceil_div(a.H, g.TH);
+  const long long tiles_m_all = (long long)ceil_div(a.n_items, g.TI) * g.tiles_x * g.tiles_y;   // pixel tiles of the launch
   g.cblocks = a.C / kBlockK;
   g.taps = a.taps;
   g.Nout = a.Nout;
@@ -692,7 +713,7 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   const __nv_bfloat16* B0 = reinterpret_cast<const __nv_bfloat16*>(a.B);
   // CTA pairs for the N >= 128 backward launches whose pixel tiles pair up (every full chunk of the encoder chain)
   const bool pair = BN >= 128 && tc_pair_enabled() && (a.planes == 2 || a.planes == kPlanesH1x2 || a.planes == kPlanesH1F8) &&
-                    (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW) && ((long long)a.n_items * g.tiles_x * g.tiles_y) % 2 == 0;
+                    (a.epi.mode == EPI_BWD || a.epi.mode == EPI_RAW) && tiles_m_all % 2 == 0;
   const int brows = pair ? BN / 2 : BN;   // B rows staged per CTA
   Maps tm;
   const int n_planes = a.planes == 3 ? 3 : 2;
@@ -700,8 +721,8 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   if (a.planes == kPlanesH1F8) {   // plane 0: fp16 [.., C]; plane 1: bytes [.., 2 C] right behind it (both 2 B per element)
     const uint8_t* A8 = reinterpret_cast<const uint8_t*>(A0) + a.A_elems * 2;
     const uint8_t* B8 = reinterpret_cast<const uint8_t*>(B0) + a.B_elems * 2;
-    LRPCAP_TRY(make_map_act(&tm.a[0], A0, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
-    LRPCAP_TRY(make_map_act_u8(&tm.a[1], A8, a.n_items, a.H, a.W, 2 * a.C, g.TW, g.TH));
+    LRPCAP_TRY(make_map_act(&tm.a[0], A0, a.n_items, a.H, a.W, a.C, g.TW, g.TH, g.TI));
+    LRPCAP_TRY(make_map_act_u8(&tm.a[1], A8, a.n_items, a.H, a.W, 2 * a.C, g.TW, g.TH, g.TI));
     LRPCAP_TRY(make_map_w(&tm.b[0], B0, a.taps * a.Nout, a.C, brows));
     LRPCAP_TRY(make_map_w_u8(&tm.b[1], B8, a.taps * a.Nout, 2 * a.C, brows));
     tm.a[2] = tm.a[0];
@@ -709,7 +730,7 @@ int tc_conv_launch(const TcConvArgs& a, cudaStream_t stream) {
   } else
   for (int pl = 0; pl < 3; ++pl) {
     const int q = pl < n_planes ? pl : 0;   // unused third slot aliases plane 0
-    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(q < a_planes ? q : 0) * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH));
+    LRPCAP_TRY(make_map_act(&tm.a[pl], A0 + (size_t)(q < a_planes ? q : 0) * a.A_elems, a.n_items, a.H, a.W, a.C, g.TW, g.TH, g.TI));
     LRPCAP_TRY(make_map_w(&tm.b[pl], B0 + (size_t)q * a.B_elems, a.taps * a.Nout, a.C, brows));
   }
 

@@ -97,6 +97,6 @@ struct SimtConvArgs {
 int simt_conv_launch(const SimtConvArgs& args, cudaStream_t stream);
 
 // Tile geometry used for a given map size (exposed for tests / docs).
-void tc_conv_tile(int H, int W, int* TW, int* TH);
+void tc_conv_tile(int H, int W, int n_items, int* TW, int* TH, int* TI);
 
 }  // namespace lrpcap

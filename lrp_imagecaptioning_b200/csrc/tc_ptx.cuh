@@ -305,10 +305,10 @@ __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, fl
 
 // TMA descriptors (defined in tc_conv.cu). Activations: bf16 [n_items, H, W, C] read as boxes {64 ch, box_w, box_h, 1},
 // 128B-swizzled, OOB zero-filled.  Weights: bf16 [rows, C] read as boxes {64 ch, box_rows}.
-int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int box_w, int box_h);
+int make_map_act(CUtensorMap* m, const void* base, int n_items, int H, int W, int C, int box_w, int box_h, int box_items = 1);
 int make_map_w(CUtensorMap* m, const void* base, int rows, int C, int box_rows);
 // Byte tensors (E4M3 planes of the fp16 + fp8 mode): rows of `Cb` bytes, boxes of 128 bytes along the row.
-int make_map_act_u8(CUtensorMap* m, const void* base, int n_items, int H, int W, int Cb, int box_w, int box_h);
+int make_map_act_u8(CUtensorMap* m, const void* base, int n_items, int H, int W, int Cb, int box_w, int box_h, int box_items = 1);
 int make_map_w_u8(CUtensorMap* m, const void* base, int rows, int Cb, int box_rows);
 // Channel-planar fp32 message [n_planes][H][W] (EpiParams::out_planar_f32) read as boxes {box_w, box_h, box_c}, OOB zero-filled.
 int make_map_planar_f32(CUtensorMap* m, const void* base, int n_planes, int H, int W, int box_w, int box_h, int box_c);

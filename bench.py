@@ -351,6 +351,9 @@ def run_ours(args, rank, local_rank, world):
                 "backward_arithmetic": mode,
                 "products_per_mac": products,
                 "tensor_pipe_frac": products * achieved / peak_tf if peak_tf else None,
+                "tensor_pipe_frac_note": "product-equivalents / measured cuBLAS bf16 peak; it can pass 1.0: the sustained cuBLAS figure is "
+                                         "itself taken under the power cap, and in the h1f8 mode half of the product-equivalents are "
+                                         "kind::f8f6f4 MMAs that run at twice the bf16 rate",
                 "kernel_ms_per_step": tc_ms, "kernel_launches_per_step": tc_n,
                 "share_of_step": tc_ms / ms if ms > 0 else None,
                 "forward_tc_ms_per_step": prof["tc_fwd"][0], "last_dgrad_ms_per_step": prof["last"][0]}

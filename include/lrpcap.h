@@ -243,10 +243,14 @@ int lrpcap_encoder_debug_multiplier(lrpcap_encoder_t* enc, int layer, int branch
  * word (row `layers`: the seed's true maximum); h_kt [layers][*chunk]: log2 of that message's scale. cap_words: room (in
  * words) of both arrays; *chunk = words of that chunk, 0 when the handle does not run the two-product path. */
 int lrpcap_encoder_debug_message_scales(lrpcap_encoder_t* enc, float* h_max, int* h_kt, int cap_words, int* chunk);
+/* Host-only: the accumulator tile the generic tcgen05 kernel uses for a [items, H, W] map: tile_w x tile_h pixels of
+ * tile_items consecutive items (<= 128 rows). No device work; unit tests of the tile chooser. */
+int lrpcap_debug_conv_tile(int items, int H, int W, int* tile_w, int* tile_h, int* tile_items);
 /* Single convolution through one implementation, raw accumulator out (unit tests of the GEMM kernels).
  * precision: LRPCAP_PREC_FP32_SIMT; LRPCAP_PREC_BF16X3_TC (two bf16 planes: the backward arithmetic); 2 = three bf16
  * planes, promoted; 3 = two IEEE half planes, promoted (the forward arithmetic); 4 = the two-product backward arithmetic
- * (A rounded to one fp16 plane x two fp16 weight planes); 5 = the fp16 + fp8 backward arithmetic.
+ * (A rounded to one fp16 plane x two fp16 weight planes); 5 = the fp16 + fp8 backward arithmetic. The environment
+ * variable LRPCAP_DEBUG_CONV_PROMOTE=<k-steps> selects the promoted kernels (tests).
  * h_A [items, H, W, C]; h_B [taps][C][Nout] (HWIO for taps = 9); h_out [items, H, W, Nout]. */
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out);

@@ -72,6 +72,7 @@ PROTOTYPES = {
     "lrpcap_encoder_debug_pool_routes": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p]),
     "lrpcap_encoder_debug_multiplier": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_float_p]),
     "lrpcap_encoder_debug_message_scales": (ctypes.c_int, [c_void_p, c_float_p, c_int_p, ctypes.c_int, c_int_p]),
+    "lrpcap_debug_conv_tile": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
     "lrpcap_debug_conv": (ctypes.c_int, [ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_float_p, ctypes.c_int, ctypes.c_int, c_float_p]),
 }
 
@@ -113,6 +114,14 @@ def iptr(a):
 def dptr(a):
     assert isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(c_double_p)
+
+
+def debug_conv_tile(items, H, W):
+    """(tile_w, tile_h, tile_items) of the generic tcgen05 kernel for an [items, H, W] map (host-only call)."""
+    lib = load()
+    tw, th, ti = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib.lrpcap_debug_conv_tile(int(items), int(H), int(W), ctypes.byref(tw), ctypes.byref(th), ctypes.byref(ti)))
+    return tw.value, th.value, ti.value
 
 
 def debug_conv(precision, A, B, taps):

@@ -157,6 +157,13 @@ int lrpcap_encoder_debug_message_scales(lrpcap_encoder_t* enc, float* h_max, int
   return enc->impl->debug_message_scales(h_max, h_kt, cap_words, chunk);
 }
 
+int lrpcap_debug_conv_tile(int items, int H, int W, int* tile_w, int* tile_h, int* tile_items) {
+  LRPCAP_REQUIRE(tile_w && tile_h && tile_items, kErrInvalidArg, "debug_conv_tile: null argument");
+  LRPCAP_REQUIRE(items > 0 && H > 0 && W > 0, kErrShape, "debug_conv_tile: bad shape");
+  tc_conv_tile(H, W, items, tile_w, tile_h, tile_items);
+  return kOk;
+}
+
 int lrpcap_debug_conv(int precision, const float* h_A, int items, int H, int W, int C, const float* h_B, int taps,
                       int Nout, float* h_out) {
   LRPCAP_REQUIRE(h_A && h_B && h_out, kErrInvalidArg, "debug_conv: null argument");

@@ -185,3 +185,29 @@ def test_keras_hdf5_reader_renames_datasets(monkeypatch, tmp_path):
     monkeypatch.setitem(sys.modules, "h5py", None)                              # import h5py -> ImportError
     with pytest.raises(ImportError):
         keras_io.read_keras_hdf5("keras_model.hdf5")
+
+
+def test_conv_tile_chooser():
+    """The accumulator tile of the generic tcgen05 kernel (csrc/tc_conv.cu: tc_conv_tile; host-only ABI call): at most 128
+    rows, divides the map, and on the 14 / 28 / 56-wide VGG maps spans 9 or 16 words (126 / 128 rows instead of 98 / 112)."""
+    from lrp_imagecaptioning_b200 import _lib
+    for n in (1, 2, 5, 9, 20, 64, 320):
+        for hw in (1, 2, 4, 7, 8, 14, 16, 28, 56, 112, 224):
+            tw, th, ti = _lib.debug_conv_tile(n, hw, hw)
+            assert 1 <= tw * th * ti <= 128 and 1 <= ti <= n
+            if hw % 16 == 0 and hw >= 16:
+                assert (tw, th, ti) == (16, 8, 1)                  # 16 x 8 pixels of one item
+            else:
+                assert hw % tw == 0 and hw % th == 0               # whole tiles only (no partially filled TMA boxes)
+    assert _lib.debug_conv_tile(320, 14, 14) == (14, 1, 9)
+    assert _lib.debug_conv_tile(320, 28, 28) == (14, 1, 9)
+    assert _lib.debug_conv_tile(320, 56, 56) == (8, 1, 16)          # 56 = 7 x 8: all 128 rows
+    assert _lib.debug_conv_tile(1, 14, 14) == (14, 7, 1)            # a single item: the old one-item tile
+    assert _lib.debug_conv_tile(1, 28, 28) == (28, 4, 1)
+    # fewest tiles wins: never more tiles than the one-item choice
+    for n in (3, 20, 64, 320):
+        for hw in (14, 28, 56):
+            tw, th, ti = _lib.debug_conv_tile(n, hw, hw)
+            tw1, th1, _ = _lib.debug_conv_tile(1, hw, hw)
+            tiles = -(-n // ti) * (hw // tw) * (hw // th)
+            assert tiles <= n * (hw // tw1) * (hw // th1)

@@ -465,8 +465,8 @@ __device__ __forceinline__ void epi_bwd_chunks(const EpiDev& e, int H, int W, in
     // N = 256 kernel was 227 KB of SASS) that each warp runs once per tile, so every pass came through the instruction cache
     // cold (ncu: stall_no_inst on the epilogue's ALU instructions, tensor pipe 49 % on the three layers under a pool). The
     // pipelined form keeps two chunks per loop body (the double-buffered multiplier registers need a static index) and
-    // loops over the sub-pixels; the promoted form indexes its register accumulator by `c` and keeps its chunks unrolled.
-    constexpr int kChunkUnroll = (UP == 2 && PIPE && NCH % 2 == 0) ? 2 : NCH;
+    // loops over the sub-pixels; the promoted form (PIPE = false) is a plain loop whose loader hands out acc[0] and rotates.
+    constexpr int kChunkUnroll = !PIPE ? 1 : (UP == 2 && NCH % 2 == 0) ? 2 : NCH;   // !PIPE: the loader rotates its registers
     constexpr int kSubUnroll = 1;   // (one iteration when UP == 1)
 #pragma unroll kChunkUnroll
     for (int c = 0; c < NCH; ++c) {

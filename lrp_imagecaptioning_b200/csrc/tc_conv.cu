@@ -348,20 +348,37 @@ tc_conv_kernel(const __grid_constant__ Maps tm, const Geom g, const EpiDev e, co
           __syncwarp();
           release_acc(buf);
         }
+        // Code size: the tile-end epilogue runs once per tile and warp; unrolled over the chunks it was 110-210 KB of SASS
+        // per kernel and came through the instruction cache cold every time (the backward kernels showed the same: see
+        // epilogue.cuh). The chunk loops below are real loops: they always read acc[0] and rotate the register array.
+        auto rotate_acc = [&]() {
+          float t0[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t0[i] = acc[0][i];
+#pragma unroll
+          for (int j = 0; j + 1 < kChunks; ++j)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[j][i] = acc[j + 1][i];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[kChunks - 1][i] = t0[i];
+        };
         if constexpr (MODE == EPI_BWD) {
           constexpr int kStep = kEpiWarps / 4;
-          auto load_acc = [&](int c, float (&v)[16]) {
+          auto load_acc = [&](int, float (&v)[16]) {   // called once per chunk, in order (and once more per pass for beta != 0)
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = acc[c][i];
+            for (int i = 0; i < 16; ++i) v[i] = acc[0][i];
+            rotate_acc();
           };
           if (e.up == 2)
             epi_bwd_chunks<2, kChunks, ST, false>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
           else
             epi_bwd_chunks<1, kChunks, ST, false>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + half * 16, 16 * kStep, valid, load_acc);
-        } else if (valid) {
-#pragma unroll
-          for (int ci = 0; ci < kChunks; ++ci)
-            epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + (half + ci * (kEpiWarps / 4)) * 16, acc[ci]);
+        } else {
+#pragma unroll 1
+          for (int ci = 0; ci < kChunks; ++ci) {
+            if (valid) epi_apply<MODE, 16, ST>(e, g.H, g.W, g.Nout, item, y, x, tc.n0 + (half + ci * (kEpiWarps / 4)) * 16, acc[0]);
+            rotate_acc();
+          }
         }
         __syncwarp();
       } else {

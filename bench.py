@@ -37,7 +37,11 @@ METRIC = "explained words/sec (full LRP to pixels)"
 UNIT = "words/s"
 T_WORDS, VOCAB, HW = 20, 10000, 224
 ENC_GFLOP_PER_WORD = 30.69      # one transposed-conv sweep of VGG16
-NCU_DRAM_MB_PER_WORD = 98.2     # measured: profiles/r01c_ncu_full_bwd_summary.csv (31.4 GB over 320 words)
+# measured DRAM read + write of the 12 transposed-conv launches per word (ncu --set full, 320 words, tools/profile_encoder.py):
+# fp16 + fp8 messages 33.07 GB (profiles/r02_ncu_enc_eps_summary.csv), one fp16 plane 17.80 GB (r02_ncu_enc_preseta_summary.csv),
+# two bf16 planes 31.4 GB (r01c_ncu_full_bwd_summary.csv)
+NCU_DRAM_MB_PER_WORD = {"h1f8": (103.4, "profiles/r02_ncu_enc_eps_summary.csv", 95.1), "f16x2": (55.6, "profiles/r02_ncu_enc_preseta_summary.csv", 47.6),
+                        "bf16x3": (98.2, "profiles/r01c_ncu_full_bwd_summary.csv", 95.1), "fp32": (None, "not captured", None)}
 
 WORKLOADS = {
     # name: (decoder kind, images per GPU (weak) or total (strong), scaling, description)
@@ -340,10 +344,10 @@ def run_ours(args, rank, local_rank, world):
     achieved = (tc_flops / 1e12) / (tc_ms / 1e3) if tc_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "tc_conv_kernel / tc_conv_vh_kernel <BN, EPI_BWD> (tcgen05 transposed conv + fused rule epilogue)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": NCU_DRAM_MB_PER_WORD * 1e6 * job.n_words * job.flop_mul / max(tc_n, 1.0),
-                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (profiles/r01c_ncu_full_bwd_summary.csv, "
-                                "320 words: 31.4 GB = %.1f MB/word; algorithmic: 95.1 MB/word of messages + the per-image multipliers), "
-                                "scaled to this run's words per launch" % NCU_DRAM_MB_PER_WORD,
+                "traffic": (NCU_DRAM_MB_PER_WORD[mode][0] * 1e6 * job.n_words * job.flop_mul / max(tc_n, 1.0)) if NCU_DRAM_MB_PER_WORD[mode][0] else None,
+                "traffic_note": "dram read+write of the 12 transposed-conv launches from ncu --set full (%s, 320 words: %s MB/word; "
+                                "algorithmic: %s MB/word of messages + the per-image multipliers), scaled to this run's words per launch"
+                                % (NCU_DRAM_MB_PER_WORD[mode][1], NCU_DRAM_MB_PER_WORD[mode][0], NCU_DRAM_MB_PER_WORD[mode][2]),
                 "peak_source": "%s bf16 cuBLAS (sustained)" % peak_src,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (2*MAC of the transposed convs, %.2f GFLOP/word) / CUDA-event "
                         "kernel time of one instrumented step; every algorithmic MAC costs %d 16-bit tensor-core MAC-equivalents (%s), "

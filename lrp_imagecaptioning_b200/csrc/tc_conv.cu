@@ -6,11 +6,13 @@
 // and, with taps == 1, the dense contractions of the decoder relevance (explainers.py:156-165).
 //
 // Structure per CTA (persistent, 384 threads = one producer warpgroup + two epilogue warpgroups, tiles of 128 pixels x BN channels):
-//   warp 0 lane 0 : TMA producer. Per k-step (tap, 64-channel block) four cp.async.bulk.tensor loads
-//                   (A_hi, A_lo as 4-D boxes shifted by the tap offset -- OOB rows/cols are zero-filled,
-//                   which *is* the 'same' padding -- and B_hi, B_lo as 2-D boxes), 128B-swizzled.
-//   warp 1 lane 0 : MMA issuer. 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi; 6 with three planes) per k-step into one
-//                   of two TMEM accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem stage.
+//   warp 0        : TMA producer (the warp runs the loop converged, one elected lane issues: tc_ptx.cuh). Per k-step
+//                   (tap, 64-channel block) up to four cp.async.bulk.tensor loads (the A planes as 4-D boxes shifted by
+//                   the tap offset -- OOB rows/cols are zero-filled, which *is* the 'same' padding -- and the B planes
+//                   as 2-D boxes), 128B-swizzled.
+//   warp 1        : MMA issuer (converged, elected lane). 4 K-slices x 3 tcgen05.mma (hi*hi, hi*lo, lo*hi; 6 with three
+//                   planes; 2 in the two-product and fp16 + fp8 modes) per k-step into one of two TMEM accumulators
+//                   (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem stage.
 //   warps 2, 3    : idle (they complete the producer warpgroup, which gives most of its registers away: setmaxnreg)
 //   warps 4..11   : epilogue (overlaps the next tile's MMAs). tcgen05.ld 32x32b.x16 -> registers -> fused rule arithmetic
 //                   -> global; with PROMO the partial accumulator of every k-step group is added in fp32 registers

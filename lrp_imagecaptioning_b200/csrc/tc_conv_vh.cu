@@ -11,13 +11,14 @@
 //     8 x 18 pixels is loaded (TMA box shifted by dx, rows y0-1 .. y0+16, OOB zero-fill = 'same' padding). A patch row
 //     is 8 pixels = one swizzle group of 8 x 128 B, so the operand for tap (dy, dx) is the same patch at byte offset
 //     dy * 1024 -- a plain SWIZZLE_128B K-major descriptor. 3 patches of 18 rows replace 9 tiles of 16 rows: 2.7x less
-//     activation traffic. Patches are 36 KB ring slots (4 of them): with one 72 KB patch per dx and 2 slots the ring
-//     was shallower than the TMA latency and the tensor pipe idled 45 % of the time;
+//     activation traffic. Patches are 18 / 36 KB ring slots (one or two planes; 4 to 8 of them, vh_rings()): with one
+//     72 KB patch per dx and 2 slots the ring was shallower than the TMA latency and the tensor pipe idled 45 % of the time;
 //   * NCAT (64 output channels): the weight planes [hi ; lo] sit back to back in shared memory and are issued as ONE
 //     N = 128 operand against A_hi (accumulator columns [0,64) = hi*hi, [64,128) = hi*lo) plus one N = 64 MMA
 //     A_lo * B_hi; the epilogue adds the two column blocks. Two MMAs instead of three, and a third less
 //     shared-memory operand bandwidth, which is what bounds N = 64 MMAs.
-// Rings: activation patches (kNA slots) and weight taps (NB slots) are separate mbarrier rings fed by one TMA thread.
+// Rings: activation patches (NA slots) and weight taps (NB slots) are separate mbarrier rings fed by the TMA warp
+// (converged, one elected lane issues: tc_ptx.cuh).
 #include "epilogue.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
